@@ -1,0 +1,220 @@
+/*
+ * pangea_b200.h -- C ABI of libpangea_b200.so: the B200-native (sm_100a CUDA)
+ * classification hot path of PANGEA+.
+ *
+ * The reference has no in-process plugin API: its boundary is argv + text
+ * files + stdout + exit status.  The three drop-in
+ * executables (rdp_classifier, tax_class/taxcollector, consensus -- see
+ * pangea-plus_b200/host/) are thin main()s over the entry points below, and a
+ * maintainer binding the path from Perl/Python/cgo binds exactly these
+ * (INTEGRATION.md shows the stubs).  Each entry point cites the reference
+ * interface it replaces (paths relative to the reference root).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function
+ * returns 0 (PG_OK) or a negative PG_E* code, with text from pg_last_error();
+ * the library never writes to stdout; handles are opaque and freed by the
+ * matching *_free; one host thread per pg_ctx.  There is NO CPU fallback:
+ * without a usable CUDA device pg_init() fails (PG_ENODEV) and nothing else
+ * can be called.
+ *
+ * "host" pointers are ordinary process memory; "dev" pointers are CUDA device
+ * memory on the context's device (e.g. torch tensor .data_ptr()).
+ */
+#ifndef PANGEA_B200_H
+#define PANGEA_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK        0
+#define PG_EINVAL   -1   /* bad argument */
+#define PG_ECUDA    -2   /* CUDA runtime / launch failure */
+#define PG_ENOMEM   -3   /* host or device allocation failed */
+#define PG_EIO      -4   /* file could not be opened / read / written */
+#define PG_ENODEV   -5   /* no CUDA device: the library has no CPU path */
+#define PG_ERANGE   -6   /* input outside the supported range (e.g. read too long) */
+#define PG_EFORMAT  -7   /* malformed file */
+
+#define PG_WORDSIZE        8        /* RDP 8-mers                                  */
+#define PG_NWORDS          65536    /* 4^8                                         */
+#define PG_NUM_BOOT        100      /* NUM_OF_RUNS                                 */
+#define PG_MIN_SEQ_LEN     50       /* ShortSequenceException gate     */
+#define PG_MAX_DEPTH       32       /* lineage levels root..genus kept per result  */
+#define PG_GENUS_TILE      32       /* genera per 128-byte table row segment       */
+#define PG_MAX_WORDS       7000     /* longest read (good words) the kernels stage */
+
+typedef struct pg_ctx   pg_ctx;
+typedef struct pg_model pg_model;
+typedef struct pg_reads pg_reads;
+typedef struct pg_tax   pg_tax;
+
+/* ------------------------------------------------------------------ context */
+
+/* One context per GPU (one process per GPU under torchrun; or one per device
+ * inside a multi-device host program).  Returns NULL on failure; the reason is
+ * then available from pg_last_error(NULL). */
+pg_ctx     *pg_init(int device);
+void        pg_shutdown(pg_ctx *ctx);
+const char *pg_last_error(const pg_ctx *ctx);
+/* Launch everything on the caller's CUDA stream (cudaStream_t / CUstream, e.g.
+ * torch.cuda.current_stream().cuda_stream).  NULL = the context's own stream. */
+int         pg_set_stream(pg_ctx *ctx, void *cuda_stream);
+int         pg_sync(pg_ctx *ctx);
+/* Number of kernels this context has launched so far (bench "gpu_launches"). */
+int64_t     pg_launch_count(const pg_ctx *ctx);
+/* Milliseconds spent inside the dominant classify kernel since the last call to
+ * pg_kernel_time_reset(), measured with CUDA events on the launching stream, and
+ * how many launches that covers. */
+int         pg_kernel_time(pg_ctx *ctx, double *classify_ms, int64_t *classify_launches);
+int         pg_kernel_time_reset(pg_ctx *ctx);
+
+/* ------------------------------------------------------------------ Stage A
+ * Replaces: `java -Xmx1g -jar rdp_classifier-2.5.jar -q <in.fa> -o <out.txt>`
+ * (README.md:119-122; installer Classify/RunRDP/install_RDPClassifier.sh:60-66).
+ * Semantics: SURVEY.md section 8(a) rows A1-A9.
+ */
+
+/* A batch of sequences: `count` records, record i = bytes[off[i] .. off[i+1]),
+ * raw FASTA residue characters (any case, IUPAC allowed, no newlines). */
+typedef struct {
+    const char    *bytes;
+    const int64_t *off;      /* count+1 entries */
+    int64_t        count;
+} pg_seqbatch;
+
+/* One classified read, 64 bytes (A7-A9). */
+typedef struct {
+    int32_t genus;                    /* genus index of the assignment; -1 if status!=0 */
+    int32_t n_words;                  /* good 8-mers used (after orientation)           */
+    float   score;                    /* A7: sequential fp32 sum of the winner          */
+    uint8_t reversed;                 /* A3: 1 if the read was reverse-complemented     */
+    uint8_t status;                   /* 0 ok; 1 = shorter than PG_MIN_SEQ_LEN (A2)     */
+    uint8_t depth;                    /* lineage levels of the genus (root first)       */
+    uint8_t _pad0;
+    uint8_t votes[PG_MAX_DEPTH];      /* A9: bootstrap votes (0..100) per lineage level */
+    uint8_t _pad1[16];
+} pg_result;
+
+/* A5+A6 training (upstream RawHierarchyTree.initWordOccurrence /
+ * TreeFactory.createGenusWordConditionalProb): integer-atomic word x genus
+ * counts, then the genus-tiled fp32 log table.  genus_of_seq[i] in [0,G).
+ * Host buffers in; the model lives on the context's device. */
+int pg_train(pg_ctx *ctx, const pg_seqbatch *seqs_host, const int32_t *genus_of_seq_host,
+             int G, pg_model **out);
+/* Same with all three arrays already resident in device memory. */
+int pg_train_dev(pg_ctx *ctx, const pg_seqbatch *seqs_dev, const int32_t *genus_of_seq_dev,
+                 int G, pg_model **out);
+void pg_model_free(pg_model *m);
+
+/* Lineage of every genus for the A9 vote: anc[g*depth + d] = taxonomy node id
+ * at level d (root first), -1 beyond the genus' own level.  depth <= PG_MAX_DEPTH.
+ * Without it every genus has the one-level lineage {g}. */
+int pg_model_set_lineage(pg_model *m, const int32_t *anc_host, int depth);
+
+int     pg_model_genera(const pg_model *m);
+int64_t pg_model_sequences(const pg_model *m);
+
+/* Parity hooks (host outputs, any may be NULL): m_wg[w*G+g], n_w[65536], M_g[G], N. */
+int pg_model_counts(const pg_model *m, int32_t *m_wg, int32_t *n_w, int32_t *M_g, int64_t *N);
+/* logPrior[65536], logLeave[G], logP[w*G+g] (dense, word-major). */
+int pg_model_tables(const pg_model *m, float *logPrior, float *logLeave, float *logP);
+
+/* Model persistence (sparse counts; tables are re-derived on load, on the GPU).
+ * `blob` is an opaque caller section (the CLI keeps the taxonomy names there). */
+int pg_model_save(const pg_model *m, const char *path, const void *blob, int64_t blob_len);
+int pg_model_load(pg_ctx *ctx, const char *path, pg_model **out, void **blob, int64_t *blob_len);
+void pg_free(void *p);
+
+/* Multi-GPU replication: the device buffers that define a model, for an
+ * external broadcast (torch.distributed / ncclBroadcast).  A receiving rank
+ * creates an empty model of the same G, broadcasts into its buffers, then
+ * calls pg_model_commit().  names: "counts_m","counts_n","counts_M","N". */
+int pg_model_create(pg_ctx *ctx, int G, pg_model **out);
+int pg_model_buffers(pg_model *m, void **dev_ptrs, size_t *nbytes, int max, int *n);
+int pg_model_commit(pg_model *m);     /* re-derive tables from the counts */
+
+/* K3: 2-bit packing.  Packs a batch into the compact device read store. */
+int  pg_reads_pack(pg_ctx *ctx, const pg_seqbatch *seqs_host, pg_reads **out);
+int  pg_reads_pack_dev(pg_ctx *ctx, const pg_seqbatch *seqs_dev, int64_t total_bytes, pg_reads **out);
+void pg_reads_free(pg_reads *r);
+int64_t pg_reads_count(const pg_reads *r);
+/* Parity hook: 2-bit codes (16 bases per uint32, base i at bits 2*(i%16)) and the
+ * validity mask (32 bases per uint32) of read i; returns its length. */
+int64_t pg_reads_unpack(const pg_reads *r, int64_t i, uint32_t *codes, uint32_t *mask, int64_t cap_words);
+
+/* Options for classification. */
+typedef struct {
+    int32_t min_boot_words;   /* 0 = RDP 2.5 (k = n/8); later releases use 5            */
+    int32_t mode;             /* 0 = strict (reference order);
+                                 1 = certified (quantised pre-filter, strict re-check)  */
+    int32_t reserved[6];
+} pg_classify_opts;
+
+/* K3-K5: word extraction + orientation, gather-sum + 100 bootstraps, argmax,
+ * vote.  results: nreads records (host for pg_classify, device for *_dev).
+ * boot_winners (optional, may be NULL): nreads*100 int32 genus index per
+ * replicate, parity hook for row A8. */
+int pg_classify(pg_ctx *ctx, const pg_model *m, const pg_seqbatch *reads_host,
+                const pg_classify_opts *opts, pg_result *results_host, int32_t *boot_winners_host);
+int pg_classify_packed(pg_ctx *ctx, const pg_model *m, const pg_reads *reads,
+                       const pg_classify_opts *opts, pg_result *results_dev, int32_t *boot_winners_dev);
+
+/* Parity hook for A1/A3: the word list the classifier uses for each read
+ * (after orientation).  words_host[off[i] + j], n_words_host[i], reversed_host[i]. */
+int pg_extract_words(pg_ctx *ctx, const pg_model *m, const pg_seqbatch *reads_host,
+                     uint16_t *words_host, int32_t *n_words_host, uint8_t *reversed_host);
+/* Parity hook for A8: the java.util.Random(1) sample list for a read of n words:
+ * out[run*k + j], k = max(n/8, min_boot_words).  Computed on the device. */
+int pg_boot_indices(pg_ctx *ctx, int32_t n, int32_t min_boot_words, uint16_t *out_host);
+
+/* ------------------------------------------------------------------ Stage B
+ * Replaces: Tax_class/ncbitc.c (`tax_class -c|-s|-g|-t|-n`, main at :841-1004)
+ * and the per-hit walk of Tax_class/NCBI-taxcollector-0.01.pl:58-300.
+ */
+
+/* == `tax_class -c` (ncbitc.c:995-998): builds gi_taxid_nucl.dmp.bin,
+ * nodes.dmp.bin, names.dmp.bin in `dir` with the reference's record layouts
+ * (ncbitc.c:98-140), so the files are interchangeable. */
+int pg_tax_build(const char *dir);
+/* Loads the three .bin files and uploads the lookup arrays. */
+int pg_tax_load(pg_ctx *ctx, const char *dir, pg_tax **out);
+void pg_tax_free(pg_tax *t);
+
+/* Batched gi -> leaf taxid (ncbitc_search_tax_id :567-599; 0 = unknown). */
+int pg_tax_leaf(pg_ctx *ctx, const pg_tax *t, const int32_t *gi_host, int64_t n, int32_t *taxid_host);
+/* Batched lineage strings exactly as taxcollector prints them between the first
+ * and second TAB (rows B5-B7): out_bytes is a caller buffer of out_cap bytes,
+ * out_off gets n+1 offsets.  Returns PG_ERANGE if out_cap is too small (needed
+ * size in out_off[n]). */
+int pg_tax_lineage(pg_ctx *ctx, const pg_tax *t, const int32_t *gi_host, int64_t n,
+                   char *out_bytes, int64_t out_cap, int64_t *out_off);
+
+/* ------------------------------------------------------------------ Stage C
+ * Replaces: Consensus/Consensus_BLAST_SOAP_RDP-1.1.pl:96-237 (rows C2-C8).
+ */
+
+/* hits: BLAST-class lines grouped by read (CSR hit_off over reads);
+ * per hit the lineage field and the pident field as text; per read the RDP
+ * triples as text.  winner[i] = index (into the hit arrays) of the line the
+ * reference would print for read i, nmatch[i] = its "#Matches found". */
+typedef struct {
+    int64_t        nreads;
+    const int64_t *hit_off;        /* nreads+1 */
+    const char    *lineage_bytes;  /* concatenated lineage fields           */
+    const int64_t *lineage_off;    /* nhits+1                               */
+    const char    *pident_bytes;   /* concatenated third-column fields      */
+    const int64_t *pident_off;     /* nhits+1                               */
+    const char    *rdp_bytes;      /* per read: text after the five TABs    */
+    const int64_t *rdp_off;        /* nreads+1                              */
+} pg_consensus_in;
+
+int pg_consensus(pg_ctx *ctx, const pg_consensus_in *in_host, int64_t *winner_host, int32_t *nmatch_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANGEA_B200_H */

@@ -1,0 +1,548 @@
+// pg_classify.cu -- K4/K5: gather-sum, 100 bootstraps, argmax, vote
+// (SURVEY.md 8(a) rows A4, A7, A8, A9).
+//
+// Replaces upstream Classifier.classify of RDP Classifier 2.5 (the jar invoked
+// at README.md:119): phase 1 per-word rows, phase 2 full-sum assignment,
+// phase 3 bootstrap with java.util.Random re-seeded to 1 per read, and the
+// per-read ancestor vote.
+//
+// Strict mode keeps the reference's arithmetic exactly: every sum is a chain of
+// single fp32 adds in the reference's order (word order for the assignment,
+// draw order for each replicate), and every argmax is "first strict maximum in
+// ascending genus index".  Parallelism is over (read, genus block, replicate),
+// never over the adds of one sum.
+//
+// Layout: one CTA = one read x one block of TG = 4*LPR genera.  The read's n
+// table rows (TG floats each) are staged once in shared memory with 16-byte
+// cp.async copies from the genus-tiled table; each group of LPR lanes then
+// owns one replicate at a time and walks its sample list with one LDS.128 and
+// four dependent FADDs per draw.  The grid is (reads, genus blocks) with reads
+// fastest, so all CTAs in flight gather from the same 65536 x 128 B table slab,
+// which stays resident in L2.
+#include "pg_internal.cuh"
+
+// ------------------------------------------------------------------ A8 sample lists
+
+#define JR_MULT 0x5DEECE66DULL
+#define JR_MASK ((1ULL << 48) - 1)
+
+__device__ __forceinline__ int32_t jr_next(unsigned long long &s, int bits)
+{
+    s = (s * JR_MULT + 0xBULL) & JR_MASK;
+    return (int32_t)(s >> (48 - bits));
+}
+
+__device__ __forceinline__ int32_t jr_next_int(unsigned long long &s, int32_t n)
+{
+    if ((n & -n) == n) return (int32_t)(((long long)n * (long long)jr_next(s, 31)) >> 31);
+    int32_t bits, val;
+    do {
+        bits = jr_next(s, 31);
+        val = bits % n;
+    } while ((long long)bits - val + (n - 1) > 0x7FFFFFFFLL);   // Java: int overflow => redraw
+    return val;
+}
+
+// One thread per distinct n: the 100 x k draws of java.util.Random(1).nextInt(n),
+// each replicate padded to a multiple of 8 with index n (the all-zero row).
+__global__ void k_boot_indices(const int32_t *__restrict__ ns, const int32_t *__restrict__ offs, int cnt,
+                               int min_boot, uint16_t *__restrict__ pool)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt) return;
+    const int n = ns[t];
+    int k = n >> 3;
+    if (k < min_boot) k = min_boot;
+    const int kpad = (k + 7) & ~7;
+    uint16_t *out = pool + offs[t];
+    unsigned long long s = (1ULL ^ JR_MULT) & JR_MASK;          // setSeed(1)
+    for (int run = 0; run < PG_NUM_BOOT; run++)
+        for (int j = 0; j < kpad; j++)
+            out[run * kpad + j] = (uint16_t)((j < k && n > 0) ? jr_next_int(s, n) : n);
+}
+
+// ------------------------------------------------------------------ keys
+
+// order-preserving map fp32 -> u32
+__device__ __forceinline__ uint32_t pg_ord(float f)
+{
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float pg_unord(uint32_t u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+// max over keys == larger score first, then SMALLER genus index (first strict max)
+__device__ __forceinline__ unsigned long long pg_key(float score, uint32_t genus)
+{
+    return ((unsigned long long)pg_ord(score) << 32) | (unsigned long long)(0xFFFFFFFFu - genus);
+}
+
+__device__ __forceinline__ void pg_cp_async16(void *smem, const void *gmem)
+{
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void pg_cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// ------------------------------------------------------------------ K4 strict
+
+template <int LPR, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK >= 1024) ? 1 : ((BLOCK >= 512) ? 2 : 4))
+k_classify_strict(const float *__restrict__ table, const uint16_t *__restrict__ words,
+                  const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
+                  const int32_t *__restrict__ order, int64_t read0,
+                  const uint16_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off,
+                  int min_boot, unsigned long long *__restrict__ best)
+{
+    constexpr int TG = 4 * LPR;
+    constexpr int NG = BLOCK / LPR;
+    extern __shared__ float4 sV[];                 // (n+1) rows x LPR float4; row n is all zero
+
+    const int tid = threadIdx.x;
+    const int64_t read = order[blockIdx.x];
+    const int n = nwords[read];
+    const int gbase = blockIdx.y * TG;
+    const float *tbase = table + ((size_t)(gbase >> 5) * PG_NWORDS) * PG_GENUS_TILE + (gbase & 31);
+    const uint16_t *w = words + off[read];
+
+    // ---- A4: stage the read's rows for this genus block
+    for (int c = tid; c < n * LPR; c += BLOCK) {
+        const int r = c / LPR, l = c % LPR;
+        pg_cp_async16(&sV[c], tbase + (size_t)w[r] * PG_GENUS_TILE + l * 4);
+    }
+    if (tid < LPR) sV[n * LPR + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pg_cp_async_wait_all();
+    __syncthreads();
+
+    const int group = tid / LPR, l = tid % LPR;
+    const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (((tid & 31) / LPR) * LPR));
+    int k = n >> 3;
+    if (k < min_boot) k = min_boot;
+    const int kpad = (k + 7) & ~7;
+    const uint16_t *bl = boot_pool + boot_off[n];
+    const float4 *row = sV + l;
+
+    // task 0 = A7 full sum (group 0 only); tasks 1..100 = A8 replicates.
+    int task = group;
+    const int stride = (group == 0) ? (PG_NUM_BOOT + 1) : (NG - 1);
+    for (; task <= PG_NUM_BOOT; task += stride) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (task == 0) {
+            const int n8 = n & ~7;
+            int j = 0;
+            for (; j < n8; j += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = row[(j + u) * LPR];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    a0 = __fadd_rn(a0, v[u].x); a1 = __fadd_rn(a1, v[u].y);
+                    a2 = __fadd_rn(a2, v[u].z); a3 = __fadd_rn(a3, v[u].w);
+                }
+            }
+            for (; j < n; j++) {
+                float4 v = row[j * LPR];
+                a0 = __fadd_rn(a0, v.x); a1 = __fadd_rn(a1, v.y);
+                a2 = __fadd_rn(a2, v.z); a3 = __fadd_rn(a3, v.w);
+            }
+        } else {
+            const uint4 *lp = reinterpret_cast<const uint4 *>(bl + (size_t)(task - 1) * kpad);
+            for (int j = 0; j < kpad; j += 8) {
+                const uint4 q = __ldg(lp + (j >> 3));
+                float4 v[8];
+                v[0] = row[(q.x & 0xFFFFu) * LPR]; v[1] = row[(q.x >> 16) * LPR];
+                v[2] = row[(q.y & 0xFFFFu) * LPR]; v[3] = row[(q.y >> 16) * LPR];
+                v[4] = row[(q.z & 0xFFFFu) * LPR]; v[5] = row[(q.z >> 16) * LPR];
+                v[6] = row[(q.w & 0xFFFFu) * LPR]; v[7] = row[(q.w >> 16) * LPR];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    a0 = __fadd_rn(a0, v[u].x); a1 = __fadd_rn(a1, v[u].y);
+                    a2 = __fadd_rn(a2, v[u].z); a3 = __fadd_rn(a3, v[u].w);
+                }
+            }
+        }
+        // first strict max in ascending genus index, inside the lane then across the group
+        const uint32_t g0 = (uint32_t)(gbase + l * 4);
+        unsigned long long key = pg_key(a0, g0);
+        unsigned long long k1 = pg_key(a1, g0 + 1), k2 = pg_key(a2, g0 + 2), k3 = pg_key(a3, g0 + 3);
+        key = key > k1 ? key : k1;
+        k2 = k2 > k3 ? k2 : k3;
+        key = key > k2 ? key : k2;
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(gmask, key, o);
+            key = key > other ? key : other;
+        }
+        if (l == 0) atomicMax(best + (size_t)(read - read0) * (PG_NUM_BOOT + 1) + task, key);
+    }
+}
+
+// ------------------------------------------------------------------ K5 vote (A9)
+
+// One warp per read: decode the 101 winners, count for every lineage level of
+// the determined genus the replicates whose winner shares that ancestor.
+__global__ void __launch_bounds__(256)
+k_vote(const unsigned long long *__restrict__ best, int64_t nreads, int64_t read0,
+       const int32_t *__restrict__ nwords, const uint8_t *__restrict__ flags,
+       const int32_t *__restrict__ anc, int depth, pg_result *__restrict__ results,
+       int32_t *__restrict__ boot_winners)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t ic = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ic >= nreads) return;
+    const int64_t i = read0 + ic;
+    pg_result *res = results + i;
+    uint32_t *raw = reinterpret_cast<uint32_t *>(res);          // 16 x uint32
+    if (flags[2 * i + 1]) {                                     // A2: short read
+        if (lane < 16) raw[lane] = (lane == 0) ? 0xFFFFFFFFu : (lane == 3 ? (1u << 8) : 0u);
+        if (boot_winners)
+            for (int r = lane; r < PG_NUM_BOOT; r += 32) boot_winners[i * PG_NUM_BOOT + r] = -1;
+        return;
+    }
+    const unsigned long long *b = best + (size_t)ic * (PG_NUM_BOOT + 1);
+    const unsigned long long key0 = b[0];
+    const int genus = (int)(0xFFFFFFFFu - (uint32_t)key0);
+    const float score = pg_unord((uint32_t)(key0 >> 32));
+
+    int gb[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int r = q * 32 + lane;
+        gb[q] = r < PG_NUM_BOOT ? (int)(0xFFFFFFFFu - (uint32_t)b[1 + r]) : -1;
+        if (boot_winners && r < PG_NUM_BOOT) boot_winners[i * PG_NUM_BOOT + r] = gb[q];
+    }
+    int myvote = 0, levels = 0;
+    const int nd = anc ? depth : 1;
+    for (int d = 0; d < nd; d++) {
+        const int a = anc ? anc[(size_t)genus * depth + d] : genus;
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            bool match = false;
+            if (gb[q] >= 0 && a >= 0) match = (anc ? anc[(size_t)gb[q] * depth + d] : gb[q]) == a;
+            cnt += __popc(__ballot_sync(0xffffffffu, match));
+        }
+        if (a >= 0) levels = d + 1;
+        if (lane == d) myvote = cnt;
+    }
+    // votes[32] live in raw[4..11]; pack four lanes per word
+    uint32_t packed = (uint32_t)myvote & 0xFFu;
+    uint32_t w0 = __shfl_sync(0xffffffffu, packed, (lane & 7) * 4 + 0);
+    uint32_t w1 = __shfl_sync(0xffffffffu, packed, (lane & 7) * 4 + 1);
+    uint32_t w2 = __shfl_sync(0xffffffffu, packed, (lane & 7) * 4 + 2);
+    uint32_t w3 = __shfl_sync(0xffffffffu, packed, (lane & 7) * 4 + 3);
+    const uint32_t vw = w0 | (w1 << 8) | (w2 << 16) | (w3 << 24);
+    if (lane == 0) {
+        raw[0] = (uint32_t)genus;
+        raw[1] = (uint32_t)nwords[i];
+        raw[2] = __float_as_uint(score);
+        raw[3] = (uint32_t)flags[2 * i] | (0u << 8) | ((uint32_t)levels << 16);
+    }
+    if (lane < 8) raw[4 + lane] = vw;
+    if (lane >= 8 && lane < 12) raw[4 + lane] = 0u;             // _pad1
+}
+
+// ------------------------------------------------------------------ host orchestration
+
+// Reads are bucketed by word count so each launch sizes its shared memory (and so
+// its CTAs/SM) for the reads it actually carries.
+struct Bucket { int nmax; int lpr; int block; };
+static const Bucket kBuckets[] = {
+    {215, 8, 256},  {250, 8, 256},  {290, 8, 256},  {350, 8, 256},  {440, 8, 256},
+    {590, 8, 256},  {900, 8, 512},  {1800, 8, 1024}, {3600, 4, 1024}, {PG_MAX_WORDS, 2, 1024},
+};
+static const int kNumBuckets = (int)(sizeof(kBuckets) / sizeof(kBuckets[0]));
+
+template <int LPR, int BLOCK>
+static int launch_strict(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, unsigned nblocks_g, size_t smem,
+                         const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
+                         const int32_t *d_order, int64_t read0, int min_boot, unsigned long long *d_best)
+{
+    // per device, so set it on every launch (a few microseconds)
+    PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_strict<LPR, BLOCK>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(nreads_b, nblocks_g);
+    k_classify_strict<LPR, BLOCK><<<grid, BLOCK, smem, ctx->stream>>>(
+        md->d_table, d_words, d_off, d_nwords, d_order, read0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, d_best);
+    PG_LAUNCHED(ctx);
+    return PG_OK;
+}
+
+int pg_classify_certified_launch(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsigned nreads_b, int nmax,
+                                 const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
+                                 const int32_t *d_order, int64_t read0, int min_boot,
+                                 unsigned long long *d_best);   // pg_certified.cu
+
+static int ensure_boot_lists(pg_ctx *ctx, const std::vector<int> &need_n, int min_boot)
+{
+    if (ctx->boot_min_words != min_boot) {          // different k rule: drop the cache
+        ctx->boot_used = 0;
+        ctx->h_boot_off.assign(PG_MAX_WORDS + 1, -1);
+        ctx->boot_min_words = min_boot;
+    }
+    if (!ctx->d_boot_off) {
+        PG_CUDA(ctx, cudaMalloc(&ctx->d_boot_off, (PG_MAX_WORDS + 1) * sizeof(int32_t)));
+        ctx->h_boot_off.assign(PG_MAX_WORDS + 1, -1);
+    }
+    std::vector<int32_t> ns, offs;
+    size_t used = ctx->boot_used;
+    for (int n : need_n) {
+        if (ctx->h_boot_off[n] >= 0) continue;
+        int k = n >> 3;
+        if (k < min_boot) k = min_boot;
+        int kpad = (k + 7) & ~7;
+        ns.push_back(n);
+        offs.push_back((int32_t)used);
+        ctx->h_boot_off[n] = (int32_t)used;
+        used += (size_t)PG_NUM_BOOT * kpad + 8;     // +8 keeps even k==0 lists distinct and aligned
+    }
+    if (ns.empty()) return PG_OK;
+    if (used > ctx->boot_cap) {
+        size_t cap = used * 2 + 4096;
+        uint16_t *np = NULL;
+        PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PG_CUDA(ctx, cudaMalloc(&np, cap * sizeof(uint16_t)));
+        if (ctx->d_boot_pool) {
+            PG_CUDA(ctx, cudaMemcpy(np, ctx->d_boot_pool, ctx->boot_used * sizeof(uint16_t), cudaMemcpyDeviceToDevice));
+            PG_CUDA(ctx, cudaFree(ctx->d_boot_pool));
+        }
+        ctx->d_boot_pool = np;
+        ctx->boot_cap = cap;
+    }
+    ctx->boot_used = used;
+    int cnt = (int)ns.size();
+    PG_TRY(pg_scratch(ctx, &ctx->s_boot, (size_t)cnt * 8));
+    int32_t *d_ns = (int32_t *)ctx->s_boot.p, *d_offs = d_ns + cnt;
+    // pageable source: cudaMemcpyAsync stages it before returning
+    PG_CUDA(ctx, cudaMemcpyAsync(d_ns, ns.data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(ctx, cudaMemcpyAsync(d_offs, offs.data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(ctx, cudaMemcpyAsync(ctx->d_boot_off, ctx->h_boot_off.data(), (PG_MAX_WORDS + 1) * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    k_boot_indices<<<(cnt + 31) / 32, 32, 0, ctx->stream>>>(d_ns, d_offs, cnt, min_boot, ctx->d_boot_pool);
+    PG_LAUNCHED(ctx);
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // ns/offs are stack vectors
+    return PG_OK;
+}
+
+int pg_extract_launch(pg_ctx *ctx, const pg_model *md, const uint32_t *d_planes, const int64_t *d_off,
+                      int64_t count, uint16_t *d_words, int32_t *d_nwords, uint8_t *d_flags);
+int pg_pack_launch(pg_ctx *ctx, const char *d_bytes, const int64_t *d_off, int64_t count, uint32_t *d_planes);
+
+static cudaEvent_t take_event(pg_ctx *ctx)
+{
+    cudaEvent_t ev;
+    if (!ctx->ev_free.empty()) { ev = ctx->ev_free.back(); ctx->ev_free.pop_back(); return ev; }
+    cudaEventCreate(&ev);
+    return ev;
+}
+
+// words/nwords/flags already on the device for `count` reads; classify + vote.
+static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off, int64_t count,
+                          const uint16_t *d_words, const int32_t *d_nwords, const uint8_t *d_flags,
+                          const pg_classify_opts *opts, pg_result *d_results, int32_t *d_boot_winners)
+{
+    const int min_boot = opts ? opts->min_boot_words : 0;
+    const int mode = opts ? opts->mode : 0;
+    if (min_boot < 0 || min_boot > 64) return pg_fail(ctx, PG_EINVAL, "min_boot_words out of range");
+    if (mode != 0 && mode != 1) return pg_fail(ctx, PG_EINVAL, "unknown classify mode %d", mode);
+    if (count == 0) return PG_OK;
+    if (count > 0x7fffffffLL) return pg_fail(ctx, PG_ERANGE, "more than 2^31-1 reads in one batch");
+
+    // n per read -> host, bucket the reads
+    PG_TRY(pg_pinned(ctx, (size_t)count * 8));
+    int32_t *h_n = (int32_t *)ctx->h_pin;
+    int32_t *h_order = h_n + count;
+    PG_CUDA(ctx, cudaMemcpyAsync(h_n, d_nwords, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+
+    std::vector<char> seen(PG_MAX_WORDS + 1, 0);
+    std::vector<int> need;
+    for (int64_t i = 0; i < count; i++) {
+        int n = h_n[i];
+        if (n > PG_MAX_WORDS)
+            return pg_fail(ctx, PG_ERANGE, "read %lld has %d good words; the limit is %d", (long long)i, n, PG_MAX_WORDS);
+        if (!seen[n]) { seen[n] = 1; need.push_back(n); }
+    }
+    PG_TRY(ensure_boot_lists(ctx, need, min_boot));
+
+    const int64_t CHUNK = 1 << 20;
+    const int nkeys = PG_NUM_BOOT + 1;
+    PG_TRY(pg_scratch(ctx, &ctx->s_best, (size_t)(count < CHUNK ? count : CHUNK) * nkeys * 8));
+    PG_TRY(pg_scratch(ctx, &ctx->s_order, (size_t)(count < CHUNK ? count : CHUNK) * 4));
+    unsigned long long *d_best = (unsigned long long *)ctx->s_best.p;
+    int32_t *d_order = (int32_t *)ctx->s_order.p;
+
+    for (int64_t c0 = 0; c0 < count; c0 += CHUNK) {
+        const int64_t cn = count - c0 < CHUNK ? count - c0 : CHUNK;
+        // counting sort of the chunk's reads by bucket (stable: keeps read order inside a bucket)
+        int64_t bcount[16] = {0}, bstart[16], bmaxn[16] = {0};
+        for (int64_t i = c0; i < c0 + cn; i++) {
+            int n = h_n[i], b = 0;
+            while (kBuckets[b].nmax < n) b++;
+            bcount[b]++;
+            if (n > bmaxn[b]) bmaxn[b] = n;
+        }
+        int64_t acc = 0;
+        for (int b = 0; b < kNumBuckets; b++) { bstart[b] = acc; acc += bcount[b]; }
+        {
+            int64_t fill[16];
+            for (int b = 0; b < kNumBuckets; b++) fill[b] = bstart[b];
+            for (int64_t i = c0; i < c0 + cn; i++) {
+                int n = h_n[i], b = 0;
+                while (kBuckets[b].nmax < n) b++;
+                h_order[c0 + fill[b]++] = (int32_t)i;
+            }
+        }
+        PG_CUDA(ctx, cudaMemcpyAsync(d_order, h_order + c0, (size_t)cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        PG_CUDA(ctx, cudaMemsetAsync(d_best, 0, (size_t)cn * nkeys * 8, ctx->stream));
+
+        for (int b = 0; b < kNumBuckets; b++) {
+            if (!bcount[b]) continue;
+            const Bucket &bk = kBuckets[b];
+            const int nmax = (int)bmaxn[b];
+            const int32_t *ord = d_order + bstart[b];
+            cudaEvent_t e0 = take_event(ctx), e1 = take_event(ctx);
+            PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+            if (mode == 1) {
+                PG_TRY(pg_classify_certified_launch(ctx, md, bk, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords,
+                                                    ord, c0, min_boot, d_best));
+            } else {
+                const int TG = 4 * bk.lpr;
+                const unsigned ngb = (unsigned)((md->G + TG - 1) / TG);
+                const size_t smem = (size_t)(nmax + 1) * bk.lpr * 16;
+                int rc;
+                if (bk.lpr == 8 && bk.block == 256)
+                    rc = launch_strict<8, 256>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+                else if (bk.lpr == 8 && bk.block == 512)
+                    rc = launch_strict<8, 512>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+                else if (bk.lpr == 8)
+                    rc = launch_strict<8, 1024>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+                else if (bk.lpr == 4)
+                    rc = launch_strict<4, 1024>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+                else
+                    rc = launch_strict<2, 1024>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+                PG_TRY(rc);
+            }
+            PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+            ctx->ev_pending.push_back(std::make_pair(e0, e1));
+        }
+        const int wpb = 8;
+        k_vote<<<(unsigned)((cn + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+            d_best, cn, c0, d_nwords, d_flags, md->d_anc, md->depth, d_results, d_boot_winners);
+        PG_LAUNCHED(ctx);
+    }
+    return PG_OK;
+}
+
+static int classify_planes(pg_ctx *ctx, const pg_model *md, const uint32_t *d_planes, const int64_t *d_off,
+                           int64_t count, int64_t total_bytes, const pg_classify_opts *opts,
+                           pg_result *d_results, int32_t *d_boot_winners)
+{
+    PG_TRY(pg_scratch(ctx, &ctx->s_words, (size_t)total_bytes * 2 + 64));
+    PG_TRY(pg_scratch(ctx, &ctx->s_nwords, (size_t)count * 4 + 64));
+    PG_TRY(pg_scratch(ctx, &ctx->s_flags, (size_t)count * 2 + 64));
+    uint16_t *d_words = (uint16_t *)ctx->s_words.p;
+    int32_t *d_nwords = (int32_t *)ctx->s_nwords.p;
+    uint8_t *d_flags = (uint8_t *)ctx->s_flags.p;
+    PG_TRY(pg_extract_launch(ctx, md, d_planes, d_off, count, d_words, d_nwords, d_flags));
+    return classify_words(ctx, md, d_off, count, d_words, d_nwords, d_flags, opts, d_results, d_boot_winners);
+}
+
+extern "C" int pg_classify_packed(pg_ctx *ctx, const pg_model *md, const pg_reads *reads,
+                                  const pg_classify_opts *opts, pg_result *results_dev, int32_t *boot_winners_dev)
+{
+    if (!ctx || !md || !reads || !results_dev) return pg_fail(ctx, PG_EINVAL, "pg_classify_packed: bad arguments");
+    if (!md->committed) return pg_fail(ctx, PG_EINVAL, "pg_classify_packed: model has no tables (commit it first)");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return classify_planes(ctx, md, reads->d_planes, reads->d_off, reads->count, reads->total_bytes, opts,
+                           results_dev, boot_winners_dev);
+}
+
+extern "C" int pg_classify(pg_ctx *ctx, const pg_model *md, const pg_seqbatch *reads, const pg_classify_opts *opts,
+                           pg_result *results_host, int32_t *boot_winners_host)
+{
+    if (!ctx || !md || !reads || !results_host || reads->count < 0)
+        return pg_fail(ctx, PG_EINVAL, "pg_classify: bad arguments");
+    if (!md->committed) return pg_fail(ctx, PG_EINVAL, "pg_classify: model has no tables (commit it first)");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = reads->count;
+    if (n == 0) return PG_OK;
+    const int64_t total = reads->off[n];
+    // upload ASCII + offsets, pack on the device
+    PG_TRY(pg_scratch(ctx, &ctx->s_bytes, (size_t)total + 64));
+    PG_TRY(pg_scratch(ctx, &ctx->s_off, (size_t)(n + 1) * 8));
+    const size_t nch = (size_t)(total >> 5) + n + 2;
+    PG_TRY(pg_scratch(ctx, &ctx->s_cand, nch * 12));
+    PG_TRY(pg_scratch(ctx, &ctx->s_results, (size_t)n * sizeof(pg_result) + (boot_winners_host ? (size_t)n * 400 : 0)));
+    char *d_bytes = (char *)ctx->s_bytes.p;
+    int64_t *d_off = (int64_t *)ctx->s_off.p;
+    uint32_t *d_planes = (uint32_t *)ctx->s_cand.p;
+    pg_result *d_res = (pg_result *)ctx->s_results.p;
+    int32_t *d_bw = boot_winners_host ? (int32_t *)(d_res + n) : NULL;
+    PG_CUDA(ctx, cudaMemcpyAsync(d_bytes, reads->bytes, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(ctx, cudaMemcpyAsync(d_off, reads->off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PG_TRY(pg_pack_launch(ctx, d_bytes, d_off, n, d_planes));
+    PG_TRY(classify_planes(ctx, md, d_planes, d_off, n, total, opts, d_res, d_bw));
+    PG_CUDA(ctx, cudaMemcpyAsync(results_host, d_res, (size_t)n * sizeof(pg_result), cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_bw)
+        PG_CUDA(ctx, cudaMemcpyAsync(boot_winners_host, d_bw, (size_t)n * 400, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+
+extern "C" int pg_extract_words(pg_ctx *ctx, const pg_model *md, const pg_seqbatch *reads,
+                                uint16_t *words_host, int32_t *n_words_host, uint8_t *reversed_host)
+{
+    if (!ctx || !md || !reads || reads->count < 0) return pg_fail(ctx, PG_EINVAL, "pg_extract_words: bad arguments");
+    if (!md->committed) return pg_fail(ctx, PG_EINVAL, "pg_extract_words: model has no tables");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = reads->count;
+    if (n == 0) return PG_OK;
+    const int64_t total = reads->off[n];
+    PG_TRY(pg_scratch(ctx, &ctx->s_bytes, (size_t)total + 64));
+    PG_TRY(pg_scratch(ctx, &ctx->s_off, (size_t)(n + 1) * 8));
+    PG_TRY(pg_scratch(ctx, &ctx->s_cand, ((size_t)(total >> 5) + n + 2) * 12));
+    PG_TRY(pg_scratch(ctx, &ctx->s_words, (size_t)total * 2 + 64));
+    PG_TRY(pg_scratch(ctx, &ctx->s_nwords, (size_t)n * 4 + 64));
+    PG_TRY(pg_scratch(ctx, &ctx->s_flags, (size_t)n * 2 + 64));
+    PG_CUDA(ctx, cudaMemcpyAsync(ctx->s_bytes.p, reads->bytes, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(ctx, cudaMemcpyAsync(ctx->s_off.p, reads->off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PG_TRY(pg_pack_launch(ctx, (const char *)ctx->s_bytes.p, (const int64_t *)ctx->s_off.p, n, (uint32_t *)ctx->s_cand.p));
+    PG_TRY(pg_extract_launch(ctx, md, (const uint32_t *)ctx->s_cand.p, (const int64_t *)ctx->s_off.p, n,
+                             (uint16_t *)ctx->s_words.p, (int32_t *)ctx->s_nwords.p, (uint8_t *)ctx->s_flags.p));
+    if (words_host)
+        PG_CUDA(ctx, cudaMemcpyAsync(words_host, ctx->s_words.p, (size_t)total * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_words_host)
+        PG_CUDA(ctx, cudaMemcpyAsync(n_words_host, ctx->s_nwords.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint8_t> fl;
+    if (reversed_host) {
+        fl.resize((size_t)n * 2);
+        PG_CUDA(ctx, cudaMemcpyAsync(fl.data(), ctx->s_flags.p, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (reversed_host)
+        for (int64_t i = 0; i < n; i++) reversed_host[i] = fl[2 * i];
+    return PG_OK;
+}
+
+extern "C" int pg_boot_indices(pg_ctx *ctx, int32_t n, int32_t min_boot_words, uint16_t *out_host)
+{
+    if (!ctx || !out_host || n < 0 || n > PG_MAX_WORDS) return pg_fail(ctx, PG_EINVAL, "pg_boot_indices: bad arguments");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int> need(1, n);
+    PG_TRY(ensure_boot_lists(ctx, need, min_boot_words));
+    int k = n >> 3;
+    if (k < min_boot_words) k = min_boot_words;
+    const int kpad = (k + 7) & ~7;
+    std::vector<uint16_t> tmp((size_t)PG_NUM_BOOT * kpad + 8);
+    PG_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->d_boot_pool + ctx->h_boot_off[n], tmp.size() * 2, cudaMemcpyDeviceToHost));
+    for (int run = 0; run < PG_NUM_BOOT; run++)
+        for (int j = 0; j < k; j++) out_host[run * k + j] = tmp[(size_t)run * kpad + j];
+    return PG_OK;
+}

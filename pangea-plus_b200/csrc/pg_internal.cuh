@@ -1,0 +1,106 @@
+// pg_internal.cuh -- shared host/device plumbing of libpangea_b200.so.
+// Not part of the ABI; the ABI is include/pangea_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <stdlib.h>
+#include <vector>
+#include <utility>
+
+#include "pangea_b200.h"
+
+struct pg_ctx {
+    int          device;
+    cudaStream_t stream;
+    cudaStream_t own_stream;
+    mutable char err[512];
+    int64_t      launches;
+
+    // java.util.Random(1) sample lists, cached per n (row A8): pool of uint16,
+    // h_boot_off[n] = offset of the list for n words (or -1), mirrored on device.
+    uint16_t            *d_boot_pool;
+    size_t               boot_cap, boot_used;     // uint16 units
+    int32_t             *d_boot_off;              // [PG_MAX_WORDS+1]
+    std::vector<int32_t> h_boot_off;
+    int                  boot_min_words;
+
+    // classify-kernel timing (CUDA events on the launching stream)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending;
+    std::vector<cudaEvent_t>                         ev_free;
+    double  classify_ms;
+    int64_t classify_launches;
+
+    // grow-only device scratch for classification
+    struct Scratch {
+        void  *p;
+        size_t cap;
+    } s_words, s_nwords, s_flags, s_best, s_order, s_results, s_boot, s_bytes, s_off, s_cand;
+    // pinned host staging
+    void  *h_pin;
+    size_t h_pin_cap;
+};
+
+struct pg_model {
+    pg_ctx  *ctx;
+    int      G, ntile, depth;
+    int64_t  N;                 // host copy, valid after commit
+    int32_t *d_m;               // [ntile][65536][32]   A5 counts, genus-tiled
+    int32_t *d_nw;              // [65536]
+    int32_t *d_M;               // [ntile*32]
+    unsigned long long *d_N;    // [1]
+    float   *d_table;           // [ntile][65536][32]   A4/A6 dense log table, genus-tiled
+    float   *d_logPrior;        // [65536]
+    float   *d_Pw;              // [65536]
+    float   *d_logLeave;        // [ntile*32]
+    int32_t *d_anc;             // [G][depth]
+    uint16_t *d_qtable;         // [ntile][65536][32]   certified mode: quantised deficits
+    float   *d_rowmax;          // [65536]
+    bool     committed;
+};
+
+struct pg_reads {
+    pg_ctx   *ctx;
+    int64_t   count;
+    int64_t   total_bytes;
+    int64_t  *d_off;            // [count+1] byte offsets of the original records
+    uint32_t *d_planes;         // 3 x uint32 per 32-base chunk: {lo, hi, valid}
+    int64_t   nchunks_cap;
+};
+
+// chunk index (32 bases per chunk) at which read i starts in the plane store:
+// floor(off[i]/32) + i never overlaps the previous read and needs no scan.
+__host__ __device__ static inline int64_t pg_chunk_start(int64_t off_i, int64_t i)
+{
+    return (off_i >> 5) + i;
+}
+
+int  pg_fail(const pg_ctx *ctx, int code, const char *fmt, ...);
+int  pg_scratch(pg_ctx *ctx, pg_ctx::Scratch *s, size_t bytes);
+int  pg_pinned(pg_ctx *ctx, size_t bytes);
+
+#define PG_CUDA(ctx, call)                                                              \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return pg_fail((ctx), PG_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,  \
+                           cudaGetErrorString(e__));                                    \
+    } while (0)
+
+#define PG_LAUNCHED(ctx)                                                                \
+    do {                                                                                \
+        (ctx)->launches++;                                                              \
+        cudaError_t e__ = cudaGetLastError();                                           \
+        if (e__ != cudaSuccess)                                                         \
+            return pg_fail((ctx), PG_ECUDA, "%s:%d launch: %s", __FILE__, __LINE__,     \
+                           cudaGetErrorString(e__));                                    \
+    } while (0)
+
+#define PG_TRY(call)                                                                    \
+    do {                                                                                \
+        int r__ = (call);                                                               \
+        if (r__ != PG_OK) return r__;                                                   \
+    } while (0)

@@ -1,0 +1,341 @@
+"""ctypes binding of libpangea_b200.so (include/pangea_b200.h).
+
+This is plumbing for the tests and bench.py; the product is the C-ABI library
+and the C command-line tools under pangea-plus_b200/host/.  There is no Python
+or CPU implementation of the hot path here: if the library is missing, or no
+B200 is visible, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent.parent          # pangea-plus_b200/
+REPO = PKG_DIR.parent
+LIB_PATH = PKG_DIR / "libpangea_b200.so"
+HEADER = REPO / "include" / "pangea_b200.h"
+
+PG_NWORDS = 65536
+PG_NUM_BOOT = 100
+PG_MAX_DEPTH = 32
+PG_MIN_SEQ_LEN = 50
+
+RESULT_DTYPE = np.dtype(
+    [
+        ("genus", "<i4"),
+        ("n_words", "<i4"),
+        ("score", "<f4"),
+        ("reversed", "u1"),
+        ("status", "u1"),
+        ("depth", "u1"),
+        ("_pad0", "u1"),
+        ("votes", "u1", (PG_MAX_DEPTH,)),
+        ("_pad1", "u1", (16,)),
+    ]
+)
+assert RESULT_DTYPE.itemsize == 64
+
+
+class PangeaError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libpangea_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _SeqBatch(C.Structure):
+    _fields_ = [("bytes", C.c_void_p), ("off", C.c_void_p), ("count", C.c_int64)]
+
+
+class _Opts(C.Structure):
+    _fields_ = [("min_boot_words", C.c_int32), ("mode", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+class _ConsensusIn(C.Structure):
+    _fields_ = [
+        ("nreads", C.c_int64),
+        ("hit_off", C.c_void_p),
+        ("lineage_bytes", C.c_void_p),
+        ("lineage_off", C.c_void_p),
+        ("pident_bytes", C.c_void_p),
+        ("pident_off", C.c_void_p),
+        ("rdp_bytes", C.c_void_p),
+        ("rdp_off", C.c_void_p),
+    ]
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile the library in-tree (nvcc, sm_100a).  Used by __graft_entry__.build()."""
+    out = subprocess.run(["make", "-C", str(PKG_DIR), "-j8", "all"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:])
+        print(out.stderr[-4000:])
+    if out.returncode != 0:
+        raise RuntimeError("building libpangea_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: run `make -C {PKG_DIR}` (or __graft_entry__.build()). "
+            "There is no fallback implementation."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.pg_init.restype = vp
+    lib.pg_init.argtypes = [C.c_int]
+    lib.pg_shutdown.argtypes = [vp]
+    lib.pg_shutdown.restype = None
+    lib.pg_last_error.restype = C.c_char_p
+    lib.pg_last_error.argtypes = [vp]
+    lib.pg_set_stream.argtypes = [vp, vp]
+    lib.pg_sync.argtypes = [vp]
+    lib.pg_launch_count.restype = i64
+    lib.pg_launch_count.argtypes = [vp]
+    lib.pg_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.pg_kernel_time_reset.argtypes = [vp]
+    lib.pg_train.argtypes = [vp, C.POINTER(_SeqBatch), vp, C.c_int, C.POINTER(vp)]
+    lib.pg_train_dev.argtypes = [vp, C.POINTER(_SeqBatch), vp, C.c_int, C.POINTER(vp)]
+    lib.pg_model_free.argtypes = [vp]
+    lib.pg_model_free.restype = None
+    lib.pg_model_set_lineage.argtypes = [vp, vp, C.c_int]
+    lib.pg_model_genera.argtypes = [vp]
+    lib.pg_model_sequences.restype = i64
+    lib.pg_model_sequences.argtypes = [vp]
+    lib.pg_model_counts.argtypes = [vp, vp, vp, vp, C.POINTER(i64)]
+    lib.pg_model_tables.argtypes = [vp, vp, vp, vp]
+    lib.pg_model_save.argtypes = [vp, C.c_char_p, vp, i64]
+    lib.pg_model_load.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
+    lib.pg_free.argtypes = [vp]
+    lib.pg_free.restype = None
+    lib.pg_model_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    lib.pg_model_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int, C.POINTER(C.c_int)]
+    lib.pg_model_commit.argtypes = [vp]
+    lib.pg_reads_pack.argtypes = [vp, C.POINTER(_SeqBatch), C.POINTER(vp)]
+    lib.pg_reads_pack_dev.argtypes = [vp, C.POINTER(_SeqBatch), i64, C.POINTER(vp)]
+    lib.pg_reads_free.argtypes = [vp]
+    lib.pg_reads_free.restype = None
+    lib.pg_reads_count.restype = i64
+    lib.pg_reads_count.argtypes = [vp]
+    lib.pg_reads_unpack.restype = i64
+    lib.pg_reads_unpack.argtypes = [vp, i64, vp, vp, i64]
+    lib.pg_classify.argtypes = [vp, vp, C.POINTER(_SeqBatch), C.POINTER(_Opts), vp, vp]
+    lib.pg_classify_packed.argtypes = [vp, vp, vp, C.POINTER(_Opts), vp, vp]
+    lib.pg_extract_words.argtypes = [vp, vp, C.POINTER(_SeqBatch), vp, vp, vp]
+    lib.pg_boot_indices.argtypes = [vp, i32, i32, vp]
+    lib.pg_tax_build.argtypes = [C.c_char_p]
+    lib.pg_tax_load.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    lib.pg_tax_free.argtypes = [vp]
+    lib.pg_tax_free.restype = None
+    lib.pg_tax_leaf.argtypes = [vp, vp, vp, i64, vp]
+    lib.pg_tax_lineage.argtypes = [vp, vp, vp, i64, vp, i64, vp]
+    lib.pg_consensus.argtypes = [vp, C.POINTER(_ConsensusIn), vp, vp]
+    _lib = lib
+    return lib
+
+
+def pack_sequences(seqs) -> tuple[np.ndarray, np.ndarray]:
+    """list of bytes/str -> (uint8 bytes, int64 offsets[count+1])."""
+    bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
+    off = np.zeros(len(bs) + 1, dtype=np.int64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs])
+    data = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, np.uint8)
+    return data, off
+
+
+def _ptr(a) -> int:
+    """address of a numpy array (host) or anything with data_ptr() (torch, device)."""
+    if a is None:
+        return 0
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+class Model:
+    def __init__(self, ctx: "Context", handle: int):
+        self.ctx, self.h = ctx, handle
+
+    @property
+    def G(self) -> int:
+        return self.ctx.lib.pg_model_genera(self.h)
+
+    @property
+    def N(self) -> int:
+        return self.ctx.lib.pg_model_sequences(self.h)
+
+    def set_lineage(self, anc: np.ndarray) -> None:
+        anc = np.ascontiguousarray(anc, dtype=np.int32)
+        assert anc.ndim == 2 and anc.shape[0] == self.G
+        self.ctx._chk(self.ctx.lib.pg_model_set_lineage(self.h, anc.ctypes.data, anc.shape[1]))
+
+    def counts(self, dense: bool = True):
+        G = self.G
+        m = np.empty((PG_NWORDS, G), np.int32) if dense else None
+        nw = np.empty(PG_NWORDS, np.int32)
+        M = np.empty(G, np.int32)
+        N = C.c_int64()
+        self.ctx._chk(self.ctx.lib.pg_model_counts(self.h, _ptr(m), nw.ctypes.data, M.ctypes.data, C.byref(N)))
+        return m, nw, M, N.value
+
+    def tables(self, dense: bool = True):
+        G = self.G
+        lp = np.empty(PG_NWORDS, np.float32)
+        ll = np.empty(G, np.float32)
+        t = np.empty((PG_NWORDS, G), np.float32) if dense else None
+        self.ctx._chk(self.ctx.lib.pg_model_tables(self.h, lp.ctypes.data, ll.ctypes.data, _ptr(t)))
+        return lp, ll, t
+
+    def save(self, path: str, blob: bytes = b"") -> None:
+        buf = C.create_string_buffer(blob, len(blob)) if blob else None
+        self.ctx._chk(self.ctx.lib.pg_model_save(self.h, str(path).encode(), C.cast(buf, C.c_void_p) if buf else None, len(blob)))
+
+    def buffers(self):
+        ptrs = (C.c_void_p * 8)()
+        sizes = (C.c_size_t * 8)()
+        n = C.c_int()
+        self.ctx._chk(self.ctx.lib.pg_model_buffers(self.h, ptrs, sizes, 8, C.byref(n)))
+        return [(ptrs[i], sizes[i]) for i in range(n.value)]
+
+    def commit(self) -> None:
+        self.ctx._chk(self.ctx.lib.pg_model_commit(self.h))
+
+    def free(self) -> None:
+        if self.h:
+            self.ctx.lib.pg_model_free(self.h)
+            self.h = 0
+
+
+class Reads:
+    def __init__(self, ctx: "Context", handle: int):
+        self.ctx, self.h = ctx, handle
+
+    def __len__(self) -> int:
+        return self.ctx.lib.pg_reads_count(self.h)
+
+    def unpack(self, i: int, length_hint: int):
+        nch = (length_hint + 31) // 32 + 1
+        codes = np.zeros(2 * nch, np.uint32)
+        mask = np.zeros(nch, np.uint32)
+        ln = self.ctx.lib.pg_reads_unpack(self.h, i, codes.ctypes.data, mask.ctypes.data, 2 * nch)
+        if ln < 0:
+            raise PangeaError(ln, self.ctx.last_error())
+        return ln, codes, mask
+
+    def free(self) -> None:
+        if self.h:
+            self.ctx.lib.pg_reads_free(self.h)
+            self.h = 0
+
+
+class Context:
+    """One pg_ctx == one GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        self.h = self.lib.pg_init(device)
+        if not self.h:
+            raise PangeaError(-5, self.lib.pg_last_error(None).decode())
+
+    def last_error(self) -> str:
+        return self.lib.pg_last_error(self.h).decode()
+
+    def _chk(self, rc: int) -> None:
+        if rc != 0:
+            raise PangeaError(rc, self.last_error())
+
+    def close(self) -> None:
+        if self.h:
+            self.lib.pg_shutdown(self.h)
+            self.h = 0
+
+    def set_stream(self, stream_ptr: int) -> None:
+        self._chk(self.lib.pg_set_stream(self.h, stream_ptr))
+
+    def sync(self) -> None:
+        self._chk(self.lib.pg_sync(self.h))
+
+    def launch_count(self) -> int:
+        return self.lib.pg_launch_count(self.h)
+
+    def kernel_time(self):
+        ms, n = C.c_double(), C.c_int64()
+        self._chk(self.lib.pg_kernel_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def kernel_time_reset(self) -> None:
+        self._chk(self.lib.pg_kernel_time_reset(self.h))
+
+    # ---- Stage A
+    def train(self, data, off, genus, G: int, device: bool = False) -> Model:
+        sb = _SeqBatch(_ptr(data), _ptr(off), len(off) - 1)
+        h = C.c_void_p()
+        fn = self.lib.pg_train_dev if device else self.lib.pg_train
+        if not device:
+            genus = np.ascontiguousarray(genus, dtype=np.int32)
+        self._chk(fn(self.h, C.byref(sb), _ptr(genus), G, C.byref(h)))
+        return Model(self, h.value)
+
+    def model_create(self, G: int) -> Model:
+        h = C.c_void_p()
+        self._chk(self.lib.pg_model_create(self.h, G, C.byref(h)))
+        return Model(self, h.value)
+
+    def model_load(self, path: str):
+        h, blob, blen = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._chk(self.lib.pg_model_load(self.h, str(path).encode(), C.byref(h), C.byref(blob), C.byref(blen)))
+        b = C.string_at(blob.value, blen.value) if blob.value else b""
+        if blob.value:
+            self.lib.pg_free(blob)
+        return Model(self, h.value), b
+
+    def pack(self, data, off, device: bool = False, total_bytes: int | None = None) -> Reads:
+        sb = _SeqBatch(_ptr(data), _ptr(off), len(off) - 1)
+        h = C.c_void_p()
+        if device:
+            self._chk(self.lib.pg_reads_pack_dev(self.h, C.byref(sb), int(total_bytes), C.byref(h)))
+        else:
+            self._chk(self.lib.pg_reads_pack(self.h, C.byref(sb), C.byref(h)))
+        return Reads(self, h.value)
+
+    def classify(self, model: Model, data: np.ndarray, off: np.ndarray, mode: int = 0, min_boot_words: int = 0,
+                 want_boot: bool = False, out: np.ndarray | None = None):
+        n = len(off) - 1
+        sb = _SeqBatch(_ptr(data), _ptr(off), n)
+        opts = _Opts(min_boot_words, mode)
+        res = out if out is not None else np.zeros(n, RESULT_DTYPE)
+        boot = np.zeros((n, PG_NUM_BOOT), np.int32) if want_boot else None
+        self._chk(self.lib.pg_classify(self.h, model.h, C.byref(sb), C.byref(opts), _ptr(res), _ptr(boot)))
+        return (res, boot) if want_boot else res
+
+    def classify_packed(self, model: Model, reads: Reads, results_dev, boot_dev=None, mode: int = 0,
+                        min_boot_words: int = 0) -> None:
+        opts = _Opts(min_boot_words, mode)
+        self._chk(self.lib.pg_classify_packed(self.h, model.h, reads.h, C.byref(opts), _ptr(results_dev), _ptr(boot_dev)))
+
+    def extract_words(self, model: Model, data: np.ndarray, off: np.ndarray):
+        n = len(off) - 1
+        sb = _SeqBatch(_ptr(data), _ptr(off), n)
+        words = np.zeros(int(off[-1]), np.uint16)
+        nw = np.zeros(n, np.int32)
+        rev = np.zeros(n, np.uint8)
+        self._chk(self.lib.pg_extract_words(self.h, model.h, C.byref(sb), words.ctypes.data, nw.ctypes.data, rev.ctypes.data))
+        return words, nw, rev
+
+    def boot_indices(self, n: int, min_boot_words: int = 0) -> np.ndarray:
+        k = max(n // 8, min_boot_words)
+        out = np.zeros((PG_NUM_BOOT, k), np.uint16)
+        self._chk(self.lib.pg_boot_indices(self.h, n, min_boot_words, out.ctypes.data))
+        return out

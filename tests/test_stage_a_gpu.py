@@ -1,0 +1,285 @@
+"""GPU parity tests for Stage A: the CUDA path (through the C ABI) against the
+CPU oracle on the same seeded inputs.  Integer / index results must be
+bit-exact; the summed log-posterior is compared bit-for-bit as well (the
+north-star tolerance is 1e-5 relative; strict mode does better)."""
+import numpy as np
+import pytest
+
+import oracle_rdp as ora
+import pangea_b200 as pg
+from pangea_b200 import pack_sequences, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def small(ctx):
+    tr = synth.synth16s(seed=21, seqs=300, genera=70, length=900)      # G not a multiple of 32
+    om = ora.Model(tr["data"], tr["off"], tr["genus"], tr["G"])
+    gm = ctx.train(tr["data"], tr["off"], tr["genus"], tr["G"])
+    gm.set_lineage(tr["anc"])
+    yield tr, om, gm
+    om.free()
+    gm.free()
+
+
+def test_counts_bit_exact(small):
+    tr, om, gm = small
+    m, nw, M, N = gm.counts()
+    rm, rnw, rM, rN = om.counts()
+    assert N == rN == len(tr["genus"])
+    assert np.array_equal(M, rM)
+    assert np.array_equal(nw, rnw)
+    assert np.array_equal(m, rm)
+
+
+def test_tables_bit_exact(small):
+    tr, om, gm = small
+    lp, ll, t = gm.tables()
+    rlp, rll, rt = om.tables()
+    assert np.array_equal(bits(lp), bits(rlp))
+    assert np.array_equal(bits(ll), bits(rll))
+    bad = np.count_nonzero(bits(t) != bits(rt))
+    assert bad == 0, f"{bad} of {t.size} table entries differ"
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 64, 243, 486, 1000, 1418, 2048, 4097, 7000])
+def test_boot_indices_match_java_random(ctx, n):
+    got = ctx.boot_indices(n)
+    k = n // 8
+    want = ora.jrandom_stream(1, n, 100 * k).reshape(100, k) if k else np.zeros((100, 0), np.int32)
+    assert np.array_equal(got.astype(np.int32), want)
+
+
+def test_boot_indices_min_words(ctx):
+    got = ctx.boot_indices(20, 5)
+    want = ora.jrandom_stream(1, 20, 500).reshape(100, 5)
+    assert np.array_equal(got.astype(np.int32), want)
+    # back to the 2.5 rule: cache must be rebuilt, not reused
+    got = ctx.boot_indices(20, 0)
+    want = ora.jrandom_stream(1, 20, 200).reshape(100, 2)
+    assert np.array_equal(got.astype(np.int32), want)
+
+
+def edge_reads(tr):
+    rng = np.random.default_rng(9)
+    seqs = [tr["data"][tr["off"][i]:tr["off"][i + 1]] for i in range(40)]
+    reads = []
+    for i, s in enumerate(seqs):
+        a = int(rng.integers(0, 300))
+        ln = int(rng.integers(50, 600))
+        r = s[a:a + ln].copy()
+        if i % 2:
+            r = synth.revcomp(r)
+        if i % 5 == 0:
+            r[rng.integers(0, len(r), 3)] = ord("N")
+        if i % 7 == 0:
+            r = np.frombuffer(r.tobytes().upper(), np.uint8)
+        reads.append(r.tobytes())
+    reads += [
+        b"",                                   # empty record
+        b"ACGT" * 12,                          # 48 bases: short (A2)
+        b"ACGTTGCA" * 6 + b"AC",               # exactly 50 bases
+        b"N" * 64,                             # long enough, no good word
+        b"ACGTACGTAC" + b"N" * 50,             # 3 words: k = 0 replicates
+        b"acgu" * 20,                          # RNA alphabet, lower case
+        b"RYKMSWBDHVN" * 8,                    # IUPAC only
+        seqs[0].tobytes(),                     # full training sequence
+        synth.revcomp(seqs[1]).tobytes(),
+    ]
+    return reads
+
+
+def check_against_oracle(ctx, gm, om, anc, reads, mode=0, min_boot=0):
+    data, off = pack_sequences(reads)
+    res, boot = ctx.classify(gm, data, off, mode=mode, min_boot_words=min_boot, want_boot=True)
+    ref = om.classify(data, off, min_boot)
+    votes = om.votes(ref, anc)
+    assert np.array_equal(res["status"], ref["status"])
+    assert np.array_equal(res["genus"], ref["genus"])
+    ok = ref["status"] == 0
+    assert np.array_equal(res["n_words"][ok], ref["n_words"][ok])
+    assert np.array_equal(res["reversed"][ok], ref["reversed"][ok])
+    assert np.array_equal(boot[ok], ref["boot"][ok])
+    assert np.array_equal(bits(res["score"][ok]), bits(ref["score"][ok]))
+    d = anc.shape[1]
+    assert np.array_equal(res["votes"][ok][:, :d].astype(np.int32), votes[ok])
+    assert (res["votes"][:, d:] == 0).all()
+    assert (res["depth"][ok] == d).all()
+    return res
+
+
+def test_pack_planes(ctx, small):
+    tr, om, gm = small
+    reads = edge_reads(tr)
+    data, off = pack_sequences(reads)
+    pk = ctx.pack(data, off)
+    assert len(pk) == len(reads)
+    code = {ord(c): v for c, v in zip("ATUGCatugc", [0, 1, 1, 2, 3, 0, 1, 1, 2, 3])}
+    for i, r in enumerate(reads):
+        ln, codes, mask = pk.unpack(i, len(r))
+        assert ln == len(r)
+        for p, ch in enumerate(r):
+            valid = (mask[p // 32] >> (p % 32)) & 1
+            assert valid == (1 if ch in code else 0)
+            if valid:
+                assert (codes[p // 16] >> (2 * (p % 16))) & 3 == code[ch]
+    pk.free()
+
+
+def test_extract_words_and_orientation(ctx, small):
+    tr, om, gm = small
+    reads = edge_reads(tr)
+    data, off = pack_sequences(reads)
+    words, nw, rev = ctx.extract_words(gm, data, off)
+    ref = om.classify(data, off)
+    L = ora.lib()
+    for i, r in enumerate(reads):
+        if len(r) < 50:
+            assert nw[i] == 0
+            continue
+        w = ora.words(r)
+        if ref[i]["reversed"]:
+            w = np.array([L.rdp_revcomp_word(int(x)) for x in w[::-1]], np.int32)
+        assert nw[i] == len(w) == ref[i]["n_words"]
+        assert rev[i] == ref[i]["reversed"]
+        assert np.array_equal(words[off[i]:off[i] + nw[i]].astype(np.int32), w)
+
+
+def test_classify_edge_cases(ctx, small):
+    tr, om, gm = small
+    check_against_oracle(ctx, gm, om, tr["anc"], edge_reads(tr))
+
+
+def test_classify_empty_batch(ctx, small):
+    tr, om, gm = small
+    res = ctx.classify(gm, np.zeros(0, np.uint8), np.zeros(1, np.int64))
+    assert len(res) == 0
+
+
+def test_classify_min_boot_words(ctx, small):
+    tr, om, gm = small
+    check_against_oracle(ctx, gm, om, tr["anc"], edge_reads(tr)[:12], min_boot=5)
+    check_against_oracle(ctx, gm, om, tr["anc"], edge_reads(tr)[:12], min_boot=0)
+
+
+def test_classify_illumina_reads(ctx, small):
+    tr, om, gm = small
+    for paired in (False, True):
+        data, off, src = synth.synth_reads(31, tr, 400, paired=paired)
+        reads = [data[off[i]:off[i + 1]].tobytes() for i in range(400)]
+        res = check_against_oracle(ctx, gm, om, tr["anc"], reads)
+        assert (res["n_words"] == (486 if paired else 243)).mean() > 0.2      # some carry an 'n'
+        assert (res["genus"] == src).mean() > 0.5
+
+
+def test_classify_self_full_length(ctx, small):
+    """config 2 in miniature: classify the training set against its own model."""
+    tr, om, gm = small
+    reads = [tr["data"][tr["off"][i]:tr["off"][i + 1]].tobytes() for i in range(len(tr["genus"]))]
+    res = check_against_oracle(ctx, gm, om, tr["anc"], reads)
+    assert (res["genus"] == tr["genus"]).mean() >= 0.99
+
+
+def test_long_reads_every_bucket(ctx):
+    """reads of 1.4k .. 6.9k words exercise the 1024-thread and narrow-tile launches."""
+    tr = synth.synth16s(seed=77, seqs=24, genera=9, length=7000)
+    om = ora.Model(tr["data"], tr["off"], tr["genus"], tr["G"])
+    gm = ctx.train(tr["data"], tr["off"], tr["genus"], tr["G"])
+    gm.set_lineage(tr["anc"])
+    seqs = [tr["data"][tr["off"][i]:tr["off"][i + 1]] for i in range(24)]
+    reads = [s[:ln].tobytes() for s, ln in zip(seqs, [1400, 1790, 1830, 2500, 3590, 3650, 5000, 6300])]
+    reads.append(synth.revcomp(seqs[8][:6999]).tobytes())
+    reads.append(seqs[9][:300].tobytes())
+    check_against_oracle(ctx, gm, om, tr["anc"], reads)
+    too_long = np.tile(seqs[0], 2)[:7300].tobytes()
+    data, off = pack_sequences([too_long])
+    with pytest.raises(pg.PangeaError) as e:
+        ctx.classify(gm, data, off)
+    assert e.value.code == -6                                        # PG_ERANGE, not a silent truncation
+    om.free()
+    gm.free()
+
+
+def test_single_genus_and_no_lineage(ctx):
+    tr = synth.synth16s(seed=5, seqs=6, genera=1, length=300)
+    om = ora.Model(tr["data"], tr["off"], tr["genus"], 1)
+    gm = ctx.train(tr["data"], tr["off"], tr["genus"], 1)
+    reads = [tr["data"][tr["off"][i]:tr["off"][i + 1]][:200].tobytes() for i in range(6)]
+    data, off = pack_sequences(reads)
+    res, boot = ctx.classify(gm, data, off, want_boot=True)
+    assert (res["genus"] == 0).all() and (boot == 0).all()
+    assert (res["depth"] == 1).all() and (res["votes"][:, 0] == 100).all()
+    ref = om.classify(data, off)
+    assert np.array_equal(bits(res["score"]), bits(ref["score"]))
+    om.free()
+    gm.free()
+
+
+def test_train_rejects_bad_genus(ctx):
+    data, off = pack_sequences([b"ACGT" * 30, b"TTGA" * 30])
+    with pytest.raises(pg.PangeaError):
+        ctx.train(data, off, np.array([0, 5], np.int32), 2)
+
+
+def test_model_save_load_roundtrip(ctx, small, tmp_path):
+    tr, om, gm = small
+    p = tmp_path / "m.pgm"
+    gm.save(p, b"taxonomy-blob")
+    gm2, blob = ctx.model_load(p)
+    assert blob == b"taxonomy-blob"
+    assert gm2.G == gm.G and gm2.N == gm.N
+    a, b = gm.tables(), gm2.tables()
+    for x, y in zip(a, b):
+        assert np.array_equal(bits(x), bits(y))
+    check_against_oracle(ctx, gm2, om, tr["anc"], edge_reads(tr)[:10])
+    gm2.free()
+
+
+def test_model_replication_buffers(ctx, small):
+    """the multi-GPU path: copy the count buffers into an empty model, commit, same tables."""
+    import ctypes as C
+
+    tr, om, gm = small
+    gm2 = ctx.model_create(gm.G)
+    cudart = C.CDLL("libcudart.so.12")
+    cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    ctx.sync()
+    for (src, n), (dst, n2) in zip(gm.buffers(), gm2.buffers()):
+        assert n == n2
+        assert cudart.cudaMemcpy(dst, src, n, 3) == 0                # cudaMemcpyDeviceToDevice
+    gm2.commit()
+    gm2.set_lineage(tr["anc"])
+    assert gm2.N == gm.N
+    for x, y in zip(gm.tables(), gm2.tables()):
+        assert np.array_equal(bits(x), bits(y))
+    gm2.free()
+
+
+def test_real_16s_subset(ctx):
+    """real type-strain 16S (subset of validation_dataset/rdp_download_373seqs.fa kept as a
+    fixture): train with genus = 2nd header token, classify every sequence and windows of it."""
+    from pathlib import Path
+
+    fa = Path(__file__).parent / "golden" / "rdp_373_subset.fa"
+    ids, hdr, seqs = synth.read_fasta(fa)
+    names = sorted({h.split()[1] for h in hdr})
+    gi = {n: i for i, n in enumerate(names)}
+    genus = np.array([gi[h.split()[1]] for h in hdr], np.int32)
+    data, off = pack_sequences(seqs)
+    om = ora.Model(data, off, genus, len(names))
+    gm = ctx.train(data, off, genus, len(names))
+    anc = np.stack([np.zeros(len(names), np.int32), 1 + np.arange(len(names), dtype=np.int32)], axis=1)
+    gm.set_lineage(anc)
+    m, nw, M, N = gm.counts()
+    rm, rnw, rM, rN = om.counts()
+    assert np.array_equal(m, rm) and np.array_equal(nw, rnw) and np.array_equal(M, rM) and N == rN
+    assert np.array_equal(bits(gm.tables()[2]), bits(om.tables()[2]))
+    reads = list(seqs) + [s[100:350] for s in seqs] + [s[-400:] for s in seqs]
+    check_against_oracle(ctx, gm, om, anc, reads)
+    om.free()
+    gm.free()
