@@ -224,8 +224,12 @@ def main():
     G = tr["G"]
 
     ctx = pg.Context(local)
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the library, the NCCL ops and the timing events all
+    # run on it, so the CUDA events bracket exactly the work that was launched
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    assert stream.cuda_stream != 0
 
     # ---- model: rank 0 trains on its GPU, the integer counts are NCCL-broadcast once,
     # every rank derives the fp32 table locally (identical bits, no table broadcast needed)

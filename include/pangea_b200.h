@@ -61,7 +61,9 @@ pg_ctx     *pg_init(int device);
 void        pg_shutdown(pg_ctx *ctx);
 const char *pg_last_error(const pg_ctx *ctx);
 /* Launch everything on the caller's CUDA stream (cudaStream_t / CUstream, e.g.
- * torch.cuda.current_stream().cuda_stream).  NULL = the context's own stream. */
+ * torch.cuda.current_stream().cuda_stream).  NULL = the context's own
+ * non-blocking stream; pass cudaStreamLegacy ((void*)1) for the legacy default
+ * stream, whose handle is also 0. */
 int         pg_set_stream(pg_ctx *ctx, void *cuda_stream);
 int         pg_sync(pg_ctx *ctx);
 /* Number of kernels this context has launched so far (bench "gpu_launches"). */

@@ -44,21 +44,41 @@ __device__ __forceinline__ int32_t jr_next_int(unsigned long long &s, int32_t n)
 }
 
 // One thread per distinct n: the 100 x k draws of java.util.Random(1).nextInt(n),
-// each replicate padded to a multiple of 8 with index n (the all-zero row).
-__global__ void k_boot_indices(const int32_t *__restrict__ ns, const int32_t *__restrict__ offs, int cnt,
-                               int min_boot, uint16_t *__restrict__ pool)
+// stored as shared-memory byte offsets (row * 128, the row pitch of a 32-genus
+// block) so the inner loop needs one IADD per draw.  Each replicate is padded to
+// nb = ceil(k/4) batches of 4 draws with row n (the all-zero row).  The IL = 32/LPR
+// replicates that the groups of one warp walk at the same time are interleaved
+// batch by batch, so the warp's list load is one contiguous 16*IL-byte segment:
+//     uint4 index of (task, batch) = ((task / IL) * nb + batch) * IL + task % IL
+// Two zero-row batches per lane follow the last block for the pipelined read-ahead.
+#define PG_ROW_PITCH 128u
+__host__ __device__ static inline size_t pg_boot_list_entries(int k, int il)
+{
+    const int nb = (k + 3) >> 2;
+    const int tblocks = (PG_NUM_BOOT + il - 1) / il;
+    return ((size_t)tblocks * nb + 2) * il * 4;            // uint32 entries
+}
+__global__ void k_boot_indices(const int32_t *__restrict__ ns, const int32_t *__restrict__ offs,
+                               const int32_t *__restrict__ ils, int cnt, int min_boot,
+                               uint32_t *__restrict__ pool)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= cnt) return;
-    const int n = ns[t];
+    const int n = ns[t], il = ils[t];
     int k = n >> 3;
     if (k < min_boot) k = min_boot;
-    const int kpad = (k + 7) & ~7;
-    uint16_t *out = pool + offs[t];
+    const int nb = (k + 3) >> 2;
+    uint32_t *out = pool + offs[t];
+    const size_t total = pg_boot_list_entries(k, il);
+    for (size_t e = 0; e < total; e++) out[e] = (uint32_t)n * PG_ROW_PITCH;
     unsigned long long s = (1ULL ^ JR_MULT) & JR_MASK;          // setSeed(1)
-    for (int run = 0; run < PG_NUM_BOOT; run++)
-        for (int j = 0; j < kpad; j++)
-            out[run * kpad + j] = (uint16_t)((j < k && n > 0) ? jr_next_int(s, n) : n);
+    for (int run = 0; run < PG_NUM_BOOT; run++) {
+        const size_t base = ((size_t)(run / il) * nb * il + (run % il)) * 4;
+        for (int j = 0; j < k; j++) {
+            const uint32_t r = n > 0 ? (uint32_t)jr_next_int(s, n) : 0u;
+            out[base + (size_t)(j >> 2) * il * 4 + (j & 3)] = r * PG_ROW_PITCH;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ keys
@@ -92,16 +112,27 @@ __device__ __forceinline__ void pg_cp_async_wait_all()
 
 // ------------------------------------------------------------------ K4 strict
 
+#define PG_ADD4(v)                                                              \
+    a0 = __fadd_rn(a0, (v).x); a1 = __fadd_rn(a1, (v).y);                       \
+    a2 = __fadd_rn(a2, (v).z); a3 = __fadd_rn(a3, (v).w);
+
+// Warp 0 computes the A7 full sum with one genus per lane (the longest chain of
+// the CTA: n dependent adds); the other warps split into groups of LPR lanes,
+// each group owning one A8 replicate at a time.  The replicate loop is software
+// pipelined two 4-draw batches deep (offsets one batch further), so the LDS and
+// list-load latencies overlap the FADD chains of the previous batch.
 template <int LPR, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK >= 1024) ? 1 : ((BLOCK >= 512) ? 2 : 4))
+__global__ void __launch_bounds__(BLOCK, (BLOCK > 512) ? 1 : ((BLOCK > 256) ? 2 : 5))
 k_classify_strict(const float *__restrict__ table, const uint16_t *__restrict__ words,
                   const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
                   const int32_t *__restrict__ order, int64_t read0,
-                  const uint16_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off,
+                  const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off,
                   int min_boot, unsigned long long *__restrict__ best)
 {
-    constexpr int TG = 4 * LPR;
-    constexpr int NG = BLOCK / LPR;
+    constexpr int TG = 4 * LPR;                    // genera per CTA
+    constexpr int NGR = (BLOCK - 32) / LPR;        // replicate groups
+    constexpr int SH = (LPR == 8) ? 0 : ((LPR == 4) ? 1 : 2);   // list offsets are row*128
+    constexpr int IL = 32 / LPR;                   // replicates interleaved in the list
     extern __shared__ float4 sV[];                 // (n+1) rows x LPR float4; row n is all zero
 
     const int tid = threadIdx.x;
@@ -110,6 +141,7 @@ k_classify_strict(const float *__restrict__ table, const uint16_t *__restrict__ 
     const int gbase = blockIdx.y * TG;
     const float *tbase = table + ((size_t)(gbase >> 5) * PG_NWORDS) * PG_GENUS_TILE + (gbase & 31);
     const uint16_t *w = words + off[read];
+    unsigned long long *mybest = best + (size_t)(read - read0) * (PG_NUM_BOOT + 1);
 
     // ---- A4: stage the read's rows for this genus block
     for (int c = tid; c < n * LPR; c += BLOCK) {
@@ -120,67 +152,72 @@ k_classify_strict(const float *__restrict__ table, const uint16_t *__restrict__ 
     pg_cp_async_wait_all();
     __syncthreads();
 
-    const int group = tid / LPR, l = tid % LPR;
+    if (tid < 32) {
+        // ---- A7: score[g] = ((0 + v[0][g]) + v[1][g]) + ... in word order; lane = genus
+        if (tid >= TG) return;
+        constexpr unsigned fmask = (TG == 32) ? 0xffffffffu : ((1u << TG) - 1u);
+        const float *col = reinterpret_cast<const float *>(sV) + tid;
+        float a = 0.f;
+        int j = 0;
+        for (; j + 16 <= n; j += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) v[u] = col[(j + u) * TG];
+#pragma unroll
+            for (int u = 0; u < 16; u++) a = __fadd_rn(a, v[u]);
+        }
+        for (; j < n; j++) a = __fadd_rn(a, col[j * TG]);
+        const uint32_t ob = pg_ord(a);
+        const uint32_t gm = __reduce_max_sync(fmask, ob);
+        const uint32_t gi = __reduce_min_sync(fmask, ob == gm ? (uint32_t)(gbase + tid) : 0xFFFFFFFFu);
+        if (tid == 0) atomicMax(mybest, ((unsigned long long)gm << 32) | (unsigned long long)(0xFFFFFFFFu - gi));
+        return;
+    }
+
+    // ---- A8: bootstrap replicates
+    const int t2 = tid - 32;
+    const int group = t2 / LPR, l = t2 % LPR;
     const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (((tid & 31) / LPR) * LPR));
     int k = n >> 3;
     if (k < min_boot) k = min_boot;
-    const int kpad = (k + 7) & ~7;
-    const uint16_t *bl = boot_pool + boot_off[n];
-    const float4 *row = sV + l;
+    const int nb = (k + 3) >> 2;                   // 4-draw batches per replicate
+    const uint4 *lists = reinterpret_cast<const uint4 *>(boot_pool + boot_off[n]);
+    const char *lane_base = reinterpret_cast<const char *>(sV) + l * 16;
+    const uint32_t g0 = (uint32_t)(gbase + l * 4);
+#define PG_ROW(o) (*reinterpret_cast<const float4 *>(lane_base + ((o) >> SH)))
 
-    // task 0 = A7 full sum (group 0 only); tasks 1..100 = A8 replicates.
-    int task = group;
-    const int stride = (group == 0) ? (PG_NUM_BOOT + 1) : (NG - 1);
-    for (; task <= PG_NUM_BOOT; task += stride) {
+    for (int task = group; task < PG_NUM_BOOT; task += NGR) {
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        if (task == 0) {
-            const int n8 = n & ~7;
-            int j = 0;
-            for (; j < n8; j += 8) {
-                float4 v[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = row[(j + u) * LPR];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    a0 = __fadd_rn(a0, v[u].x); a1 = __fadd_rn(a1, v[u].y);
-                    a2 = __fadd_rn(a2, v[u].z); a3 = __fadd_rn(a3, v[u].w);
-                }
+        if (nb > 0) {
+            const uint4 *lp = lists + (size_t)(task / IL) * nb * IL + (task % IL);
+            uint4 qa = __ldg(lp), qb = __ldg(lp + IL);
+            float4 x0 = PG_ROW(qa.x), x1 = PG_ROW(qa.y), x2 = PG_ROW(qa.z), x3 = PG_ROW(qa.w);
+            float4 y0, y1, y2, y3;
+            int b = 0;
+            while (b + 1 < nb) {
+                y0 = PG_ROW(qb.x); y1 = PG_ROW(qb.y); y2 = PG_ROW(qb.z); y3 = PG_ROW(qb.w);
+                qa = __ldg(lp + (b + 2) * IL);
+                PG_ADD4(x0) PG_ADD4(x1) PG_ADD4(x2) PG_ADD4(x3)
+                x0 = PG_ROW(qa.x); x1 = PG_ROW(qa.y); x2 = PG_ROW(qa.z); x3 = PG_ROW(qa.w);
+                qb = __ldg(lp + (b + 3) * IL);
+                PG_ADD4(y0) PG_ADD4(y1) PG_ADD4(y2) PG_ADD4(y3)
+                b += 2;
             }
-            for (; j < n; j++) {
-                float4 v = row[j * LPR];
-                a0 = __fadd_rn(a0, v.x); a1 = __fadd_rn(a1, v.y);
-                a2 = __fadd_rn(a2, v.z); a3 = __fadd_rn(a3, v.w);
-            }
-        } else {
-            const uint4 *lp = reinterpret_cast<const uint4 *>(bl + (size_t)(task - 1) * kpad);
-            for (int j = 0; j < kpad; j += 8) {
-                const uint4 q = __ldg(lp + (j >> 3));
-                float4 v[8];
-                v[0] = row[(q.x & 0xFFFFu) * LPR]; v[1] = row[(q.x >> 16) * LPR];
-                v[2] = row[(q.y & 0xFFFFu) * LPR]; v[3] = row[(q.y >> 16) * LPR];
-                v[4] = row[(q.z & 0xFFFFu) * LPR]; v[5] = row[(q.z >> 16) * LPR];
-                v[6] = row[(q.w & 0xFFFFu) * LPR]; v[7] = row[(q.w >> 16) * LPR];
-#pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    a0 = __fadd_rn(a0, v[u].x); a1 = __fadd_rn(a1, v[u].y);
-                    a2 = __fadd_rn(a2, v[u].z); a3 = __fadd_rn(a3, v[u].w);
-                }
-            }
+            if (b < nb) { PG_ADD4(x0) PG_ADD4(x1) PG_ADD4(x2) PG_ADD4(x3) }
         }
-        // first strict max in ascending genus index, inside the lane then across the group
-        const uint32_t g0 = (uint32_t)(gbase + l * 4);
-        unsigned long long key = pg_key(a0, g0);
-        unsigned long long k1 = pg_key(a1, g0 + 1), k2 = pg_key(a2, g0 + 2), k3 = pg_key(a3, g0 + 3);
-        key = key > k1 ? key : k1;
-        k2 = k2 > k3 ? k2 : k3;
-        key = key > k2 ? key : k2;
-#pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1) {
-            unsigned long long other = __shfl_xor_sync(gmask, key, o);
-            key = key > other ? key : other;
-        }
-        if (l == 0) atomicMax(best + (size_t)(read - read0) * (PG_NUM_BOOT + 1) + task, key);
+        // first strict max in ascending genus index: inside the lane, then across the group
+        float bv = a0;
+        uint32_t bi = g0;
+        if (a1 > bv) { bv = a1; bi = g0 + 1; }
+        if (a2 > bv) { bv = a2; bi = g0 + 2; }
+        if (a3 > bv) { bv = a3; bi = g0 + 3; }
+        const uint32_t ob = pg_ord(bv);
+        const uint32_t gm = __reduce_max_sync(gmask, ob);
+        const uint32_t gi = __reduce_min_sync(gmask, ob == gm ? bi : 0xFFFFFFFFu);
+        if (l == 0)
+            atomicMax(mybest + 1 + task, ((unsigned long long)gm << 32) | (unsigned long long)(0xFFFFFFFFu - gi));
     }
+#undef PG_ROW
 }
 
 // ------------------------------------------------------------------ K5 vote (A9)
@@ -253,11 +290,18 @@ k_vote(const unsigned long long *__restrict__ best, int64_t nreads, int64_t read
 // Reads are bucketed by word count so each launch sizes its shared memory (and so
 // its CTAs/SM) for the reads it actually carries.
 struct Bucket { int nmax; int lpr; int block; };
+// block = 32 (full-sum warp) + groups*LPR: 20 groups x 5 replicates, 52 x 2, 100 x 1.
 static const Bucket kBuckets[] = {
-    {215, 8, 256},  {250, 8, 256},  {290, 8, 256},  {350, 8, 256},  {440, 8, 256},
-    {590, 8, 256},  {900, 8, 512},  {1800, 8, 1024}, {3600, 4, 1024}, {PG_MAX_WORDS, 2, 1024},
+    {215, 8, 192},  {250, 8, 192},  {290, 8, 192},  {350, 8, 192},  {440, 8, 192},
+    {590, 8, 192},  {900, 8, 448},  {1800, 8, 832}, {3600, 4, 832}, {PG_MAX_WORDS, 2, 832},
 };
 static const int kNumBuckets = (int)(sizeof(kBuckets) / sizeof(kBuckets[0]));
+static const Bucket &bucket_of(int n)
+{
+    int b = 0;
+    while (kBuckets[b].nmax < n) b++;
+    return kBuckets[b];
+}
 
 template <int LPR, int BLOCK>
 static int launch_strict(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, unsigned nblocks_g, size_t smem,
@@ -290,26 +334,26 @@ static int ensure_boot_lists(pg_ctx *ctx, const std::vector<int> &need_n, int mi
         PG_CUDA(ctx, cudaMalloc(&ctx->d_boot_off, (PG_MAX_WORDS + 1) * sizeof(int32_t)));
         ctx->h_boot_off.assign(PG_MAX_WORDS + 1, -1);
     }
-    std::vector<int32_t> ns, offs;
+    std::vector<int32_t> ns, offs, ils;
     size_t used = ctx->boot_used;
     for (int n : need_n) {
         if (ctx->h_boot_off[n] >= 0) continue;
         int k = n >> 3;
         if (k < min_boot) k = min_boot;
-        int kpad = (k + 7) & ~7;
         ns.push_back(n);
         offs.push_back((int32_t)used);
+        ils.push_back(32 / bucket_of(n).lpr);
         ctx->h_boot_off[n] = (int32_t)used;
-        used += (size_t)PG_NUM_BOOT * kpad + 8;     // +8 keeps even k==0 lists distinct and aligned
+        used += (pg_boot_list_entries(k, ils.back()) + 31) & ~(size_t)31;   // keep every list 128-byte aligned
     }
     if (ns.empty()) return PG_OK;
     if (used > ctx->boot_cap) {
         size_t cap = used * 2 + 4096;
-        uint16_t *np = NULL;
+        uint32_t *np = NULL;
         PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        PG_CUDA(ctx, cudaMalloc(&np, cap * sizeof(uint16_t)));
+        PG_CUDA(ctx, cudaMalloc(&np, cap * sizeof(uint32_t)));
         if (ctx->d_boot_pool) {
-            PG_CUDA(ctx, cudaMemcpy(np, ctx->d_boot_pool, ctx->boot_used * sizeof(uint16_t), cudaMemcpyDeviceToDevice));
+            PG_CUDA(ctx, cudaMemcpy(np, ctx->d_boot_pool, ctx->boot_used * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
             PG_CUDA(ctx, cudaFree(ctx->d_boot_pool));
         }
         ctx->d_boot_pool = np;
@@ -317,14 +361,15 @@ static int ensure_boot_lists(pg_ctx *ctx, const std::vector<int> &need_n, int mi
     }
     ctx->boot_used = used;
     int cnt = (int)ns.size();
-    PG_TRY(pg_scratch(ctx, &ctx->s_boot, (size_t)cnt * 8));
-    int32_t *d_ns = (int32_t *)ctx->s_boot.p, *d_offs = d_ns + cnt;
+    PG_TRY(pg_scratch(ctx, &ctx->s_boot, (size_t)cnt * 12));
+    int32_t *d_ns = (int32_t *)ctx->s_boot.p, *d_offs = d_ns + cnt, *d_ils = d_offs + cnt;
+    PG_CUDA(ctx, cudaMemcpyAsync(d_ils, ils.data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
     // pageable source: cudaMemcpyAsync stages it before returning
     PG_CUDA(ctx, cudaMemcpyAsync(d_ns, ns.data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
     PG_CUDA(ctx, cudaMemcpyAsync(d_offs, offs.data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
     PG_CUDA(ctx, cudaMemcpyAsync(ctx->d_boot_off, ctx->h_boot_off.data(), (PG_MAX_WORDS + 1) * sizeof(int32_t),
                                  cudaMemcpyHostToDevice, ctx->stream));
-    k_boot_indices<<<(cnt + 31) / 32, 32, 0, ctx->stream>>>(d_ns, d_offs, cnt, min_boot, ctx->d_boot_pool);
+    k_boot_indices<<<(cnt + 31) / 32, 32, 0, ctx->stream>>>(d_ns, d_offs, d_ils, cnt, min_boot, ctx->d_boot_pool);
     PG_LAUNCHED(ctx);
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // ns/offs are stack vectors
     return PG_OK;
@@ -417,16 +462,16 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
                 const unsigned ngb = (unsigned)((md->G + TG - 1) / TG);
                 const size_t smem = (size_t)(nmax + 1) * bk.lpr * 16;
                 int rc;
-                if (bk.lpr == 8 && bk.block == 256)
-                    rc = launch_strict<8, 256>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
-                else if (bk.lpr == 8 && bk.block == 512)
-                    rc = launch_strict<8, 512>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+                if (bk.lpr == 8 && bk.block == 192)
+                    rc = launch_strict<8, 192>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+                else if (bk.lpr == 8 && bk.block == 448)
+                    rc = launch_strict<8, 448>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
                 else if (bk.lpr == 8)
-                    rc = launch_strict<8, 1024>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+                    rc = launch_strict<8, 832>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
                 else if (bk.lpr == 4)
-                    rc = launch_strict<4, 1024>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+                    rc = launch_strict<4, 832>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
                 else
-                    rc = launch_strict<2, 1024>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+                    rc = launch_strict<2, 832>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
                 PG_TRY(rc);
             }
             PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
@@ -539,10 +584,13 @@ extern "C" int pg_boot_indices(pg_ctx *ctx, int32_t n, int32_t min_boot_words, u
     PG_TRY(ensure_boot_lists(ctx, need, min_boot_words));
     int k = n >> 3;
     if (k < min_boot_words) k = min_boot_words;
-    const int kpad = (k + 7) & ~7;
-    std::vector<uint16_t> tmp((size_t)PG_NUM_BOOT * kpad + 8);
-    PG_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->d_boot_pool + ctx->h_boot_off[n], tmp.size() * 2, cudaMemcpyDeviceToHost));
+    const int nb = (k + 3) >> 2, il = 32 / bucket_of(n).lpr;
+    std::vector<uint32_t> tmp(pg_boot_list_entries(k, il));
+    PG_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->d_boot_pool + ctx->h_boot_off[n], tmp.size() * 4, cudaMemcpyDeviceToHost));
     for (int run = 0; run < PG_NUM_BOOT; run++)
-        for (int j = 0; j < k; j++) out_host[run * k + j] = tmp[(size_t)run * kpad + j];
+        for (int j = 0; j < k; j++) {
+            size_t e = ((size_t)(run / il) * nb * il + (run % il)) * 4 + (size_t)(j >> 2) * il * 4 + (j & 3);
+            out_host[run * k + j] = (uint16_t)(tmp[e] / PG_ROW_PITCH);
+        }
     return PG_OK;
 }

@@ -20,10 +20,10 @@ struct pg_ctx {
     mutable char err[512];
     int64_t      launches;
 
-    // java.util.Random(1) sample lists, cached per n (row A8): pool of uint16,
+    // java.util.Random(1) sample lists, cached per n (row A8): pool of uint32 smem offsets,
     // h_boot_off[n] = offset of the list for n words (or -1), mirrored on device.
-    uint16_t            *d_boot_pool;
-    size_t               boot_cap, boot_used;     // uint16 units
+    uint32_t            *d_boot_pool;
+    size_t               boot_cap, boot_used;     // uint32 units
     int32_t             *d_boot_off;              // [PG_MAX_WORDS+1]
     std::vector<int32_t> h_boot_off;
     int                  boot_min_words;
