@@ -156,6 +156,13 @@ typedef struct {
     int32_t reserved[6];
 } pg_classify_opts;
 
+/* 1 if the model's quantised table certifies every deficit (mode 1 is then the
+ * certified path; otherwise mode 1 silently runs the strict kernels). */
+int pg_model_certifiable(const pg_model *m);
+/* How the reads of the last pg_classify*() call were routed: through the certified
+ * kernels, through the strict kernels, and handed back from certified to strict. */
+int pg_classify_stats(const pg_ctx *ctx, int64_t *certified_reads, int64_t *strict_reads, int64_t *handed_back);
+
 /* K3-K5: word extraction + orientation, gather-sum + 100 bootstraps, argmax,
  * vote.  results: nreads records (host for pg_classify, device for *_dev).
  * boot_winners (optional, may be NULL): nreads*100 int32 genus index per

@@ -1,18 +1,495 @@
-// pg_certified.cu -- certified-margin fast path (mode 1).  Placeholder: the
-// quantised table is not derived yet and mode 1 is refused.
-#include "pg_internal.cuh"
+// pg_certified.cu -- certified-margin fast path for K4/K5 (classify mode 1).
+//
+// Same results as strict mode (and so as the reference order of operations,
+// SURVEY.md rows A7-A9), obtained with half the shared-memory traffic:
+//
+//  * At training time every table entry is restated as its DEFICIT below the best
+//    genus of the same word, D[w][g] = max_g' V[w][g'] - V[w][g] >= 0, quantised
+//    downwards to q = floor(D * 128) (12 bits).  For a multiset of draws the row
+//    maxima are common to all genera, so  argmax_g sum V  ==  argmin_g sum D.
+//  * Integer sums are exact and order-free: with Sq = sum q,
+//        Sq/128  <=  sum D  <  (Sq + terms)/128 .
+//  * The reference's fp32 running sum F differs from the real sum S by at most
+//        E = gamma(terms-1) * terms * max|V|        (gamma(m) = m u / (1 - m u), u = 2^-24).
+//    If g* is the reference's winner and b the genus with the smallest Sq, then
+//    S(g*) >= F(g*) - E >= F(b) - E >= S(b) - 2E, hence
+//        Sq(g*)  <  Sq(b) + terms + 256 E .
+//    Every genus outside that margin is PROVABLY not the reference's winner.
+//  * Survivors (almost always one) are re-evaluated in strict fp32 order straight
+//    from the fp32 table; ties resolve to the lowest genus index as in the reference.
+//
+// Phase 1 (k_classify_q): one CTA per (read, 64-genus block); packed 2 x 16-bit
+// adds, four per LDS.128; a per-(read, replicate) champion slot is maintained with
+// 64-bit atomicMin and near-ties are appended to a short per-read list.
+// Phase 2 (k_resolve): one warp per read; strict re-check of survivors, then the A9 vote.
+// Reads whose list overflows are handed back to the strict kernels.
+#include "pg_classify_common.cuh"
 
-struct Bucket { int nmax; int lpr; int block; };
+#define PG_Q_SCALE 128.0            // units per nat
+#define PG_Q_MAX   4095             // 12-bit field: 16 rows x 4095 < 65536
+#define PG_CANDCAP 128              // near-tie entries kept per read
+#define PG_CHAMP_INIT 0xFFFFFFFFFFFFFFFFULL
+
+// ------------------------------------------------------------------ derive
+
+// one warp per word: maximum over the real genera, and global max |V|
+__global__ void k_rowmax(const float *__restrict__ table, int G, int ntile, float *__restrict__ rowmax,
+                         unsigned int *__restrict__ vmax_bits)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= PG_NWORDS) return;
+    float mx = __int_as_float(0xff800000), amax = 0.f;
+    for (int t = 0; t < ntile; t++) {
+        int g = t * 32 + lane;
+        if (g < G) {
+            float v = table[((size_t)t * PG_NWORDS + w) * PG_GENUS_TILE + lane];
+            mx = fmaxf(mx, v);
+            amax = fmaxf(amax, fabsf(v));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    }
+    if (lane == 0) {
+        rowmax[w] = mx;
+        atomicMax(vmax_bits, __float_as_uint(amax));      // non-negative floats order as uints
+    }
+}
+
+// one thread per (tile64, word, genus-in-tile): exact in double (difference of two
+// fp32 values, power-of-two scale), rounded DOWN.
+__global__ void k_quantise(const float *__restrict__ table, const float *__restrict__ rowmax, int G,
+                           size_t total, uint16_t *__restrict__ q, unsigned int *__restrict__ qmax)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int l = (int)(idx & 63);
+    const int w = (int)((idx >> 6) & (PG_NWORDS - 1));
+    const int t64 = (int)(idx >> 22);
+    const int g = t64 * 64 + l;
+    unsigned int v = PG_Q_MAX;
+    if (g < G) {
+        const float x = table[((size_t)(g >> 5) * PG_NWORDS + w) * PG_GENUS_TILE + (g & 31)];
+        const double d = ((double)rowmax[w] - (double)x) * PG_Q_SCALE;
+        const double f = floor(d);
+        unsigned int u = f >= 4.0e9 ? 0xFFFFFFFFu : (unsigned int)f;
+        atomicMax(qmax, u);
+        v = u > PG_Q_MAX ? PG_Q_MAX : u;
+    }
+    q[idx] = (uint16_t)v;
+}
 
 int pg_model_derive_quantised(pg_model *md)
 {
-    (void)md;
+    pg_ctx *ctx = md->ctx;
+    md->ntile64 = (md->G + 63) / 64;
+    md->q_ok = false;
+    const size_t cells = (size_t)md->ntile64 * PG_NWORDS * 64;
+    if (!md->d_qtable) {
+        cudaError_t e;
+        if ((e = cudaMalloc(&md->d_qtable, cells * 2)) != cudaSuccess ||
+            (e = cudaMalloc(&md->d_rowmax, PG_NWORDS * 4)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return pg_fail(ctx, PG_ENOMEM, "quantised table allocation failed: %s", cudaGetErrorString(e));
+        }
+    }
+    unsigned int *d_stat = NULL;
+    PG_CUDA(ctx, cudaMalloc(&d_stat, 8));
+    PG_CUDA(ctx, cudaMemsetAsync(d_stat, 0, 8, ctx->stream));
+    k_rowmax<<<PG_NWORDS / 8, 256, 0, ctx->stream>>>(md->d_table, md->G, md->ntile, md->d_rowmax, d_stat);
+    PG_LAUNCHED(ctx);
+    k_quantise<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(md->d_table, md->d_rowmax, md->G, cells,
+                                                                         md->d_qtable, d_stat + 1);
+    PG_LAUNCHED(ctx);
+    unsigned int stat[2];
+    PG_CUDA(ctx, cudaMemcpyAsync(stat, d_stat, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_stat);
+    float vm;
+    memcpy(&vm, &stat[0], 4);
+    md->vmax = (double)vm;
+    md->q_ok = stat[1] <= PG_Q_MAX;      // no entry was clamped: upper bounds hold for every genus
     return PG_OK;
 }
 
-int pg_classify_certified_launch(pg_ctx *ctx, const pg_model *, const Bucket &, unsigned, int,
-                                 const uint16_t *, const int64_t *, const int32_t *, const int32_t *, int64_t, int,
-                                 unsigned long long *)
+// ------------------------------------------------------------------ shared device pieces
+
+// margin in quantisation units: terms (floor error) + 2E*128 (fp32 order error) + 1
+__device__ __forceinline__ uint32_t pg_margin(int terms, double vmax)
 {
-    return pg_fail(ctx, PG_EINVAL, "classify mode 1 (certified) is not built yet");
+    if (terms <= 1) return (uint32_t)terms + 1u;
+    const double u = 5.9604644775390625e-08;                 // 2^-24
+    const double m = (double)(terms - 1) * u;
+    const double E = m / (1.0 - m) * (double)terms * vmax * 1.0001;
+    return (uint32_t)terms + (uint32_t)ceil(2.0 * E * PG_Q_SCALE) + 1u;
+}
+
+__device__ __forceinline__ void pg_emit(unsigned int *ncand, unsigned long long *cand, int task, uint32_t genus,
+                                        uint32_t sum)
+{
+    const unsigned int slot = atomicAdd(ncand, 1u);
+    if (slot < PG_CANDCAP)
+        cand[slot] = ((unsigned long long)task << 56) | ((unsigned long long)genus << 32) | sum;
+}
+
+// After a task's sums are known: update the champion slot, append near-ties.
+//   sums[i] belongs to genus genus0+i; `mask` = the lanes sharing this task.
+template <int NV>
+__device__ __forceinline__ void pg_task_epilogue(unsigned mask, bool leader, int leader_lane, const uint32_t *sums,
+                                                 uint32_t genus0, int G, int task, uint32_t margin,
+                                                 unsigned long long *champ_slot, unsigned int *ncand,
+                                                 unsigned long long *cand)
+{
+    uint32_t lmin = 0xFFFFFFFFu, lgen = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const uint32_t g = genus0 + i;
+        const uint32_t s = (int)g < G ? sums[i] : 0xFFFFFFFFu;
+        if (s < lmin) { lmin = s; lgen = g; }
+    }
+    const uint32_t bm = __reduce_min_sync(mask, lmin);
+    const uint32_t bg = __reduce_min_sync(mask, lmin == bm ? lgen : 0xFFFFFFFFu);
+    const unsigned long long mine = ((unsigned long long)bm << 32) | bg;
+    unsigned long long old = 0;
+    if (leader) old = atomicMin(champ_slot, mine);
+    old = __shfl_sync(mask, old, leader_lane);
+    const bool took = mine < old;                              // this block holds the new champion
+    const unsigned long long cursum = (took ? mine : old) >> 32;
+    const unsigned long long thr = cursum + margin;
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        const uint32_t g = genus0 + i;
+        if ((int)g < G && (unsigned long long)sums[i] <= thr && !(took && g == bg)) pg_emit(ncand, cand, task, g, sums[i]);
+    }
+    // the displaced champion stays a candidate if it is within the margin of the new one
+    if (leader && took && old != PG_CHAMP_INIT && (old >> 32) <= (unsigned long long)bm + margin)
+        pg_emit(ncand, cand, task, (uint32_t)old, (uint32_t)(old >> 32));
+}
+
+// ------------------------------------------------------------------ phase 1
+
+#define PG_QADD4(v) c0 += (v).x; c1 += (v).y; c2 += (v).z; c3 += (v).w;
+#define PG_QSPILL()                                                                   \
+    s0 += c0 & 0xFFFFu; s1 += c0 >> 16; s2 += c1 & 0xFFFFu; s3 += c1 >> 16;           \
+    s4 += c2 & 0xFFFFu; s5 += c2 >> 16; s6 += c3 & 0xFFFFu; s7 += c3 >> 16;           \
+    c0 = c1 = c2 = c3 = 0u;
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK > 512) ? 1 : ((BLOCK > 256) ? 2 : 5))
+k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
+             const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
+             const uint8_t *__restrict__ flags, const int32_t *__restrict__ order, int64_t read0,
+             const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot, int G,
+             double vmax, unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand,
+             unsigned long long *__restrict__ cand)
+{
+    constexpr int LPR = 8;                          // lanes per 128-byte row (64 genera x 16 bit)
+    constexpr int NGR = (BLOCK - 32) / LPR;
+    constexpr int IL = 4;
+    extern __shared__ uint4 sQ[];                   // (n+1) rows x 8 uint4; row n is all zero
+
+    const int tid = threadIdx.x;
+    const int64_t read = order[blockIdx.x];
+    if (flags[2 * read + 1]) return;                // short read (A2)
+    const int n = nwords[read];
+    if (n == 0) return;                             // no word: phase 2 writes genus 0 directly
+    const int gbase = blockIdx.y * 64;
+    const uint16_t *tbase = qtable + (size_t)blockIdx.y * PG_NWORDS * 64;
+    const uint16_t *w = words + off[read];
+    const size_t rc = (size_t)(read - read0);
+    unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
+    unsigned int *mync = ncand + rc;
+    unsigned long long *mycand = cand + rc * PG_CANDCAP;
+
+    for (int c = tid; c < n * LPR; c += BLOCK) {
+        const int r = c / LPR, l = c % LPR;
+        pg_cp_async16(&sQ[c], tbase + (size_t)w[r] * 64 + l * 8);
+    }
+    if (tid < LPR) sQ[n * LPR + tid] = make_uint4(0u, 0u, 0u, 0u);
+    pg_cp_async_wait_all();
+    __syncthreads();
+
+    if (tid < 32) {
+        // ---- full sum (task 0): lane = one packed pair of genera, 16 rows per spill
+        const uint32_t *col = reinterpret_cast<const uint32_t *>(sQ) + tid;
+        uint32_t lo = 0u, hi = 0u;
+        int j = 0;
+        for (; j + 16 <= n; j += 16) {
+            uint32_t v[16], c = 0u;
+#pragma unroll
+            for (int u = 0; u < 16; u++) v[u] = col[(j + u) * 32];
+#pragma unroll
+            for (int u = 0; u < 16; u++) c += v[u];
+            lo += c & 0xFFFFu;
+            hi += c >> 16;
+        }
+        uint32_t c = 0u;
+        for (; j < n; j++) c += col[j * 32];
+        lo += c & 0xFFFFu;
+        hi += c >> 16;
+        const uint32_t sums[2] = {lo, hi};
+        pg_task_epilogue<2>(0xffffffffu, tid == 0, 0, sums, (uint32_t)(gbase + 2 * tid), G, 0, pg_margin(n, vmax),
+                            mychamp, mync, mycand);
+        return;
+    }
+
+    // ---- replicates (tasks 1..100)
+    int k = n >> 3;
+    if (k < min_boot) k = min_boot;
+    const int nb = (k + 3) >> 2;
+    if (nb == 0) return;                            // k == 0: every sum is 0, genus 0 wins (phase 2)
+    const int t2 = tid - 32;
+    const int group = t2 / LPR, l = t2 % LPR;
+    const int lane = tid & 31;
+    const unsigned gmask = 0xFFu << ((lane / LPR) * LPR);
+    const uint4 *lists = reinterpret_cast<const uint4 *>(boot_pool + boot_off[n]);
+    const char *lane_base = reinterpret_cast<const char *>(sQ) + l * 16;
+    const uint32_t margin = pg_margin(k, vmax);
+#define PG_QROW(o) (*reinterpret_cast<const uint4 *>(lane_base + (o)))
+
+    for (int task = group; task < PG_NUM_BOOT; task += NGR) {
+        uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
+        uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u, s4 = 0u, s5 = 0u, s6 = 0u, s7 = 0u;
+        const uint4 *lp = lists + (size_t)(task / IL) * nb * IL + (task % IL);
+        uint4 qa = __ldg(lp), qb = __ldg(lp + IL);
+        uint4 x0 = PG_QROW(qa.x), x1 = PG_QROW(qa.y), x2 = PG_QROW(qa.z), x3 = PG_QROW(qa.w);
+        uint4 y0, y1, y2, y3;
+        int b = 0;
+        while (b + 1 < nb) {
+            y0 = PG_QROW(qb.x); y1 = PG_QROW(qb.y); y2 = PG_QROW(qb.z); y3 = PG_QROW(qb.w);
+            qa = __ldg(lp + (b + 2) * IL);
+            PG_QADD4(x0) PG_QADD4(x1) PG_QADD4(x2) PG_QADD4(x3)
+            x0 = PG_QROW(qa.x); x1 = PG_QROW(qa.y); x2 = PG_QROW(qa.z); x3 = PG_QROW(qa.w);
+            qb = __ldg(lp + (b + 3) * IL);
+            PG_QADD4(y0) PG_QADD4(y1) PG_QADD4(y2) PG_QADD4(y3)
+            b += 2;
+            if ((b & 3) == 0) { PG_QSPILL() }       // every 16 rows: 16 x 4095 < 2^16
+        }
+        if (b < nb) { PG_QADD4(x0) PG_QADD4(x1) PG_QADD4(x2) PG_QADD4(x3) }
+        PG_QSPILL()
+        const uint32_t sums[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
+        pg_task_epilogue<8>(gmask, l == 0, (lane / LPR) * LPR, sums, (uint32_t)(gbase + l * 8), G, 1 + task, margin,
+                            mychamp + 1 + task, mync, mycand);
+    }
+#undef PG_QROW
+}
+
+// ------------------------------------------------------------------ phase 2
+
+// strict fp32 sum of genus g over the task's rows, in the reference's order
+__device__ float pg_strict_sum(const float *__restrict__ table, const uint16_t *sw, int n, int k, int nb,
+                               const uint32_t *__restrict__ list, int task, uint32_t g)
+{
+    const float *tb = table + ((size_t)(g >> 5) * PG_NWORDS) * PG_GENUS_TILE + (g & 31);
+    float a = 0.f;
+    if (task == 0) {
+#pragma unroll 4
+        for (int j = 0; j < n; j++) a = __fadd_rn(a, __ldg(tb + (size_t)sw[j] * PG_GENUS_TILE));
+    } else {
+        const int t = task - 1;
+        const uint32_t *lp = list + ((size_t)(t / 4) * nb * 4 + (t % 4)) * 4;
+#pragma unroll 4
+        for (int j = 0; j < k; j++) {
+            const uint32_t r = __ldg(lp + (size_t)(j >> 2) * 16 + (j & 3)) / PG_ROW_PITCH;
+            a = __fadd_rn(a, __ldg(tb + (size_t)sw[r] * PG_GENUS_TILE));
+        }
+    }
+    return a;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS)
+k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
+          const int32_t *__restrict__ nwords, const uint8_t *__restrict__ flags, const int32_t *__restrict__ order,
+          int nreads_b, int64_t read0, int nmax, const uint32_t *__restrict__ boot_pool,
+          const int32_t *__restrict__ boot_off, int min_boot, int G, double vmax,
+          const unsigned long long *__restrict__ champ, const unsigned int *__restrict__ ncand,
+          const unsigned long long *__restrict__ cand, const int32_t *__restrict__ anc, int depth,
+          pg_result *__restrict__ results, int32_t *__restrict__ boot_winners, int *__restrict__ fb_count,
+          int32_t *__restrict__ fb_list)
+{
+    extern __shared__ unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * WARPS + warp;
+    if (slot >= nreads_b) return;
+    const size_t per_warp = (((size_t)nmax * 2 + 15) & ~(size_t)15) + (PG_NUM_BOOT + 1) * 4 + 16;
+    unsigned char *mine = smem_raw + warp * per_warp;
+    uint16_t *sw = reinterpret_cast<uint16_t *>(mine);
+    int *winners = reinterpret_cast<int *>(mine + (((size_t)nmax * 2 + 15) & ~(size_t)15));
+    unsigned int *need = reinterpret_cast<unsigned int *>(winners + PG_NUM_BOOT + 1);
+
+    const int64_t read = order[slot];
+    pg_result *res = results + read;
+    uint32_t *raw = reinterpret_cast<uint32_t *>(res);
+    if (flags[2 * read + 1]) {                                  // A2: short read
+        if (lane < 16) raw[lane] = (lane == 0) ? 0xFFFFFFFFu : (lane == 3 ? (1u << 8) : 0u);
+        if (boot_winners)
+            for (int r = lane; r < PG_NUM_BOOT; r += 32) boot_winners[read * PG_NUM_BOOT + r] = -1;
+        return;
+    }
+    const size_t rc = (size_t)(read - read0);
+    const unsigned int nc = ncand[rc];
+    if (nc > PG_CANDCAP) {                                      // too many near-ties: strict kernels take it
+        if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int32_t)read;
+        return;
+    }
+    const int n = nwords[read];
+    int k = n >> 3;
+    if (k < min_boot) k = min_boot;
+    const int nb = (k + 3) >> 2;
+    const uint16_t *w = words + off[read];
+    for (int j = lane; j < n; j += 32) sw[j] = w[j];
+    const unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
+    const unsigned long long *mycand = cand + rc * PG_CANDCAP;
+    const uint32_t *list = boot_pool + boot_off[n];
+    const uint32_t margin_full = pg_margin(n, vmax), margin_rep = pg_margin(k, vmax);
+    const bool trivial_rep = (nb == 0 || n == 0);               // k == 0: all sums 0 -> genus 0
+
+    for (int t = lane; t <= PG_NUM_BOOT; t += 32)
+        winners[t] = (n == 0 || (t > 0 && trivial_rep)) ? 0 : (int)(uint32_t)mychamp[t];
+    if (lane < 4) need[lane] = 0u;
+    __syncwarp();
+    if (n > 0) {
+        if (lane == 0) need[0] = 1u;                            // task 0: the score is always strict
+        for (unsigned int e = lane; e < nc; e += 32) {
+            const unsigned long long en = mycand[e];
+            const int t = (int)(en >> 56);
+            if (t > 0 && trivial_rep) continue;
+            const unsigned long long csum = mychamp[t] >> 32;
+            if ((en & 0xFFFFFFFFu) <= csum + (t == 0 ? margin_full : margin_rep)) atomicOr(&need[t >> 5], 1u << (t & 31));
+        }
+    }
+    __syncwarp();
+
+    float score = 0.f;
+    for (int wd = 0; wd < 4; wd++) {
+        unsigned int bits = need[wd];
+        while (bits) {
+            const int t = wd * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            const unsigned long long ch = mychamp[t];
+            const unsigned long long thr = (ch >> 32) + (t == 0 ? margin_full : margin_rep);
+            uint32_t best_ord = 0u, best_g = 0xFFFFFFFFu;
+            // virtual list: entries 0..nc-1, then the champion at index nc
+            for (unsigned int e0 = 0; e0 <= nc; e0 += 32) {
+                const unsigned int e = e0 + lane;
+                bool match = false;
+                uint32_t g = 0;
+                if (e < nc) {
+                    const unsigned long long en = mycand[e];
+                    match = ((int)(en >> 56) == t) && ((en & 0xFFFFFFFFu) <= thr);
+                    g = (uint32_t)(en >> 32) & 0xFFFFFFu;
+                } else if (e == nc) {
+                    match = true;
+                    g = (uint32_t)ch;
+                }
+                const unsigned int bal = __ballot_sync(0xffffffffu, match);
+                if (match) {
+                    const float a = pg_strict_sum(table, sw, n, k, nb, list, t, g);
+                    const uint32_t ob = pg_ord(a);
+                    const uint32_t gm = __reduce_max_sync(bal, ob);
+                    const uint32_t gi = __reduce_min_sync(bal, ob == gm ? g : 0xFFFFFFFFu);
+                    if (gm > best_ord || (gm == best_ord && gi < best_g)) { best_ord = gm; best_g = gi; }
+                }
+                if (bal) {
+                    const int src = __ffs(bal) - 1;
+                    best_ord = __shfl_sync(0xffffffffu, best_ord, src);
+                    best_g = __shfl_sync(0xffffffffu, best_g, src);
+                }
+            }
+            if (lane == 0) winners[t] = (int)best_g;
+            if (t == 0) score = pg_unord(best_ord);
+        }
+    }
+    __syncwarp();
+
+    // ---- A9 vote
+    const int genus = winners[0];
+    int gb[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int r = q * 32 + lane;
+        gb[q] = r < PG_NUM_BOOT ? winners[1 + r] : -1;
+        if (boot_winners && r < PG_NUM_BOOT) boot_winners[read * PG_NUM_BOOT + r] = gb[q];
+    }
+    int myvote = 0, levels = 0;
+    const int nd = anc ? depth : 1;
+    for (int d = 0; d < nd; d++) {
+        const int a = anc ? anc[(size_t)genus * depth + d] : genus;
+        int cnt = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            bool match = false;
+            if (gb[q] >= 0 && a >= 0) match = (anc ? anc[(size_t)gb[q] * depth + d] : gb[q]) == a;
+            cnt += __popc(__ballot_sync(0xffffffffu, match));
+        }
+        if (a >= 0) levels = d + 1;
+        if (lane == d) myvote = cnt;
+    }
+    const uint32_t packed = (uint32_t)myvote & 0xFFu;
+    const uint32_t w0 = __shfl_sync(0xffffffffu, packed, (lane & 7) * 4 + 0);
+    const uint32_t w1 = __shfl_sync(0xffffffffu, packed, (lane & 7) * 4 + 1);
+    const uint32_t w2 = __shfl_sync(0xffffffffu, packed, (lane & 7) * 4 + 2);
+    const uint32_t w3 = __shfl_sync(0xffffffffu, packed, (lane & 7) * 4 + 3);
+    const uint32_t vw = w0 | (w1 << 8) | (w2 << 16) | (w3 << 24);
+    if (lane == 0) {
+        raw[0] = (uint32_t)genus;
+        raw[1] = (uint32_t)n;
+        raw[2] = __float_as_uint(score);
+        raw[3] = (uint32_t)flags[2 * read] | ((uint32_t)levels << 16);
+    }
+    if (lane < 8) raw[4 + lane] = vw;
+    if (lane >= 8 && lane < 12) raw[4 + lane] = 0u;
+}
+
+// ------------------------------------------------------------------ host
+
+template <int BLOCK>
+static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, size_t smem, const uint16_t *d_words,
+                    const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags, const int32_t *d_order,
+                    int64_t read0, int min_boot, unsigned long long *d_champ, unsigned int *d_ncand,
+                    unsigned long long *d_cand)
+{
+    PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(nreads_b, (unsigned)md->ntile64);
+    k_classify_q<BLOCK><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
+                                                          read0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->G,
+                                                          md->vmax, d_champ, d_ncand, d_cand);
+    PG_LAUNCHED(ctx);
+    return PG_OK;
+}
+
+// phase 1 for one bucket (timed by the caller as the dominant kernel)
+int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsigned nreads_b, int nmax,
+                        const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
+                        const uint8_t *d_flags, const int32_t *d_order, int64_t read0, int min_boot,
+                        unsigned long long *d_champ, unsigned int *d_ncand, unsigned long long *d_cand)
+{
+    const size_t smem = (size_t)(nmax + 1) * 128;
+    if (bk.block == 192)
+        return launch_q<192>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand);
+    if (bk.block == 448)
+        return launch_q<448>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand);
+    return launch_q<832>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand);
+}
+
+// phase 2 for one bucket: strict re-check of survivors + vote; overflowing reads go to fb_list
+int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, const uint16_t *d_words,
+                        const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags,
+                        const int32_t *d_order, int64_t read0, int min_boot, const unsigned long long *d_champ,
+                        const unsigned int *d_ncand, const unsigned long long *d_cand, pg_result *d_results,
+                        int32_t *d_boot_winners, int *d_fb_count, int32_t *d_fb_list)
+{
+    constexpr int WARPS = 4;
+    const size_t per_warp = (((size_t)nmax * 2 + 15) & ~(size_t)15) + (PG_NUM_BOOT + 1) * 4 + 16;
+    const size_t smem = per_warp * WARPS;
+    PG_CUDA(ctx, cudaFuncSetAttribute(k_resolve<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_resolve<WARPS><<<(nreads_b + WARPS - 1) / WARPS, 32 * WARPS, smem, ctx->stream>>>(
+        md->d_table, d_words, d_off, d_nwords, d_flags, d_order, (int)nreads_b, read0, nmax, ctx->d_boot_pool,
+        ctx->d_boot_off, min_boot, md->G, md->vmax, d_champ, d_ncand, d_cand, md->d_anc, md->depth, d_results,
+        d_boot_winners, d_fb_count, d_fb_list);
+    PG_LAUNCHED(ctx);
+    return PG_OK;
 }

@@ -19,96 +19,7 @@
 // four dependent FADDs per draw.  The grid is (reads, genus blocks) with reads
 // fastest, so all CTAs in flight gather from the same 65536 x 128 B table slab,
 // which stays resident in L2.
-#include "pg_internal.cuh"
-
-// ------------------------------------------------------------------ A8 sample lists
-
-#define JR_MULT 0x5DEECE66DULL
-#define JR_MASK ((1ULL << 48) - 1)
-
-__device__ __forceinline__ int32_t jr_next(unsigned long long &s, int bits)
-{
-    s = (s * JR_MULT + 0xBULL) & JR_MASK;
-    return (int32_t)(s >> (48 - bits));
-}
-
-__device__ __forceinline__ int32_t jr_next_int(unsigned long long &s, int32_t n)
-{
-    if ((n & -n) == n) return (int32_t)(((long long)n * (long long)jr_next(s, 31)) >> 31);
-    int32_t bits, val;
-    do {
-        bits = jr_next(s, 31);
-        val = bits % n;
-    } while ((long long)bits - val + (n - 1) > 0x7FFFFFFFLL);   // Java: int overflow => redraw
-    return val;
-}
-
-// One thread per distinct n: the 100 x k draws of java.util.Random(1).nextInt(n),
-// stored as shared-memory byte offsets (row * 128, the row pitch of a 32-genus
-// block) so the inner loop needs one IADD per draw.  Each replicate is padded to
-// nb = ceil(k/4) batches of 4 draws with row n (the all-zero row).  The IL = 32/LPR
-// replicates that the groups of one warp walk at the same time are interleaved
-// batch by batch, so the warp's list load is one contiguous 16*IL-byte segment:
-//     uint4 index of (task, batch) = ((task / IL) * nb + batch) * IL + task % IL
-// Two zero-row batches per lane follow the last block for the pipelined read-ahead.
-#define PG_ROW_PITCH 128u
-__host__ __device__ static inline size_t pg_boot_list_entries(int k, int il)
-{
-    const int nb = (k + 3) >> 2;
-    const int tblocks = (PG_NUM_BOOT + il - 1) / il;
-    return ((size_t)tblocks * nb + 2) * il * 4;            // uint32 entries
-}
-__global__ void k_boot_indices(const int32_t *__restrict__ ns, const int32_t *__restrict__ offs,
-                               const int32_t *__restrict__ ils, int cnt, int min_boot,
-                               uint32_t *__restrict__ pool)
-{
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= cnt) return;
-    const int n = ns[t], il = ils[t];
-    int k = n >> 3;
-    if (k < min_boot) k = min_boot;
-    const int nb = (k + 3) >> 2;
-    uint32_t *out = pool + offs[t];
-    const size_t total = pg_boot_list_entries(k, il);
-    for (size_t e = 0; e < total; e++) out[e] = (uint32_t)n * PG_ROW_PITCH;
-    unsigned long long s = (1ULL ^ JR_MULT) & JR_MASK;          // setSeed(1)
-    for (int run = 0; run < PG_NUM_BOOT; run++) {
-        const size_t base = ((size_t)(run / il) * nb * il + (run % il)) * 4;
-        for (int j = 0; j < k; j++) {
-            const uint32_t r = n > 0 ? (uint32_t)jr_next_int(s, n) : 0u;
-            out[base + (size_t)(j >> 2) * il * 4 + (j & 3)] = r * PG_ROW_PITCH;
-        }
-    }
-}
-
-// ------------------------------------------------------------------ keys
-
-// order-preserving map fp32 -> u32
-__device__ __forceinline__ uint32_t pg_ord(float f)
-{
-    uint32_t b = __float_as_uint(f);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float pg_unord(uint32_t u)
-{
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
-}
-// max over keys == larger score first, then SMALLER genus index (first strict max)
-__device__ __forceinline__ unsigned long long pg_key(float score, uint32_t genus)
-{
-    return ((unsigned long long)pg_ord(score) << 32) | (unsigned long long)(0xFFFFFFFFu - genus);
-}
-
-__device__ __forceinline__ void pg_cp_async16(void *smem, const void *gmem)
-{
-    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void pg_cp_async_wait_all()
-{
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-}
+#include "pg_classify_common.cuh"
 
 // ------------------------------------------------------------------ K4 strict
 
@@ -226,14 +137,14 @@ k_classify_strict(const float *__restrict__ table, const uint16_t *__restrict__ 
 // the determined genus the replicates whose winner shares that ancestor.
 __global__ void __launch_bounds__(256)
 k_vote(const unsigned long long *__restrict__ best, int64_t nreads, int64_t read0,
-       const int32_t *__restrict__ nwords, const uint8_t *__restrict__ flags,
+       const int32_t *__restrict__ order, const int32_t *__restrict__ nwords, const uint8_t *__restrict__ flags,
        const int32_t *__restrict__ anc, int depth, pg_result *__restrict__ results,
        int32_t *__restrict__ boot_winners)
 {
     const int lane = threadIdx.x & 31;
     const int64_t ic = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ic >= nreads) return;
-    const int64_t i = read0 + ic;
+    const int64_t i = order ? (int64_t)order[ic] : read0 + ic;
     pg_result *res = results + i;
     uint32_t *raw = reinterpret_cast<uint32_t *>(res);          // 16 x uint32
     if (flags[2 * i + 1]) {                                     // A2: short read
@@ -242,7 +153,7 @@ k_vote(const unsigned long long *__restrict__ best, int64_t nreads, int64_t read
             for (int r = lane; r < PG_NUM_BOOT; r += 32) boot_winners[i * PG_NUM_BOOT + r] = -1;
         return;
     }
-    const unsigned long long *b = best + (size_t)ic * (PG_NUM_BOOT + 1);
+    const unsigned long long *b = best + (size_t)(i - read0) * (PG_NUM_BOOT + 1);
     const unsigned long long key0 = b[0];
     const int genus = (int)(0xFFFFFFFFu - (uint32_t)key0);
     const float score = pg_unord((uint32_t)(key0 >> 32));
@@ -287,9 +198,6 @@ k_vote(const unsigned long long *__restrict__ best, int64_t nreads, int64_t read
 
 // ------------------------------------------------------------------ host orchestration
 
-// Reads are bucketed by word count so each launch sizes its shared memory (and so
-// its CTAs/SM) for the reads it actually carries.
-struct Bucket { int nmax; int lpr; int block; };
 // block = 32 (full-sum warp) + groups*LPR: 20 groups x 5 replicates, 52 x 2, 100 x 1.
 static const Bucket kBuckets[] = {
     {215, 8, 192},  {250, 8, 192},  {290, 8, 192},  {350, 8, 192},  {440, 8, 192},
@@ -318,10 +226,16 @@ static int launch_strict(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, uns
     return PG_OK;
 }
 
-int pg_classify_certified_launch(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsigned nreads_b, int nmax,
-                                 const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
-                                 const int32_t *d_order, int64_t read0, int min_boot,
-                                 unsigned long long *d_best);   // pg_certified.cu
+int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsigned nreads_b, int nmax,
+                        const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
+                        const uint8_t *d_flags, const int32_t *d_order, int64_t read0, int min_boot,
+                        unsigned long long *d_champ, unsigned int *d_ncand, unsigned long long *d_cand);
+int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, const uint16_t *d_words,
+                        const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags,
+                        const int32_t *d_order, int64_t read0, int min_boot, const unsigned long long *d_champ,
+                        const unsigned int *d_ncand, const unsigned long long *d_cand, pg_result *d_results,
+                        int32_t *d_boot_winners, int *d_fb_count, int32_t *d_fb_list);   // pg_certified.cu
+#define PG_CANDCAP 128
 
 static int ensure_boot_lists(pg_ctx *ctx, const std::vector<int> &need_n, int min_boot)
 {
@@ -416,12 +330,31 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
     }
     PG_TRY(ensure_boot_lists(ctx, need, min_boot));
 
-    const int64_t CHUNK = 1 << 20;
+    const bool certified = (mode == 1) && md->q_ok;
+    ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
+    const int64_t CHUNK = certified ? (1 << 18) : (1 << 20);
     const int nkeys = PG_NUM_BOOT + 1;
-    PG_TRY(pg_scratch(ctx, &ctx->s_best, (size_t)(count < CHUNK ? count : CHUNK) * nkeys * 8));
-    PG_TRY(pg_scratch(ctx, &ctx->s_order, (size_t)(count < CHUNK ? count : CHUNK) * 4));
+    const int64_t cmax = count < CHUNK ? count : CHUNK;
+    PG_TRY(pg_scratch(ctx, &ctx->s_best, (size_t)cmax * nkeys * 8));
+    PG_TRY(pg_scratch(ctx, &ctx->s_order, (size_t)cmax * 4));
     unsigned long long *d_best = (unsigned long long *)ctx->s_best.p;
     int32_t *d_order = (int32_t *)ctx->s_order.p;
+    unsigned long long *d_champ = NULL, *d_cand = NULL;
+    unsigned int *d_ncand = NULL;
+    int *d_fbc = NULL;
+    int32_t *d_fbl = NULL;
+    if (certified) {
+        PG_TRY(pg_scratch(ctx, &ctx->s_champ, (size_t)cmax * nkeys * 8));
+        PG_TRY(pg_scratch(ctx, &ctx->s_ncand, (size_t)cmax * 4));
+        PG_TRY(pg_scratch(ctx, &ctx->s_candl, (size_t)cmax * PG_CANDCAP * 8));
+        PG_TRY(pg_scratch(ctx, &ctx->s_fb, (size_t)cmax * 4 + 16));
+        d_champ = (unsigned long long *)ctx->s_champ.p;
+        d_ncand = (unsigned int *)ctx->s_ncand.p;
+        d_cand = (unsigned long long *)ctx->s_candl.p;
+        d_fbc = (int *)ctx->s_fb.p;
+        d_fbl = (int32_t *)ctx->s_fb.p + 4;
+    }
+    const int wpb = 8;
 
     for (int64_t c0 = 0; c0 < count; c0 += CHUNK) {
         const int64_t cn = count - c0 < CHUNK ? count - c0 : CHUNK;
@@ -446,41 +379,96 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
         }
         PG_CUDA(ctx, cudaMemcpyAsync(d_order, h_order + c0, (size_t)cn * 4, cudaMemcpyHostToDevice, ctx->stream));
         PG_CUDA(ctx, cudaMemsetAsync(d_best, 0, (size_t)cn * nkeys * 8, ctx->stream));
+        if (certified) {
+            PG_CUDA(ctx, cudaMemsetAsync(d_champ, 0xFF, (size_t)cn * nkeys * 8, ctx->stream));
+            PG_CUDA(ctx, cudaMemsetAsync(d_ncand, 0, (size_t)cn * 4, ctx->stream));
+            PG_CUDA(ctx, cudaMemsetAsync(d_fbc, 0, 16, ctx->stream));
+        }
+
+        // one bucket of reads through the strict kernels (also the certified path's fallback)
+        auto run_strict = [&](const Bucket &bk, const int32_t *ord, unsigned cnt, int nmax, bool timed) -> int {
+            cudaEvent_t e0 = NULL, e1 = NULL;
+            if (timed) {
+                e0 = take_event(ctx); e1 = take_event(ctx);
+                PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+            }
+            const int TG = 4 * bk.lpr;
+            const unsigned ngb = (unsigned)((md->G + TG - 1) / TG);
+            const size_t smem = (size_t)(nmax + 1) * bk.lpr * 16;
+            int rc;
+            if (bk.lpr == 8 && bk.block == 192)
+                rc = launch_strict<8, 192>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+            else if (bk.lpr == 8 && bk.block == 448)
+                rc = launch_strict<8, 448>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+            else if (bk.lpr == 8)
+                rc = launch_strict<8, 832>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+            else if (bk.lpr == 4)
+                rc = launch_strict<4, 832>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+            else
+                rc = launch_strict<2, 832>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
+            PG_TRY(rc);
+            if (timed) {
+                PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+                ctx->ev_pending.push_back(std::make_pair(e0, e1));
+            }
+            k_vote<<<(cnt + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(d_best, cnt, c0, ord, d_nwords, d_flags, md->d_anc,
+                                                                      md->depth, d_results, d_boot_winners);
+            PG_LAUNCHED(ctx);
+            return PG_OK;
+        };
 
         for (int b = 0; b < kNumBuckets; b++) {
             if (!bcount[b]) continue;
             const Bucket &bk = kBuckets[b];
             const int nmax = (int)bmaxn[b];
             const int32_t *ord = d_order + bstart[b];
-            cudaEvent_t e0 = take_event(ctx), e1 = take_event(ctx);
-            PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-            if (mode == 1) {
-                PG_TRY(pg_classify_certified_launch(ctx, md, bk, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords,
-                                                    ord, c0, min_boot, d_best));
+            if (certified && bk.lpr == 8) {
+                ctx->st_certified += bcount[b];
+                cudaEvent_t e0 = take_event(ctx), e1 = take_event(ctx);
+                PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+                PG_TRY(pg_certified_phase1(ctx, md, bk, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords, d_flags, ord,
+                                           c0, min_boot, d_champ, d_ncand, d_cand));
+                PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+                ctx->ev_pending.push_back(std::make_pair(e0, e1));
+                PG_TRY(pg_certified_phase2(ctx, md, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords, d_flags, ord, c0,
+                                           min_boot, d_champ, d_ncand, d_cand, d_results, d_boot_winners, d_fbc, d_fbl));
             } else {
-                const int TG = 4 * bk.lpr;
-                const unsigned ngb = (unsigned)((md->G + TG - 1) / TG);
-                const size_t smem = (size_t)(nmax + 1) * bk.lpr * 16;
-                int rc;
-                if (bk.lpr == 8 && bk.block == 192)
-                    rc = launch_strict<8, 192>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
-                else if (bk.lpr == 8 && bk.block == 448)
-                    rc = launch_strict<8, 448>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
-                else if (bk.lpr == 8)
-                    rc = launch_strict<8, 832>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
-                else if (bk.lpr == 4)
-                    rc = launch_strict<4, 832>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
-                else
-                    rc = launch_strict<2, 832>(ctx, md, (unsigned)bcount[b], ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
-                PG_TRY(rc);
+                ctx->st_strict += bcount[b];
+                PG_TRY(run_strict(bk, ord, (unsigned)bcount[b], nmax, true));
             }
-            PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
-            ctx->ev_pending.push_back(std::make_pair(e0, e1));
         }
-        const int wpb = 8;
-        k_vote<<<(unsigned)((cn + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
-            d_best, cn, c0, d_nwords, d_flags, md->d_anc, md->depth, d_results, d_boot_winners);
-        PG_LAUNCHED(ctx);
+
+        if (certified) {
+            // reads whose near-tie list overflowed are redone by the strict kernels
+            int nfb = 0;
+            PG_CUDA(ctx, cudaMemcpyAsync(&nfb, d_fbc, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (nfb > 0) {
+                ctx->st_handed_back += nfb;
+                std::vector<int32_t> fb((size_t)nfb), sorted((size_t)nfb);
+                PG_CUDA(ctx, cudaMemcpyAsync(fb.data(), d_fbl, (size_t)nfb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                int64_t fcount[16] = {0}, fstart[16], fmaxn[16] = {0}, ffill[16];
+                for (int32_t r : fb) {
+                    int n = h_n[r], b = 0;
+                    while (kBuckets[b].nmax < n) b++;
+                    fcount[b]++;
+                    if (n > fmaxn[b]) fmaxn[b] = n;
+                }
+                int64_t a2 = 0;
+                for (int b = 0; b < kNumBuckets; b++) { fstart[b] = ffill[b] = a2; a2 += fcount[b]; }
+                for (int32_t r : fb) {
+                    int n = h_n[r], b = 0;
+                    while (kBuckets[b].nmax < n) b++;
+                    sorted[(size_t)ffill[b]++] = r;
+                }
+                PG_CUDA(ctx, cudaMemcpyAsync(d_order, sorted.data(), (size_t)nfb * 4, cudaMemcpyHostToDevice, ctx->stream));
+                for (int b = 0; b < kNumBuckets; b++)
+                    if (fcount[b])
+                        PG_TRY(run_strict(kBuckets[b], d_order + fstart[b], (unsigned)fcount[b], (int)fmaxn[b], false));
+                PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // `sorted` is a stack vector
+            }
+        }
     }
     return PG_OK;
 }

@@ -51,7 +51,8 @@ extern "C" pg_ctx *pg_init(int device)
     ctx->boot_min_words = -1;
     ctx->classify_ms = 0.0;
     ctx->classify_launches = 0;
-    memset(&ctx->s_words, 0, sizeof(pg_ctx::Scratch) * 10);
+    ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
+    memset(&ctx->s_words, 0, sizeof(pg_ctx::Scratch) * pg_ctx::kNumScratch);
     ctx->h_pin = NULL;
     ctx->h_pin_cap = 0;
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
@@ -69,7 +70,7 @@ extern "C" void pg_shutdown(pg_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     pg_ctx::Scratch *s = &ctx->s_words;
-    for (int i = 0; i < 10; i++) cudaFree(s[i].p);
+    for (int i = 0; i < pg_ctx::kNumScratch; i++) cudaFree(s[i].p);
     cudaFree(ctx->d_boot_pool);
     cudaFree(ctx->d_boot_off);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -91,6 +92,15 @@ extern "C" int pg_sync(pg_ctx *ctx)
     if (!ctx) return PG_EINVAL;
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+
+extern "C" int pg_classify_stats(const pg_ctx *ctx, int64_t *certified_reads, int64_t *strict_reads, int64_t *handed_back)
+{
+    if (!ctx) return PG_EINVAL;
+    if (certified_reads) *certified_reads = ctx->st_certified;
+    if (strict_reads) *strict_reads = ctx->st_strict;
+    if (handed_back) *handed_back = ctx->st_handed_back;
     return PG_OK;
 }
 

@@ -33,12 +33,15 @@ struct pg_ctx {
     std::vector<cudaEvent_t>                         ev_free;
     double  classify_ms;
     int64_t classify_launches;
+    int64_t st_certified, st_strict, st_handed_back;   // routing of the last classify call
 
     // grow-only device scratch for classification
     struct Scratch {
         void  *p;
         size_t cap;
-    } s_words, s_nwords, s_flags, s_best, s_order, s_results, s_boot, s_bytes, s_off, s_cand;
+    } s_words, s_nwords, s_flags, s_best, s_order, s_results, s_boot, s_bytes, s_off, s_cand,
+      s_champ, s_ncand, s_candl, s_fb;
+    static const int kNumScratch = 14;
     // pinned host staging
     void  *h_pin;
     size_t h_pin_cap;
@@ -57,8 +60,13 @@ struct pg_model {
     float   *d_Pw;              // [65536]
     float   *d_logLeave;        // [ntile*32]
     int32_t *d_anc;             // [G][depth]
-    uint16_t *d_qtable;         // [ntile][65536][32]   certified mode: quantised deficits
+    // certified mode (pg_certified.cu): deficits below the per-word row maximum in units of
+    // 2^-7 nat, 64 genera per 128-byte row segment
+    uint16_t *d_qtable;         // [ntile64][65536][64]
     float   *d_rowmax;          // [65536]
+    int      ntile64;
+    double   vmax;              // max |table entry| over real genera (fp32 error bound)
+    bool     q_ok;              // every deficit fits the 12-bit field: certificates are valid
     bool     committed;
 };
 

@@ -111,6 +111,8 @@ def load_library() -> C.CDLL:
     lib.pg_model_free.restype = None
     lib.pg_model_set_lineage.argtypes = [vp, vp, C.c_int]
     lib.pg_model_genera.argtypes = [vp]
+    lib.pg_model_certifiable.argtypes = [vp]
+    lib.pg_classify_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.pg_model_sequences.restype = i64
     lib.pg_model_sequences.argtypes = [vp]
     lib.pg_model_counts.argtypes = [vp, vp, vp, vp, C.POINTER(i64)]
@@ -175,6 +177,10 @@ class Model:
     @property
     def N(self) -> int:
         return self.ctx.lib.pg_model_sequences(self.h)
+
+    @property
+    def certifiable(self) -> bool:
+        return bool(self.ctx.lib.pg_model_certifiable(self.h))
 
     def set_lineage(self, anc: np.ndarray) -> None:
         anc = np.ascontiguousarray(anc, dtype=np.int32)
@@ -274,6 +280,11 @@ class Context:
         ms, n = C.c_double(), C.c_int64()
         self._chk(self.lib.pg_kernel_time(self.h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def classify_stats(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._chk(self.lib.pg_classify_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"certified": a.value, "strict": b.value, "handed_back": c.value}
 
     def kernel_time_reset(self) -> None:
         self._chk(self.lib.pg_kernel_time_reset(self.h))

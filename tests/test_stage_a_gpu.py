@@ -97,6 +97,11 @@ def edge_reads(tr):
 def check_against_oracle(ctx, gm, om, anc, reads, mode=0, min_boot=0):
     data, off = pack_sequences(reads)
     res, boot = ctx.classify(gm, data, off, mode=mode, min_boot_words=min_boot, want_boot=True)
+    st = ctx.classify_stats()
+    if mode == 1:
+        assert gm.certifiable and st["certified"] > 0, st      # the certified kernels really ran
+    else:
+        assert st["certified"] == 0 and st["handed_back"] == 0
     ref = om.classify(data, off, min_boot)
     votes = om.votes(ref, anc)
     assert np.array_equal(res["status"], ref["status"])
@@ -150,9 +155,13 @@ def test_extract_words_and_orientation(ctx, small):
         assert np.array_equal(words[off[i]:off[i] + nw[i]].astype(np.int32), w)
 
 
-def test_classify_edge_cases(ctx, small):
+MODES = pytest.mark.parametrize("mode", [0, 1], ids=["strict", "certified"])
+
+
+@MODES
+def test_classify_edge_cases(ctx, small, mode):
     tr, om, gm = small
-    check_against_oracle(ctx, gm, om, tr["anc"], edge_reads(tr))
+    check_against_oracle(ctx, gm, om, tr["anc"], edge_reads(tr), mode=mode)
 
 
 def test_classify_empty_batch(ctx, small):
@@ -161,32 +170,37 @@ def test_classify_empty_batch(ctx, small):
     assert len(res) == 0
 
 
-def test_classify_min_boot_words(ctx, small):
+@MODES
+def test_classify_min_boot_words(ctx, small, mode):
     tr, om, gm = small
-    check_against_oracle(ctx, gm, om, tr["anc"], edge_reads(tr)[:12], min_boot=5)
-    check_against_oracle(ctx, gm, om, tr["anc"], edge_reads(tr)[:12], min_boot=0)
+    check_against_oracle(ctx, gm, om, tr["anc"], edge_reads(tr)[:12], min_boot=5, mode=mode)
+    check_against_oracle(ctx, gm, om, tr["anc"], edge_reads(tr)[:12], min_boot=0, mode=mode)
 
 
-def test_classify_illumina_reads(ctx, small):
+@MODES
+def test_classify_illumina_reads(ctx, small, mode):
     tr, om, gm = small
     for paired in (False, True):
         data, off, src = synth.synth_reads(31, tr, 400, paired=paired)
         reads = [data[off[i]:off[i + 1]].tobytes() for i in range(400)]
-        res = check_against_oracle(ctx, gm, om, tr["anc"], reads)
+        res = check_against_oracle(ctx, gm, om, tr["anc"], reads, mode=mode)
         assert (res["n_words"] == (486 if paired else 243)).mean() > 0.2      # some carry an 'n'
         assert (res["genus"] == src).mean() > 0.5
 
 
-def test_classify_self_full_length(ctx, small):
+@MODES
+def test_classify_self_full_length(ctx, small, mode):
     """config 2 in miniature: classify the training set against its own model."""
     tr, om, gm = small
     reads = [tr["data"][tr["off"][i]:tr["off"][i + 1]].tobytes() for i in range(len(tr["genus"]))]
-    res = check_against_oracle(ctx, gm, om, tr["anc"], reads)
+    res = check_against_oracle(ctx, gm, om, tr["anc"], reads, mode=mode)
     assert (res["genus"] == tr["genus"]).mean() >= 0.99
 
 
-def test_long_reads_every_bucket(ctx):
-    """reads of 1.4k .. 6.9k words exercise the 1024-thread and narrow-tile launches."""
+@MODES
+def test_long_reads_every_bucket(ctx, mode):
+    """reads of 1.4k .. 6.9k words exercise the 1-CTA/SM and narrow-tile launches
+    (certified mode hands the narrow-tile buckets to the strict kernels)."""
     tr = synth.synth16s(seed=77, seqs=24, genera=9, length=7000)
     om = ora.Model(tr["data"], tr["off"], tr["genus"], tr["G"])
     gm = ctx.train(tr["data"], tr["off"], tr["genus"], tr["G"])
@@ -195,7 +209,7 @@ def test_long_reads_every_bucket(ctx):
     reads = [s[:ln].tobytes() for s, ln in zip(seqs, [1400, 1790, 1830, 2500, 3590, 3650, 5000, 6300])]
     reads.append(synth.revcomp(seqs[8][:6999]).tobytes())
     reads.append(seqs[9][:300].tobytes())
-    check_against_oracle(ctx, gm, om, tr["anc"], reads)
+    check_against_oracle(ctx, gm, om, tr["anc"], reads, mode=mode)
     too_long = np.tile(seqs[0], 2)[:7300].tobytes()
     data, off = pack_sequences([too_long])
     with pytest.raises(pg.PangeaError) as e:
@@ -280,6 +294,68 @@ def test_real_16s_subset(ctx):
     assert np.array_equal(m, rm) and np.array_equal(nw, rnw) and np.array_equal(M, rM) and N == rN
     assert np.array_equal(bits(gm.tables()[2]), bits(om.tables()[2]))
     reads = list(seqs) + [s[100:350] for s in seqs] + [s[-400:] for s in seqs]
-    check_against_oracle(ctx, gm, om, anc, reads)
+    check_against_oracle(ctx, gm, om, anc, reads, mode=0)
+    check_against_oracle(ctx, gm, om, anc, reads, mode=1)
+    om.free()
+    gm.free()
+
+
+def _twin_model(ctx, copies):
+    """genera that are exact copies of one another: every sum ties, the reference's
+    first-maximum rule decides, and the certified path sees near-ties everywhere."""
+    base = synth.synth16s(seed=404, seqs=60, genera=12, length=600)
+    G0 = base["G"]
+    datas, offs, gen = [], [0], []
+    for c in range(copies):
+        for i in range(len(base["genus"])):
+            s = base["data"][base["off"][i]:base["off"][i + 1]]
+            datas.append(s)
+            offs.append(offs[-1] + len(s))
+            gen.append(base["genus"][i] + c * G0)
+    data = np.concatenate(datas)
+    off = np.array(offs, np.int64)
+    genus = np.array(gen, np.int32)
+    G = G0 * copies
+    anc = np.concatenate([base["anc"]] * copies, axis=0).copy()
+    anc[:, -1] = 1000 + np.arange(G)                     # distinct genus nodes, shared ancestors
+    om = ora.Model(data, off, genus, G)
+    gm = ctx.train(data, off, genus, G)
+    gm.set_lineage(anc)
+    reads = [base["data"][base["off"][i]:base["off"][i + 1]][40:40 + 260].tobytes() for i in range(30)]
+    return om, gm, anc, reads
+
+
+@pytest.mark.parametrize("copies", [2, 3, 7])
+def test_certified_with_exact_ties(ctx, copies):
+    """2 copies: the twin is a near-tie in every replicate; 3 and 7 copies overflow the
+    near-tie list and exercise the hand-back to the strict kernels."""
+    om, gm, anc, reads = _twin_model(ctx, copies)
+    res = check_against_oracle(ctx, gm, om, anc, reads, mode=1)
+    st = ctx.classify_stats()
+    assert (st["handed_back"] > 0) == (copies > 2), st   # 3+ copies overflow the near-tie list
+    assert (res["genus"] < 12).all()                     # lowest index among identical genera
+    check_against_oracle(ctx, gm, om, anc, reads, mode=0)
+    om.free()
+    gm.free()
+
+
+def test_certified_close_genera(ctx):
+    """genera 0.4 % apart: many replicates have several survivors inside the margin."""
+    tr = synth.synth16s(seed=99, seqs=400, genera=90, length=700)
+    rng = np.random.default_rng(1)
+    src = [tr["data"][tr["off"][i]:tr["off"][i + 1]].copy() for i in range(len(tr["genus"]))]
+    proto = src[0][:630]
+    seqs = []
+    for i in range(len(src)):
+        s = proto.copy()
+        hit = rng.random(s.size) < 0.004
+        s[hit] = synth.BASES[rng.integers(0, 4, int(hit.sum()))]
+        seqs.append(s.tobytes())
+    data, off = pack_sequences(seqs)
+    om = ora.Model(data, off, tr["genus"], tr["G"])
+    gm = ctx.train(data, off, tr["genus"], tr["G"])
+    gm.set_lineage(tr["anc"])
+    reads = [s[30:30 + 250] for s in seqs[:120]]
+    check_against_oracle(ctx, gm, om, tr["anc"], reads, mode=1)
     om.free()
     gm.free()
