@@ -134,34 +134,55 @@ __device__ __forceinline__ void pg_emit(unsigned int *ncand, unsigned long long 
         cand[slot] = ((unsigned long long)task << 56) | ((unsigned long long)genus << 32) | sum;
 }
 
-// After a task's sums are known: update the champion slot, append near-ties.
-//   sums[i] belongs to genus genus0+i; `mask` = the lanes sharing this task.
+// Task epilogue, split in two so the returning atomic's latency hides behind the
+// next replicate's main loop.
+//   begin : block minimum as one REDUX over (sum << 6 | genus-in-block), then the group
+//           leader posts it to the (read, task) champion slot with a 64-bit atomicMin.
+//   finish: with the slot's previous value, append near-ties of the running minimum to
+//           the read's list; the displaced champion stays listed if it is still close.
+// sums[i] belongs to genus genus0+i; `mask` = the lanes sharing this task.
+struct PgPending {
+    unsigned long long old;      // leader only: value the slot held before our atomicMin
+    uint32_t bkey;               // block minimum: sum << 6 | genus - gbase
+    uint32_t lmin;               // this lane's smallest sum
+};
+
 template <int NV>
-__device__ __forceinline__ void pg_task_epilogue(unsigned mask, bool leader, int leader_lane, const uint32_t *sums,
-                                                 uint32_t genus0, int G, int task, uint32_t margin,
-                                                 unsigned long long *champ_slot, unsigned int *ncand,
-                                                 unsigned long long *cand)
+__device__ __forceinline__ void pg_epilogue_begin(unsigned mask, bool leader, const uint32_t *sums, uint32_t genus0,
+                                                  uint32_t gbase, int G, unsigned long long *champ_slot,
+                                                  PgPending &p)
 {
-    uint32_t lmin = 0xFFFFFFFFu, lgen = 0xFFFFFFFFu;
+    uint32_t lkey = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
         const uint32_t g = genus0 + i;
-        const uint32_t s = (int)g < G ? sums[i] : 0xFFFFFFFFu;
-        if (s < lmin) { lmin = s; lgen = g; }
+        const uint32_t key = (int)g < G ? ((sums[i] << 6) | (g - gbase)) : 0xFFFFFFFFu;
+        lkey = min(lkey, key);
     }
-    const uint32_t bm = __reduce_min_sync(mask, lmin);
-    const uint32_t bg = __reduce_min_sync(mask, lmin == bm ? lgen : 0xFFFFFFFFu);
+    p.lmin = lkey >> 6;
+    p.bkey = __reduce_min_sync(mask, lkey);
+    p.old = 0;
+    if (leader)
+        p.old = atomicMin(champ_slot, ((unsigned long long)(p.bkey >> 6) << 32) | (gbase + (p.bkey & 63u)));
+}
+
+template <int NV>
+__device__ __forceinline__ void pg_epilogue_finish(unsigned mask, bool leader, int leader_lane, const uint32_t *sums,
+                                                   uint32_t genus0, uint32_t gbase, int G, int task,
+                                                   uint32_t margin, const PgPending &p, unsigned int *ncand,
+                                                   unsigned long long *cand)
+{
+    const unsigned long long old = __shfl_sync(mask, p.old, leader_lane);
+    const uint32_t bm = p.bkey >> 6, bg = gbase + (p.bkey & 63u);
     const unsigned long long mine = ((unsigned long long)bm << 32) | bg;
-    unsigned long long old = 0;
-    if (leader) old = atomicMin(champ_slot, mine);
-    old = __shfl_sync(mask, old, leader_lane);
     const bool took = mine < old;                              // this block holds the new champion
-    const unsigned long long cursum = (took ? mine : old) >> 32;
-    const unsigned long long thr = cursum + margin;
+    const unsigned long long thr = ((took ? mine : old) >> 32) + margin;
+    if ((unsigned long long)p.lmin <= thr) {
 #pragma unroll
-    for (int i = 0; i < NV; i++) {
-        const uint32_t g = genus0 + i;
-        if ((int)g < G && (unsigned long long)sums[i] <= thr && !(took && g == bg)) pg_emit(ncand, cand, task, g, sums[i]);
+        for (int i = 0; i < NV; i++) {
+            const uint32_t g = genus0 + i;
+            if ((int)g < G && (unsigned long long)sums[i] <= thr && !(took && g == bg)) pg_emit(ncand, cand, task, g, sums[i]);
+        }
     }
     // the displaced champion stays a candidate if it is within the margin of the new one
     if (leader && took && old != PG_CHAMP_INIT && (old >> 32) <= (unsigned long long)bm + margin)
@@ -177,7 +198,7 @@ __device__ __forceinline__ void pg_task_epilogue(unsigned mask, bool leader, int
     c0 = c1 = c2 = c3 = 0u;
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK > 512) ? 1 : ((BLOCK > 256) ? 2 : 5))
+__global__ void __launch_bounds__(BLOCK, (BLOCK > 512) ? 1 : ((BLOCK > 256) ? 2 : 3))
 k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
              const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
              const uint8_t *__restrict__ flags, const int32_t *__restrict__ order, int64_t read0,
@@ -230,8 +251,10 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
         lo += c & 0xFFFFu;
         hi += c >> 16;
         const uint32_t sums[2] = {lo, hi};
-        pg_task_epilogue<2>(0xffffffffu, tid == 0, 0, sums, (uint32_t)(gbase + 2 * tid), G, 0, pg_margin(n, vmax),
-                            mychamp, mync, mycand);
+        PgPending pp;
+        pg_epilogue_begin<2>(0xffffffffu, tid == 0, sums, (uint32_t)(gbase + 2 * tid), (uint32_t)gbase, G, mychamp, pp);
+        pg_epilogue_finish<2>(0xffffffffu, tid == 0, 0, sums, (uint32_t)(gbase + 2 * tid), (uint32_t)gbase, G, 0,
+                              pg_margin(n, vmax), pp, mync, mycand);
         return;
     }
 
@@ -249,6 +272,11 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
     const uint32_t margin = pg_margin(k, vmax);
 #define PG_QROW(o) (*reinterpret_cast<const uint4 *>(lane_base + (o)))
 
+    const int leader_lane = (lane / LPR) * LPR;
+    const uint32_t genus0 = (uint32_t)(gbase + l * 8);
+    PgPending pend;
+    uint32_t psum[8];
+    int ptask = -1;
     for (int task = group; task < PG_NUM_BOOT; task += NGR) {
         uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
         uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u, s4 = 0u, s5 = 0u, s6 = 0u, s7 = 0u;
@@ -269,10 +297,18 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
         }
         if (b < nb) { PG_QADD4(x0) PG_QADD4(x1) PG_QADD4(x2) PG_QADD4(x3) }
         PG_QSPILL()
-        const uint32_t sums[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
-        pg_task_epilogue<8>(gmask, l == 0, (lane / LPR) * LPR, sums, (uint32_t)(gbase + l * 8), G, 1 + task, margin,
-                            mychamp + 1 + task, mync, mycand);
+        // the previous replicate's atomic has had a whole main loop to come back
+        if (ptask >= 0)
+            pg_epilogue_finish<8>(gmask, l == 0, leader_lane, psum, genus0, (uint32_t)gbase, G, 1 + ptask, margin, pend,
+                                  mync, mycand);
+        psum[0] = s0; psum[1] = s1; psum[2] = s2; psum[3] = s3;
+        psum[4] = s4; psum[5] = s5; psum[6] = s6; psum[7] = s7;
+        ptask = task;
+        pg_epilogue_begin<8>(gmask, l == 0, psum, genus0, (uint32_t)gbase, G, mychamp + 1 + task, pend);
     }
+    if (ptask >= 0)
+        pg_epilogue_finish<8>(gmask, l == 0, leader_lane, psum, genus0, (uint32_t)gbase, G, 1 + ptask, margin, pend, mync,
+                              mycand);
 #undef PG_QROW
 }
 
