@@ -277,26 +277,38 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
     PgPending pend;
     uint32_t psum[8];
     int ptask = -1;
+#define PG_LD4(d, q) d##0 = PG_QROW((q).x); d##1 = PG_QROW((q).y); d##2 = PG_QROW((q).z); d##3 = PG_QROW((q).w);
+#define PG_ADD16(d) PG_QADD4(d##0) PG_QADD4(d##1) PG_QADD4(d##2) PG_QADD4(d##3)
+    const int nquad = nb >> 2, tail = nb & 3;
     for (int task = group; task < PG_NUM_BOOT; task += NGR) {
         uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
         uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u, s4 = 0u, s5 = 0u, s6 = 0u, s7 = 0u;
         const uint4 *lp = lists + (size_t)(task / IL) * nb * IL + (task % IL);
         uint4 qa = __ldg(lp), qb = __ldg(lp + IL);
-        uint4 x0 = PG_QROW(qa.x), x1 = PG_QROW(qa.y), x2 = PG_QROW(qa.z), x3 = PG_QROW(qa.w);
-        uint4 y0, y1, y2, y3;
+        uint4 x0, x1, x2, x3, y0, y1, y2, y3;
+        PG_LD4(x, qa)
+        // four 4-draw batches per trip: loads run one batch ahead of the adds, list reads two;
+        // 16 rows x 4095 < 2^16, so the packed accumulators are spilled once per trip
         int b = 0;
-        while (b + 1 < nb) {
-            y0 = PG_QROW(qb.x); y1 = PG_QROW(qb.y); y2 = PG_QROW(qb.z); y3 = PG_QROW(qb.w);
-            qa = __ldg(lp + (b + 2) * IL);
-            PG_QADD4(x0) PG_QADD4(x1) PG_QADD4(x2) PG_QADD4(x3)
-            x0 = PG_QROW(qa.x); x1 = PG_QROW(qa.y); x2 = PG_QROW(qa.z); x3 = PG_QROW(qa.w);
-            qb = __ldg(lp + (b + 3) * IL);
-            PG_QADD4(y0) PG_QADD4(y1) PG_QADD4(y2) PG_QADD4(y3)
-            b += 2;
-            if ((b & 3) == 0) { PG_QSPILL() }       // every 16 rows: 16 x 4095 < 2^16
+        for (int it = 0; it < nquad; it++, b += 4) {
+            PG_LD4(y, qb) qa = __ldg(lp + (b + 2) * IL); PG_ADD16(x)
+            PG_LD4(x, qa) qb = __ldg(lp + (b + 3) * IL); PG_ADD16(y)
+            PG_LD4(y, qb) qa = __ldg(lp + (b + 4) * IL); PG_ADD16(x)
+            if (b + 4 < nb) { PG_LD4(x, qa) }
+            qb = __ldg(lp + (b + 5) * IL);
+            PG_ADD16(y)
+            PG_QSPILL()
         }
-        if (b < nb) { PG_QADD4(x0) PG_QADD4(x1) PG_QADD4(x2) PG_QADD4(x3) }
-        PG_QSPILL()
+        if (tail) {                                 // x holds batch b, qb the list entry of batch b+1
+            if (tail >= 2) { PG_LD4(y, qb) qa = __ldg(lp + (b + 2) * IL); }
+            PG_ADD16(x)
+            if (tail >= 2) {
+                if (tail == 3) { PG_LD4(x, qa) }
+                PG_ADD16(y)
+                if (tail == 3) { PG_ADD16(x) }
+            }
+            PG_QSPILL()
+        }
         // the previous replicate's atomic has had a whole main loop to come back
         if (ptask >= 0)
             pg_epilogue_finish<8>(gmask, l == 0, leader_lane, psum, genus0, (uint32_t)gbase, G, 1 + ptask, margin, pend,
