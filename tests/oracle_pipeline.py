@@ -1,0 +1,82 @@
+"""ctypes wrapper of oracle/libpipeline_ref.so (Stage B / C CPU checkers) and helpers that
+drive the REAL reference (Perl + compiled ncbitc.c) when it is available.  Tests only."""
+import ctypes as C
+import shutil
+import subprocess
+import tempfile
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parent.parent
+ORACLE_DIR = REPO / "oracle"
+REF = Path("/root/reference")
+REF_TAX_CLASS = ORACLE_DIR / "_ref" / "tax_class"
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = ORACLE_DIR / "libpipeline_ref.so"
+        srcs = [ORACLE_DIR / "taxcollector_ref.c", ORACLE_DIR / "consensus_ref.c"]
+        if not so.exists() or any(so.stat().st_mtime < s.stat().st_mtime for s in srcs):
+            subprocess.run(["make", "-C", str(ORACLE_DIR), str(so)], check=True, capture_output=True)
+        L = C.CDLL(str(so))
+        L.txc_file.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+        L.cns_run.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64]
+        _lib = L
+    return _lib
+
+
+def have_reference() -> bool:
+    return (REF / "Tax_class" / "NCBI-taxcollector-0.01.pl").exists() and shutil.which("perl") is not None
+
+
+def ref_tax_class() -> Path:
+    """the reference's tax_class: prebuilt oracle/_ref/tax_class, rebuilt here when the sources are present"""
+    if not REF_TAX_CLASS.exists() and (REF / "Tax_class" / "ncbitc.c").exists():
+        subprocess.run(["make", "-C", str(ORACLE_DIR), "ref"], check=True, capture_output=True)
+    return REF_TAX_CLASS
+
+
+def ref_build_bins(dump_dir: Path, out_dir: Path):
+    """tax_class -c of the reference in a scratch copy of the dumps"""
+    out_dir.mkdir(parents=True, exist_ok=True)
+    for f in ("nodes.dmp", "names.dmp", "gi_taxid_nucl.dmp"):
+        shutil.copy(Path(dump_dir) / f, out_dir / f)
+    subprocess.run([str(ref_tax_class()), "-c"], cwd=out_dir, check=True)
+
+
+def oracle_taxcollector(bin_dir, hits, out) -> int:
+    return lib().txc_file(str(bin_dir).encode(), str(hits).encode(), str(out).encode())
+
+
+def oracle_consensus(blast, rdp, out, grace=16) -> int:
+    return lib().cns_run(str(blast).encode(), str(rdp).encode(), str(out).encode(), grace)
+
+
+def real_taxcollector(dump_dir, hits, out):
+    with tempfile.TemporaryDirectory() as wd:
+        wd = Path(wd)
+        ref_build_bins(Path(dump_dir), wd / "Tax_class")
+        shutil.copy(ref_tax_class(), wd / "Tax_class" / "tax_class")
+        subprocess.run(["perl", str(REF / "Tax_class" / "NCBI-taxcollector-0.01.pl"), "-f", str(hits), "-o", str(out)],
+                       cwd=wd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+
+
+def real_consensus(blast, rdp, out, timeout=120):
+    subprocess.run(["perl", str(REF / "Consensus" / "Consensus_BLAST_SOAP_RDP-1.1.pl"), "-b", str(blast), "-r", str(rdp),
+                    "-o", str(out)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=timeout)
+
+
+def group_lineages(class_file):
+    ids, by = [], []
+    for l in Path(class_file).read_text().split("\n"):
+        if not l:
+            continue
+        f = l.split("\t")
+        if not ids or ids[-1] != f[0]:
+            ids.append(f[0])
+            by.append([])
+        by[-1].append(f[1] if len(f) > 1 else "")
+    return ids, by
