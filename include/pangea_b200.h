@@ -202,6 +202,18 @@ int pg_tax_leaf(pg_ctx *ctx, const pg_tax *t, const int32_t *gi_host, int64_t n,
 int pg_tax_lineage(pg_ctx *ctx, const pg_tax *t, const int32_t *gi_host, int64_t n,
                    char *out_bytes, int64_t out_cap, int64_t *out_off);
 
+/* Views for the drop-in `tax_class -s|-g|-t|-n` executable.  pg_tax_chain walks the parent
+ * chain on the device exactly like ncbitc.c:941-952 (the nodes whose parent is not 1, leaf
+ * first; chain_len < 0 = the walk left the node table after -1-chain_len nodes).  The two
+ * record getters copy the raw 28-/196-byte records (ncbitc.c:98-133) of the loaded files;
+ * pg_tax_name_records returns how many records `tax_class -n` would print. */
+int pg_tax_chain(pg_ctx *ctx, const pg_tax *t, const int32_t *taxid_host, int64_t n, int32_t maxlen,
+                 int32_t *chain_host, int32_t *chain_len_host);
+int pg_tax_node_record(const pg_tax *t, int32_t taxid, void *rec28);
+int pg_tax_name_records(const pg_tax *t, int32_t taxid, void *rec196, int32_t max_records);
+int64_t pg_tax_max_gi(const pg_tax *t);
+int64_t pg_tax_max_taxid(const pg_tax *t);
+
 /* ------------------------------------------------------------------ Stage C
  * Replaces: Consensus/Consensus_BLAST_SOAP_RDP-1.1.pl:96-237 (rows C2-C8).
  */
@@ -219,8 +231,13 @@ typedef struct {
     const int64_t *pident_off;     /* nhits+1                               */
     const char    *rdp_bytes;      /* per read: text after the five TABs    */
     const int64_t *rdp_off;        /* nreads+1                              */
+    int32_t        first_is_fresh; /* 1: read 0 is the first group the script ever flushes
+                                      ($blastsim still undef, :186-204); 0: it is "0" */
+    int32_t        reserved;
 } pg_consensus_in;
 
+/* winner_host[i] = -1 when no hit of read i updates the script's $tempresult (the script then
+ * prints the previous read's line again; the caller carries that over). */
 int pg_consensus(pg_ctx *ctx, const pg_consensus_in *in_host, int64_t *winner_host, int32_t *nmatch_host);
 
 #ifdef __cplusplus

@@ -1,0 +1,187 @@
+/*
+ * consensus -- drop-in for
+ *   perl Consensus_BLAST_SOAP_RDP-1.1.pl -b <blast_class> -r <rdp> [-s <soap>] -o <out>
+ * (Consensus/Consensus_BLAST_SOAP_RDP-1.1.pl; README.md:149-169).
+ * Same flags (the -s file is opened and never read, as in the script), same stdout lines,
+ * same output file: the winning BLAST line of every read followed by "#Matches found: N".
+ *
+ * The host part below is the script's single forward cursor over the BLAST file (C2, C8):
+ * it attaches each run of BLAST lines to the RDP line the script would compare it with and
+ * skips ("not found:") the BLAST ids that have no RDP line.  The per-hit rank matching and
+ * the per-read best-hit rules run on the GPU (pg_consensus).
+ *
+ * One documented deviation: where the script prints "not found:" forever (an RDP id with no
+ * BLAST line left), this program stops with a message on stderr and exit status 2.
+ */
+#include <getopt.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "pangea_b200.h"
+#include "pg_host_common.h"
+
+/* field k of split(/\t\t|\t/, line) */
+static int tab_field(const char *s, size_t n, int k, const char **f, size_t *fl)
+{
+    size_t p = 0, start = 0;
+    int idx = 0;
+    while (p < n) {
+        if (s[p] == '\t') {
+            size_t sep = (p + 1 < n && s[p + 1] == '\t') ? 2 : 1;
+            if (idx == k) { *f = s + start; *fl = p - start; return 1; }
+            idx++;
+            p += sep;
+            start = p;
+        } else p++;
+    }
+    if (idx == k) { *f = s + start; *fl = n - start; return 1; }   /* last field (may be empty -> dropped by Perl) */
+    *f = s; *fl = 0;
+    return 0;
+}
+
+typedef struct { char *p; size_t n, cap; } buf;
+static void buf_add(buf *b, const char *s, size_t n)
+{
+    if (b->n + n + 1 > b->cap) { b->cap = (b->n + n + 1) * 2 + 4096; b->p = (char *)realloc(b->p, b->cap); }
+    if (n) memcpy(b->p + b->n, s, n);
+    b->n += n;
+}
+
+int main(int argc, char **argv)
+{
+    static struct option lo[] = {{"device", required_argument, 0, 'G'}, {"quiet", no_argument, 0, 'Q'}, {0, 0, 0, 0}};
+    const char *pb = NULL, *pr = NULL, *ps = NULL, *po = NULL;
+    int device = 0, quiet = 0;
+    for (;;) {
+        int c = getopt_long(argc, argv, "b:r:s:o:", lo, NULL);
+        if (c == -1) break;
+        if (c == 'b') pb = optarg;
+        else if (c == 'r') pr = optarg;
+        else if (c == 's') ps = optarg;
+        else if (c == 'o') po = optarg;
+        else if (c == 'G') device = atoi(optarg);
+        else if (c == 'Q') quiet = 1;
+    }
+    if (!pb || !pr || !po) {
+        printf("Usage: perl Consensus-1.0.pl \n\t-b Classification results (Blast)\n\t-r Classification results (RDP)\n"
+               "\t-s Classification results (SOAP2)\n\t-o Output file (txt)\n");
+        return 0;
+    }
+    printf("\nLoading input files...\n");
+    pg_lines B, R;
+    if (pg_lines_read(pb, &B)) { printf("Error: Unable to open %s file.\n", pb); return 0; }
+    if (pg_lines_read(pr, &R)) { printf("Error: Unable to open %s file.\n", pr); return 0; }
+    if (ps) {
+        FILE *fs = fopen(ps, "r");                       /* C7: opened, never read */
+        if (!fs) { printf("Error: Unable to open %s file.\n", ps); return 0; }
+        fclose(fs);
+    }
+    printf("%s\n", po);
+    FILE *fo = fopen(po, "w");
+    if (!fo) { printf("Error: Unable to open output file %s.\n", po); return 0; }
+
+    /* ---- the cursor (C2, C8): which BLAST lines belong to which RDP line */
+    int64_t nr = R.count, nbl = B.count;
+    int64_t *hit_off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nr + 1));
+    int64_t *rdp_of_group = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nr + 1));
+    int64_t *hit_line = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nbl + 1));
+    int64_t ng = 0, nh = 0, i = 0;
+    int found = -1, stuck = 0;
+    for (int64_t r = 0; r < nr && !stuck; r++) {
+        const char *rid = R.line[r];
+        size_t ridn = R.len[r];
+        for (size_t p = 0; p + 5 <= R.len[r]; p++)
+            if (memcmp(R.line[r] + p, "\t\t\t\t\t", 5) == 0) { ridn = p; break; }
+        int open_group = 0;
+        for (;;) {
+            const char *bid = "";
+            size_t bidn = 0;
+            if (i < nbl) tab_field(B.line[i], B.len[i], 0, &bid, &bidn);
+            if (bidn == ridn && (ridn == 0 || memcmp(bid, rid, ridn) == 0)) {
+                if (i >= nbl) { stuck = 1; break; }        /* empty id against an exhausted BLAST file */
+                if (!open_group) { hit_off[ng] = nh; rdp_of_group[ng] = r; open_group = 1; }
+                found = 1;
+                hit_line[nh++] = i++;
+                continue;
+            }
+            if (found == 0) {
+                if (i >= nbl) { stuck = 1; break; }        /* the script loops forever here */
+                if (!quiet) { printf("not found: "); fwrite(bid, 1, bidn, stdout); printf("\t "); fwrite(rid, 1, ridn, stdout); printf("\n"); }
+                i++;
+                continue;
+            }
+            if (found == 1) { ng += open_group ? 1 : 0; found = 0; }
+            break;
+        }
+        /* a group still open when the cursor got stuck was never flushed by the script either */
+    }
+    hit_off[ng] = nh;
+
+    /* ---- per-hit / per-read text for the device */
+    buf lin = {0, 0, 0}, pid = {0, 0, 0}, rdp = {0, 0, 0};
+    int64_t *lin_off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nh + 1));
+    int64_t *pid_off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(nh + 1));
+    int64_t *rdp_off = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ng + 1));
+    for (int64_t h = 0; h < nh; h++) {
+        const char *f;
+        size_t fl;
+        lin_off[h] = (int64_t)lin.n;
+        pid_off[h] = (int64_t)pid.n;
+        const char *s = B.line[hit_line[h]];
+        size_t n = B.len[hit_line[h]];
+        tab_field(s, n, 1, &f, &fl);
+        buf_add(&lin, f, fl);
+        tab_field(s, n, 2, &f, &fl);
+        buf_add(&pid, f, fl);
+    }
+    lin_off[nh] = (int64_t)lin.n;
+    pid_off[nh] = (int64_t)pid.n;
+    for (int64_t g = 0; g < ng; g++) {
+        rdp_off[g] = (int64_t)rdp.n;
+        int64_t r = rdp_of_group[g];
+        const char *s = R.line[r];
+        size_t n = R.len[r];
+        for (size_t p = 0; p + 5 <= n; p++)
+            if (memcmp(s + p, "\t\t\t\t\t", 5) == 0) {
+                const char *rest = s + p + 5;
+                size_t rn = n - p - 5;
+                for (size_t q = 0; q + 5 <= rn; q++)
+                    if (memcmp(rest + q, "\t\t\t\t\t", 5) == 0) { rn = q; break; }
+                buf_add(&rdp, rest, rn);
+                break;
+            }
+    }
+    rdp_off[ng] = (int64_t)rdp.n;
+
+    int64_t *winner = (int64_t *)malloc(sizeof(int64_t) * (size_t)(ng + 1));
+    int32_t *nmatch = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ng + 1));
+    if (ng > 0) {
+        pg_ctx *ctx = pg_init(device);
+        if (!ctx) { fprintf(stderr, "consensus: %s\n", pg_last_error(NULL)); return 1; }
+        pg_consensus_in in;
+        memset(&in, 0, sizeof in);
+        in.nreads = ng; in.hit_off = hit_off;
+        in.lineage_bytes = lin.p ? lin.p : ""; in.lineage_off = lin_off;
+        in.pident_bytes = pid.p ? pid.p : ""; in.pident_off = pid_off;
+        in.rdp_bytes = rdp.p ? rdp.p : ""; in.rdp_off = rdp_off;
+        in.first_is_fresh = 1;
+        if (pg_consensus(ctx, &in, winner, nmatch) != PG_OK) { fprintf(stderr, "consensus: %s\n", pg_last_error(ctx)); return 1; }
+        pg_shutdown(ctx);
+    }
+    /* ---- output: "$tempresult\n#Matches found: N\n"; an unset $tempresult repeats the previous line */
+    int64_t prev = -1;
+    for (int64_t g = 0; g < ng; g++) {
+        int64_t wl = winner[g] >= 0 ? hit_line[winner[g]] : prev;
+        if (wl >= 0) fwrite(B.line[wl], 1, B.len[wl], fo);
+        fprintf(fo, "\n#Matches found: %d\n", nmatch[g]);
+        prev = wl;
+    }
+    fclose(fo);
+    if (stuck) {
+        fprintf(stderr, "consensus: an RDP id has no BLAST line left; the reference script would print "
+                        "\"not found:\" forever here -- stopping\n");
+        return 2;
+    }
+    printf("\nDone!\n");
+    return 0;
+}

@@ -64,6 +64,8 @@ class _ConsensusIn(C.Structure):
         ("pident_off", C.c_void_p),
         ("rdp_bytes", C.c_void_p),
         ("rdp_off", C.c_void_p),
+        ("first_is_fresh", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -143,6 +145,13 @@ def load_library() -> C.CDLL:
     lib.pg_tax_leaf.argtypes = [vp, vp, vp, i64, vp]
     lib.pg_tax_lineage.argtypes = [vp, vp, vp, i64, vp, i64, vp]
     lib.pg_consensus.argtypes = [vp, C.POINTER(_ConsensusIn), vp, vp]
+    lib.pg_tax_chain.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    lib.pg_tax_node_record.argtypes = [vp, i32, vp]
+    lib.pg_tax_name_records.argtypes = [vp, i32, vp, i32]
+    lib.pg_tax_max_gi.restype = i64
+    lib.pg_tax_max_gi.argtypes = [vp]
+    lib.pg_tax_max_taxid.restype = i64
+    lib.pg_tax_max_taxid.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -350,3 +359,65 @@ class Context:
         out = np.zeros((PG_NUM_BOOT, k), np.uint16)
         self._chk(self.lib.pg_boot_indices(self.h, n, min_boot_words, out.ctypes.data))
         return out
+
+
+    # ---- Stage B
+    def tax_load(self, directory) -> "Tax":
+        h = C.c_void_p()
+        self._chk(self.lib.pg_tax_load(self.h, str(directory).encode(), C.byref(h)))
+        return Tax(self, h.value)
+
+    # ---- Stage C
+    def consensus(self, hit_off, lineages, pidents, rdps, first_is_fresh=True):
+        """lineages/pidents: list[bytes] per hit; rdps: list[bytes] per read (text after the 5 TABs)."""
+        lb, lo = pack_sequences(lineages)
+        pb, po = pack_sequences(pidents)
+        rb, ro = pack_sequences(rdps)
+        hit_off = np.ascontiguousarray(hit_off, np.int64)
+        n = len(hit_off) - 1
+        inp = _ConsensusIn(n, hit_off.ctypes.data, lb.ctypes.data, lo.ctypes.data, pb.ctypes.data, po.ctypes.data,
+                           rb.ctypes.data, ro.ctypes.data, 1 if first_is_fresh else 0, 0)
+        win = np.zeros(n, np.int64)
+        nm = np.zeros(n, np.int32)
+        self._chk(self.lib.pg_consensus(self.h, C.byref(inp), win.ctypes.data, nm.ctypes.data))
+        return win, nm
+
+
+def tax_build(directory) -> None:
+    """== tax_class -c: pure file conversion, needs no GPU."""
+    lib = load_library()
+    rc = lib.pg_tax_build(str(directory).encode())
+    if rc != 0:
+        raise PangeaError(rc, lib.pg_last_error(None).decode())
+
+
+class Tax:
+    def __init__(self, ctx: Context, handle: int):
+        self.ctx, self.h = ctx, handle
+
+    def leaf(self, gi) -> np.ndarray:
+        gi = np.ascontiguousarray(gi, np.int32)
+        out = np.zeros(len(gi), np.int32)
+        self.ctx._chk(self.ctx.lib.pg_tax_leaf(self.ctx.h, self.h, gi.ctypes.data, len(gi), out.ctypes.data))
+        return out
+
+    def lineage(self, gi) -> list[bytes]:
+        gi = np.ascontiguousarray(gi, np.int32)
+        n = len(gi)
+        off = np.zeros(n + 1, np.int64)
+        cap = max(4096, 160 * n)
+        while True:
+            buf = np.zeros(cap, np.uint8)
+            rc = self.ctx.lib.pg_tax_lineage(self.ctx.h, self.h, gi.ctypes.data, n, buf.ctypes.data, cap, off.ctypes.data)
+            if rc == -6 and off[n] > cap:
+                cap = int(off[n]) + 64
+                continue
+            self.ctx._chk(rc)
+            break
+        raw = buf.tobytes()
+        return [raw[off[i]:off[i + 1]] for i in range(n)]
+
+    def free(self) -> None:
+        if self.h:
+            self.ctx.lib.pg_tax_free(self.h)
+            self.h = 0

@@ -97,3 +97,47 @@ def test_consensus_oracle_terminates_where_the_reference_loops(tmp_path):
     blast.write_text("A\t[0]Bacteria;\t90.0\n")
     rdp.write_text("A" + "\t" * 5 + "Bacteria\tdomain\t1.0\nB" + "\t" * 5 + "Bacteria\tdomain\t1.0\n")
     assert op.oracle_consensus(blast, rdp, tmp_path / "o.txt") == 1
+
+
+def _masked_bins_equal(ref_dir: Path, my_dir: Path):
+    """.bin files must be interchangeable.  The reference leaves bytes after a string's NUL (and
+    struct padding) uninitialised / stale (ncbitc.c:511-557); those bytes are don't-care."""
+    import numpy as np
+
+    assert (ref_dir / "gi_taxid_nucl.dmp.bin").read_bytes() == (my_dir / "gi_taxid_nucl.dmp.bin").read_bytes()
+    a = np.frombuffer((ref_dir / "nodes.dmp.bin").read_bytes(), np.uint8).reshape(-1, 28).copy()
+    b = np.frombuffer((my_dir / "nodes.dmp.bin").read_bytes(), np.uint8).reshape(-1, 28).copy()
+    assert a.shape == b.shape
+    for x in (a, b):
+        x[:, [15, 19, 27]] = 0                                   # struct padding
+        e = x[:, 9:12]
+        e[e[:, 0] == 0] = 0                                      # embl code: bytes after the first NUL
+        e[(e[:, 0] != 0) & (e[:, 1] == 0), 2] = 0
+    assert (a == b).all()
+    ra, rb = (ref_dir / "names.dmp.bin").read_bytes(), (my_dir / "names.dmp.bin").read_bytes()
+    assert len(ra) == len(rb) and ra[:4] == rb[:4]
+    a = np.frombuffer(ra[4:], np.uint8).reshape(-1, 196).copy()
+    b = np.frombuffer(rb[4:], np.uint8).reshape(-1, 196).copy()
+    assert (a[:, :4] == b[:, :4]).all()
+    for lo in (4, 68, 132):
+        for x, y in zip(a[:, lo:lo + 64], b[:, lo:lo + 64]):
+            sx, sy = bytes(x).split(b"\0")[0], bytes(y).split(b"\0")[0]
+            assert sx == sy
+
+
+@needs_ref_binary
+@pytest.mark.parametrize("case", ["tax_mini", "tax_synth"])
+def test_tax_build_writes_the_reference_bin_layout(case, tmp_path):
+    """pg_tax_build == `tax_class -c` (B1-B3): pure file conversion, runs without a GPU."""
+    import pangea_b200 as pg
+
+    op.ref_build_bins(GOLD / case, tmp_path / "ref")
+    mine = tmp_path / "mine"
+    mine.mkdir()
+    for f in ("nodes.dmp", "names.dmp", "gi_taxid_nucl.dmp"):
+        shutil.copy(GOLD / case / f, mine / f)
+    pg.tax_build(mine)
+    _masked_bins_equal(tmp_path / "ref", mine)
+    # and the reference's own reader accepts our files
+    out = subprocess.run([str(op.ref_tax_class()), "-n", "2" if case == "tax_mini" else "1"], cwd=mine, capture_output=True, text=True)
+    assert "scientific name" in out.stdout
