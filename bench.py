@@ -238,13 +238,11 @@ def main():
     else:
         model = ctx.model_create(G)
     if world > 1:
-        class _Dev:
-            def __init__(self, ptr, nbytes):
-                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        from pangea_b200 import dist as pgdist
+
         ctx.sync()
-        for ptr, nbytes in model.buffers():
-            t = torch.as_tensor(_Dev(ptr, nbytes), device=dev)
-            dist.broadcast(t, src=0)
+        pgdist.broadcast_buffers([torch.as_tensor(pgdist.DeviceBuffer(ptr, nbytes), device=dev)
+                                  for ptr, nbytes in model.buffers()], src=0)
         torch.cuda.synchronize()
         if rank != 0:
             model.commit()

@@ -359,3 +359,65 @@ def test_certified_close_genera(ctx):
     check_against_oracle(ctx, gm, om, tr["anc"], reads, mode=1)
     om.free()
     gm.free()
+
+
+# ------------------------------------------------------------------ BASELINE configs at their full sizes
+
+@pytest.fixture(scope="module")
+def baseline_model(ctx):
+    """the bench's model: synth16s(0x9178, 9178 seqs, 1219 genera) -- the stand-in for the
+    reference's absent rdp_download_9178seqs.fa"""
+    tr = synth.synth16s(0x9178, 9178, 1219)
+    gm = ctx.train(tr["data"], tr["off"], tr["genus"], tr["G"])
+    gm.set_lineage(tr["anc"])
+    om = ora.Model(tr["data"], tr["off"], tr["genus"], tr["G"])
+    yield tr, om, gm
+    om.free()
+    gm.free()
+
+
+def test_config0_real_16s_queries_vs_9178_model(ctx, baseline_model):
+    """configs[0]: real full-length 16S queries (subset of rdp_download_373seqs.fa) against the 9178-seq model"""
+    from pathlib import Path
+
+    tr, om, gm = baseline_model
+    ids, hdr, seqs = synth.read_fasta(Path(__file__).parent / "golden" / "rdp_373_subset.fa")
+    for mode in (0, 1):
+        check_against_oracle(ctx, gm, om, tr["anc"], seqs, mode=mode)
+
+
+def test_config1_self_classification_full_size(ctx, baseline_model):
+    """configs[1]: all 9178 training sequences against their own model.  Oracle parity on a
+    600-read sample; on the full set strict == certified record for record, >= 99 % self-genus,
+    votes(root) = 100 and monotone non-increasing down the lineage."""
+    tr, om, gm = baseline_model
+    n = len(tr["genus"])
+    sample = [tr["data"][tr["off"][i]:tr["off"][i + 1]].tobytes() for i in range(0, n, n // 600)]
+    check_against_oracle(ctx, gm, om, tr["anc"], sample, mode=1)
+    a, ba = ctx.classify(gm, tr["data"], tr["off"], mode=0, want_boot=True)
+    b, bb = ctx.classify(gm, tr["data"], tr["off"], mode=1, want_boot=True)
+    assert a.tobytes() == b.tobytes() and np.array_equal(ba, bb)
+    assert (a["genus"] == tr["genus"]).mean() >= 0.99
+    d = tr["anc"].shape[1]
+    assert (a["votes"][:, 0] == 100).all() and (np.diff(a["votes"][:, :d].astype(int), axis=1) <= 0).all()
+
+
+def test_config2_illumina_reads_full_size(ctx, baseline_model):
+    """configs[2]: 2^18 joined 250 bp pairs (the bench's step).  Oracle parity on a sample;
+    strict == certified on every record; checksum of the records is order-stable."""
+    from pangea_b200 import dist as pgdist
+
+    tr, om, gm = baseline_model
+    data, off, src = synth.synth_reads(0x250, tr, 1 << 18, paired=True)
+    reads = [data[off[i]:off[i + 1]].tobytes() for i in range(0, 1 << 18, 257)]
+    check_against_oracle(ctx, gm, om, tr["anc"], reads, mode=1)
+    a, ba = ctx.classify(gm, data, off, mode=0, want_boot=True)
+    b, bb = ctx.classify(gm, data, off, mode=1, want_boot=True)
+    st = ctx.classify_stats()
+    assert a.tobytes() == b.tobytes() and np.array_equal(ba, bb)
+    assert st["certified"] == 1 << 18
+    assert (a["genus"] == src).mean() > 0.95
+    assert pgdist.records_checksum(a) == pgdist.records_checksum(b)
+    # idempotence: classifying the same batch again gives the same records
+    c = ctx.classify(gm, data, off, mode=1)
+    assert c.tobytes() == b.tobytes()
