@@ -106,11 +106,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
+def ncu_traffic(reads_per_launch: float):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/classify_traffic.json), per launch: the capture was one
+    launch of 65536 reads, so it is carried to this run's launch size per read."""
     p = REPO / "profiles" / "classify_traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get("dram_bytes_per_launch")
+            return json.loads(p.read_text())["dram_bytes_per_read"] * reads_per_launch
         except Exception:
             return None
     return None
@@ -330,8 +333,8 @@ def main():
                            mode="strict" if args.mode == 0 else "certified", parallelism=f"reads sharded x{world}",
                            median_words=n_words),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                         "kernel": "k_classify", "kernel_ms_per_launch": kms / max(klaunch, 1),
+                         "frac": achieved / peak, "traffic": ncu_traffic(reads_per_launch), "peak_source": peak_src,
+                         "kernel": "k_classify_q" if args.mode == 1 else "k_classify_strict", "kernel_ms_per_launch": kms / max(klaunch, 1),
                          "kernel_share_of_step": kms / ms if ms > 0 else None,
                          "algorithmic_bytes_per_read": bpr, "reads_per_launch": reads_per_launch},
             "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": ms_e2e / args.steps,
