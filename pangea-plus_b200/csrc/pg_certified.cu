@@ -198,13 +198,13 @@ __device__ __forceinline__ void pg_epilogue_finish(unsigned mask, bool leader, i
     c0 = c1 = c2 = c3 = 0u;
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK > 512) ? 1 : ((BLOCK > 256) ? 2 : 3))
+__global__ void __launch_bounds__(BLOCK, (BLOCK > 512) ? 1 : ((BLOCK > 320) ? 2 : 3))
 k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
              const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
              const uint8_t *__restrict__ flags, const int32_t *__restrict__ order, int64_t read0,
              const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot, int G,
              double vmax, unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand,
-             unsigned long long *__restrict__ cand)
+             unsigned long long *__restrict__ cand, const int32_t *__restrict__ guess)
 {
     constexpr int LPR = 8;                          // lanes per 128-byte row (64 genera x 16 bit)
     constexpr int NGR = (BLOCK - 32) / LPR;
@@ -216,10 +216,22 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
     if (flags[2 * read + 1]) return;                // short read (A2)
     const int n = nwords[read];
     if (n == 0) return;                             // no word: phase 2 writes genus 0 directly
-    const int gbase = blockIdx.y * 64;
-    const uint16_t *tbase = qtable + (size_t)blockIdx.y * PG_NWORDS * 64;
-    const uint16_t *w = words + off[read];
     const size_t rc = (size_t)(read - read0);
+    // Branch and bound over genus blocks: grid row 0 takes the read's most promising block
+    // (k_guess_block) and runs it in full, which seeds the champion slots; every other block
+    // then stops a replicate as soon as ALL its 64 partial sums exceed champion + margin --
+    // deficits are non-negative, so a partial sum is a lower bound of the final one and no
+    // genus of the block can be the winner or a near-tie any more.
+    int blk = blockIdx.y;
+    bool prune_on = false;
+    if (guess) {
+        const int gs = guess[rc];
+        blk = (blockIdx.y == 0) ? gs : (((int)blockIdx.y - 1 < gs) ? (int)blockIdx.y - 1 : (int)blockIdx.y);
+        prune_on = blockIdx.y != 0;
+    }
+    const int gbase = blk * 64;
+    const uint16_t *tbase = qtable + (size_t)blk * PG_NWORDS * 64;
+    const uint16_t *w = words + off[read];
     unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
     unsigned int *mync = ncand + rc;
     unsigned long long *mycand = cand + rc * PG_CANDCAP;
@@ -235,6 +247,12 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
     if (tid < 32) {
         // ---- full sum (task 0): lane = one packed pair of genera, 16 rows per spill
         const uint32_t *col = reinterpret_cast<const uint32_t *>(sQ) + tid;
+        const uint32_t margin_full = pg_margin(n, vmax);
+        unsigned long long thr_full = ~0ULL;
+        if (prune_on) {
+            const unsigned long long c0v = *reinterpret_cast<volatile unsigned long long *>(mychamp);
+            if (c0v != PG_CHAMP_INIT) thr_full = (c0v >> 32) + margin_full;
+        }
         uint32_t lo = 0u, hi = 0u;
         int j = 0;
         for (; j + 16 <= n; j += 16) {
@@ -245,6 +263,7 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
             for (int u = 0; u < 16; u++) c += v[u];
             lo += c & 0xFFFFu;
             hi += c >> 16;
+            if (prune_on && (unsigned long long)__reduce_min_sync(0xffffffffu, min(lo, hi)) > thr_full) return;
         }
         uint32_t c = 0u;
         for (; j < n; j++) c += col[j * 32];
@@ -254,7 +273,7 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
         PgPending pp;
         pg_epilogue_begin<2>(0xffffffffu, tid == 0, sums, (uint32_t)(gbase + 2 * tid), (uint32_t)gbase, G, mychamp, pp);
         pg_epilogue_finish<2>(0xffffffffu, tid == 0, 0, sums, (uint32_t)(gbase + 2 * tid), (uint32_t)gbase, G, 0,
-                              pg_margin(n, vmax), pp, mync, mycand);
+                              margin_full, pp, mync, mycand);
         return;
     }
 
@@ -280,30 +299,60 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
 #define PG_LD4(d, q) d##0 = PG_QROW((q).x); d##1 = PG_QROW((q).y); d##2 = PG_QROW((q).z); d##3 = PG_QROW((q).w);
 #define PG_ADD16(d) PG_QADD4(d##0) PG_QADD4(d##1) PG_QADD4(d##2) PG_QADD4(d##3)
     const int nquad = nb >> 2, tail = nb & 3;
+#define PG_LD4P(d, q) if (active) { PG_LD4(d, q) }
+    // lower bound of the group's smallest total: spilled part + packed part (min of sums >= sum of mins)
+#define PG_PRUNE_CHECK()                                                                        \
+    {                                                                                           \
+        const uint32_t m2 = __vminu2(__vminu2(c0, c1), __vminu2(c2, c3));                        \
+        uint32_t lb = smin + min(m2 & 0xFFFFu, m2 >> 16);                                        \
+        lb = min(lb, __shfl_xor_sync(0xffffffffu, lb, 1));                                       \
+        lb = min(lb, __shfl_xor_sync(0xffffffffu, lb, 2));                                       \
+        lb = min(lb, __shfl_xor_sync(0xffffffffu, lb, 4));                                       \
+        if ((unsigned long long)lb > thr) active = false;                                        \
+    }
+    unsigned long long champ_next = PG_CHAMP_INIT;
+    if (prune_on && group < PG_NUM_BOOT) champ_next = *reinterpret_cast<volatile unsigned long long *>(mychamp + 1 + group);
     for (int task = group; task < PG_NUM_BOOT; task += NGR) {
         uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
         uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u, s4 = 0u, s5 = 0u, s6 = 0u, s7 = 0u;
+        uint32_t smin = 0u;
+        bool active = true;
+        // champion of this replicate as of a moment ago (stale values are larger: conservative)
+        const unsigned long long thr = (champ_next == PG_CHAMP_INIT) ? ~0ULL : (champ_next >> 32) + margin;
+        if (prune_on && task + NGR < PG_NUM_BOOT)
+            champ_next = *reinterpret_cast<volatile unsigned long long *>(mychamp + 1 + task + NGR);
         const uint4 *lp = lists + (size_t)(task / IL) * nb * IL + (task % IL);
         uint4 qa = __ldg(lp), qb = __ldg(lp + IL);
         uint4 x0, x1, x2, x3, y0, y1, y2, y3;
+        x0 = x1 = x2 = x3 = y0 = y1 = y2 = y3 = make_uint4(0u, 0u, 0u, 0u);
         PG_LD4(x, qa)
         // four 4-draw batches per trip: loads run one batch ahead of the adds, list reads two;
-        // 16 rows x 4095 < 2^16, so the packed accumulators are spilled once per trip
+        // 16 rows x 4095 < 2^16, so the packed accumulators are spilled once per trip.
+        // The four groups of a warp walk in lockstep; a pruned group stops issuing LDS.
         int b = 0;
         for (int it = 0; it < nquad; it++, b += 4) {
-            PG_LD4(y, qb) qa = __ldg(lp + (b + 2) * IL); PG_ADD16(x)
-            PG_LD4(x, qa) qb = __ldg(lp + (b + 3) * IL); PG_ADD16(y)
-            PG_LD4(y, qb) qa = __ldg(lp + (b + 4) * IL); PG_ADD16(x)
-            if (b + 4 < nb) { PG_LD4(x, qa) }
+            PG_LD4P(y, qb) qa = __ldg(lp + (b + 2) * IL); PG_ADD16(x)
+            PG_LD4P(x, qa) qb = __ldg(lp + (b + 3) * IL); PG_ADD16(y)
+            if (prune_on) {
+                PG_PRUNE_CHECK()
+                if (!__any_sync(0xffffffffu, active)) break;
+            }
+            PG_LD4P(y, qb) qa = __ldg(lp + (b + 4) * IL); PG_ADD16(x)
+            if (b + 4 < nb) { PG_LD4P(x, qa) }
             qb = __ldg(lp + (b + 5) * IL);
             PG_ADD16(y)
             PG_QSPILL()
+            if (prune_on) {
+                smin = min(min(min(s0, s1), min(s2, s3)), min(min(s4, s5), min(s6, s7)));
+                PG_PRUNE_CHECK()
+                if (!__any_sync(0xffffffffu, active)) break;
+            }
         }
-        if (tail) {                                 // x holds batch b, qb the list entry of batch b+1
-            if (tail >= 2) { PG_LD4(y, qb) qa = __ldg(lp + (b + 2) * IL); }
+        if (tail && __any_sync(0xffffffffu, active)) {   // x holds batch b, qb the list entry of batch b+1
+            if (tail >= 2) { PG_LD4P(y, qb) qa = __ldg(lp + (b + 2) * IL); }
             PG_ADD16(x)
             if (tail >= 2) {
-                if (tail == 3) { PG_LD4(x, qa) }
+                if (tail == 3) { PG_LD4P(x, qa) }
                 PG_ADD16(y)
                 if (tail == 3) { PG_ADD16(x) }
             }
@@ -313,15 +362,56 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
         if (ptask >= 0)
             pg_epilogue_finish<8>(gmask, l == 0, leader_lane, psum, genus0, (uint32_t)gbase, G, 1 + ptask, margin, pend,
                                   mync, mycand);
-        psum[0] = s0; psum[1] = s1; psum[2] = s2; psum[3] = s3;
-        psum[4] = s4; psum[5] = s5; psum[6] = s6; psum[7] = s7;
-        ptask = task;
-        pg_epilogue_begin<8>(gmask, l == 0, psum, genus0, (uint32_t)gbase, G, mychamp + 1 + task, pend);
+        ptask = -1;
+        if (active) {                                   // not pruned: this block may hold the winner or a near-tie
+            psum[0] = s0; psum[1] = s1; psum[2] = s2; psum[3] = s3;
+            psum[4] = s4; psum[5] = s5; psum[6] = s6; psum[7] = s7;
+            ptask = task;
+            pg_epilogue_begin<8>(gmask, l == 0, psum, genus0, (uint32_t)gbase, G, mychamp + 1 + task, pend);
+        }
     }
     if (ptask >= 0)
         pg_epilogue_finish<8>(gmask, l == 0, leader_lane, psum, genus0, (uint32_t)gbase, G, 1 + ptask, margin, pend, mync,
                               mycand);
+#undef PG_LD4P
+#undef PG_PRUNE_CHECK
 #undef PG_QROW
+}
+
+// ------------------------------------------------------------------ phase 0: most promising block
+
+// One warp per read: deficit sums over 16 evenly spaced words for every genus block; the block
+// holding the smallest sum is processed first and in full.  A wrong guess costs pruning
+// efficiency only, never correctness.
+__global__ void __launch_bounds__(256)
+k_guess_block(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
+              const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
+              const int32_t *__restrict__ order, int nreads_b, int64_t read0, int ntile64, int32_t *__restrict__ guess)
+{
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slot >= nreads_b) return;
+    const int64_t read = order[slot];
+    const int n = nwords[read];
+    int best = 0;
+    if (n > 0) {
+        const uint16_t *w = words + off[read];
+        const int ns = n < 16 ? n : 16, stride = n / ns;
+        uint32_t wv[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) wv[j] = j < ns ? (uint32_t)__ldg(w + j * stride) : 0u;
+        const uint32_t *q32 = reinterpret_cast<const uint32_t *>(qtable);
+        uint32_t bestv = 0xFFFFFFFFu;
+        for (int b = 0; b < ntile64; b++) {
+            uint32_t acc = 0u;                           // 16 rows x 4095 < 2^16: no carry between the halves
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (j < ns) acc += __ldg(q32 + ((size_t)b * PG_NWORDS + wv[j]) * 32 + lane);
+            const uint32_t v = __reduce_min_sync(0xffffffffu, min(acc & 0xFFFFu, acc >> 16));
+            if (v < bestv) { bestv = v; best = b; }
+        }
+    }
+    if (lane == 0) guess[read - read0] = best;
 }
 
 // ------------------------------------------------------------------ phase 2
@@ -498,13 +588,13 @@ template <int BLOCK>
 static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, size_t smem, const uint16_t *d_words,
                     const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags, const int32_t *d_order,
                     int64_t read0, int min_boot, unsigned long long *d_champ, unsigned int *d_ncand,
-                    unsigned long long *d_cand)
+                    unsigned long long *d_cand, const int32_t *d_guess)
 {
     PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nreads_b, (unsigned)md->ntile64);
     k_classify_q<BLOCK><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
                                                           read0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->G,
-                                                          md->vmax, d_champ, d_ncand, d_cand);
+                                                          md->vmax, d_champ, d_ncand, d_cand, d_guess);
     PG_LAUNCHED(ctx);
     return PG_OK;
 }
@@ -513,14 +603,32 @@ static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, size_t s
 int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsigned nreads_b, int nmax,
                         const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
                         const uint8_t *d_flags, const int32_t *d_order, int64_t read0, int min_boot,
-                        unsigned long long *d_champ, unsigned int *d_ncand, unsigned long long *d_cand)
+                        unsigned long long *d_champ, unsigned int *d_ncand, unsigned long long *d_cand,
+                        int32_t *d_guess)
 {
     const size_t smem = (size_t)(nmax + 1) * 128;
+    static int noprune = -1;                            // PG_NO_PRUNE=1: every block in full (A/B switch for profiling)
+    if (noprune < 0) { const char *e = getenv("PG_NO_PRUNE"); noprune = (e && atoi(e)) ? 1 : 0; }
+    if (noprune || md->ntile64 < 2) d_guess = NULL;
+    if (d_guess) {
+        k_guess_block<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_order,
+                                                                  (int)nreads_b, read0, md->ntile64, d_guess);
+        PG_LAUNCHED(ctx);
+    }
+    // experiment hook: PG_Q_BLOCK overrides the block size of the small-read buckets
+    static int forced = -1;
+    if (forced < 0) { const char *e = getenv("PG_Q_BLOCK"); forced = e ? atoi(e) : 0; }
+    if (bk.block == 192 && forced == 256)
+        return launch_q<256>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
+    if (bk.block == 192 && forced == 320)
+        return launch_q<320>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
+    if (bk.block == 192 && forced == 160)
+        return launch_q<160>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
     if (bk.block == 192)
-        return launch_q<192>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand);
+        return launch_q<192>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
     if (bk.block == 448)
-        return launch_q<448>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand);
-    return launch_q<832>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand);
+        return launch_q<448>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
+    return launch_q<832>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
 }
 
 // phase 2 for one bucket: strict re-check of survivors + vote; overflowing reads go to fb_list

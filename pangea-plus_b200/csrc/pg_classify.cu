@@ -229,7 +229,8 @@ static int launch_strict(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, uns
 int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsigned nreads_b, int nmax,
                         const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
                         const uint8_t *d_flags, const int32_t *d_order, int64_t read0, int min_boot,
-                        unsigned long long *d_champ, unsigned int *d_ncand, unsigned long long *d_cand);
+                        unsigned long long *d_champ, unsigned int *d_ncand, unsigned long long *d_cand,
+                        int32_t *d_guess);
 int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, const uint16_t *d_words,
                         const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags,
                         const int32_t *d_order, int64_t read0, int min_boot, const unsigned long long *d_champ,
@@ -353,6 +354,7 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
         d_cand = (unsigned long long *)ctx->s_candl.p;
         d_fbc = (int *)ctx->s_fb.p;
         d_fbl = (int32_t *)ctx->s_fb.p + 4;
+        PG_TRY(pg_scratch(ctx, &ctx->s_guess, (size_t)cmax * 4));
     }
     const int wpb = 8;
 
@@ -427,7 +429,7 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
                 cudaEvent_t e0 = take_event(ctx), e1 = take_event(ctx);
                 PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
                 PG_TRY(pg_certified_phase1(ctx, md, bk, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords, d_flags, ord,
-                                           c0, min_boot, d_champ, d_ncand, d_cand));
+                                           c0, min_boot, d_champ, d_ncand, d_cand, (int32_t *)ctx->s_guess.p));
                 PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
                 ctx->ev_pending.push_back(std::make_pair(e0, e1));
                 PG_TRY(pg_certified_phase2(ctx, md, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords, d_flags, ord, c0,

@@ -40,8 +40,8 @@ struct pg_ctx {
         void  *p;
         size_t cap;
     } s_words, s_nwords, s_flags, s_best, s_order, s_results, s_boot, s_bytes, s_off, s_cand,
-      s_champ, s_ncand, s_candl, s_fb;
-    static const int kNumScratch = 14;
+      s_champ, s_ncand, s_candl, s_fb, s_guess;
+    static const int kNumScratch = 15;
     // pinned host staging
     void  *h_pin;
     size_t h_pin_cap;
