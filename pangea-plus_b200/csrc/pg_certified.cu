@@ -304,12 +304,12 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
 #define PG_PRUNE_CHECK()                                                                        \
     {                                                                                           \
         const uint32_t m2 = __vminu2(__vminu2(c0, c1), __vminu2(c2, c3));                        \
-        uint32_t lb = smin + min(m2 & 0xFFFFu, m2 >> 16);                                        \
-        lb = min(lb, __shfl_xor_sync(0xffffffffu, lb, 1));                                       \
-        lb = min(lb, __shfl_xor_sync(0xffffffffu, lb, 2));                                       \
-        lb = min(lb, __shfl_xor_sync(0xffffffffu, lb, 4));                                       \
-        if ((unsigned long long)lb > thr) active = false;                                        \
+        const uint32_t lb = smin + min(m2 & 0xFFFFu, m2 >> 16);                                  \
+        /* the group is pruned when every one of its 8 lanes is above the threshold: one vote */ \
+        const unsigned over = __ballot_sync(0xffffffffu, (unsigned long long)lb > thr);          \
+        if (((over >> gshift) & 0xFFu) == 0xFFu) active = false;                                 \
     }
+    const int gshift = (lane / LPR) * LPR;
     unsigned long long champ_next = PG_CHAMP_INIT;
     if (prune_on && group < PG_NUM_BOOT) champ_next = *reinterpret_cast<volatile unsigned long long *>(mychamp + 1 + group);
     for (int task = group; task < PG_NUM_BOOT; task += NGR) {
