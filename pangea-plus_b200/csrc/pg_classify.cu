@@ -333,7 +333,12 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
 
     const bool certified = (mode == 1) && md->q_ok;
     ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
-    const int64_t CHUNK = certified ? (1 << 18) : (1 << 20);
+    // certified mode walks the 20 genus blocks of a chunk one after the other (tile-major grid);
+    // the chunk's word ids, champion slots and near-tie lists should stay in the 126 MB L2
+    // across those passes, so the chunk is kept small (2^14 reads: 16 MB + 13 MB + 17 MB worst case; measured best)
+    static int64_t chunk_override = -1;
+    if (chunk_override < 0) { const char *e = getenv("PG_CHUNK_LOG2"); chunk_override = e ? atoi(e) : 0; }
+    const int64_t CHUNK = certified ? ((int64_t)1 << (chunk_override ? chunk_override : 14)) : (1 << 20);
     const int nkeys = PG_NUM_BOOT + 1;
     const int64_t cmax = count < CHUNK ? count : CHUNK;
     PG_TRY(pg_scratch(ctx, &ctx->s_best, (size_t)cmax * nkeys * 8));
