@@ -11,6 +11,18 @@
 //   int64 idx[65537] | int32 genus[npairs] | int32 count[npairs] | blob
 #include "pg_internal.cuh"
 
+// one warp per word: its (genus, count) pairs go to m[genus/32][word][genus%32]
+__global__ void k_scatter_counts(const int64_t *__restrict__ idx, const int32_t *__restrict__ genus,
+                                 const int32_t *__restrict__ count, int32_t *__restrict__ m)
+{
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= PG_NWORDS) return;
+    for (int64_t p = idx[w] + (threadIdx.x & 31); p < idx[w + 1]; p += 32) {
+        const int g = genus[p];
+        m[((size_t)(g >> 5) * PG_NWORDS + w) * PG_GENUS_TILE + (g & 31)] = count[p];
+    }
+}
+
 static const char kMagic[8] = {'P', 'G', 'M', 'O', 'D', 'E', 'L', '1'};
 
 extern "C" int pg_model_save(const pg_model *md, const char *path, const void *blob, int64_t blob_len)
@@ -92,23 +104,33 @@ extern "C" int pg_model_load(pg_ctx *ctx, const char *path, pg_model **out, void
     pg_model *md = NULL;
     int rc = pg_model_create(ctx, G, &md);
     if (rc != PG_OK) { free(b); return rc; }
-    // scatter the sparse counts into the genus-tiled layout on the host, upload once
-    size_t cells = (size_t)md->ntile * PG_NWORDS * PG_GENUS_TILE;
-    std::vector<int32_t> tiled(cells, 0);
-    for (int w = 0; w < PG_NWORDS; w++)
-        for (int64_t p = idx[w]; p < idx[w + 1]; p++) {
-            int g = pgx[p];
-            tiled[((size_t)(g >> 5) * PG_NWORDS + w) * PG_GENUS_TILE + (g & 31)] = pcx[p];
-        }
+    // upload the sparse pairs and scatter them into the genus-tiled layout on the device
     unsigned long long N64 = (unsigned long long)N;
+    int64_t *d_idx = NULL;
+    int32_t *d_pg = NULL, *d_pc = NULL;
     cudaError_t e;
-    if ((e = cudaMemcpy(md->d_m, tiled.data(), cells * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+    if ((e = cudaMalloc(&d_idx, (PG_NWORDS + 1) * 8)) != cudaSuccess ||
+        (e = cudaMalloc(&d_pg, (size_t)(npairs + 1) * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&d_pc, (size_t)(npairs + 1) * 4)) != cudaSuccess ||
+        (e = cudaMemcpy(d_idx, idx.data(), (PG_NWORDS + 1) * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(d_pg, pgx.data(), (size_t)npairs * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(d_pc, pcx.data(), (size_t)npairs * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(md->d_nw, nw.data(), PG_NWORDS * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(md->d_M, M.data(), (size_t)G * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(md->d_N, &N64, 8, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        cudaFree(d_idx); cudaFree(d_pg); cudaFree(d_pc);
         pg_model_free(md);
         free(b);
         return pg_fail(ctx, PG_ECUDA, "pg_model_load: upload failed: %s", cudaGetErrorString(e));
+    }
+    k_scatter_counts<<<PG_NWORDS / 8, 256, 0, ctx->stream>>>(d_idx, d_pg, d_pc, md->d_m);
+    ctx->launches++;
+    e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_idx); cudaFree(d_pg); cudaFree(d_pc);
+    if (e != cudaSuccess) {
+        pg_model_free(md);
+        free(b);
+        return pg_fail(ctx, PG_ECUDA, "pg_model_load: scatter failed: %s", cudaGetErrorString(e));
     }
     rc = pg_model_commit(md);
     if (rc == PG_OK && depth > 0) rc = pg_model_set_lineage(md, anc.data(), depth);

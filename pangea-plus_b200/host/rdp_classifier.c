@@ -25,6 +25,14 @@
 #include <string.h>
 #include "pangea_b200.h"
 #include "pg_host_common.h"
+#include <time.h>
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 typedef struct {
     int    nnodes;
@@ -234,8 +242,12 @@ int main(int argc, char **argv)
     }
     int ifmt = strcmp(fmt, "allrank") == 0 ? 0 : strcmp(fmt, "fixrank") == 0 ? 1 : strcmp(fmt, "pangea") == 0 ? 2 : -1;
     if (ifmt < 0) { fprintf(stderr, "rdp_classifier: unknown format %s\n", fmt); return 1; }
+    const int timing = getenv("PG_TIMING") != NULL;
+    double t0 = now_s(), t1;
     pg_ctx *ctx = pg_init(device);
     if (!ctx) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(NULL)); return 1; }
+#define LAP(what) do { if (timing) { t1 = now_s(); fprintf(stderr, "[timing] %-22s %.3f s\n", what, t1 - t0); t0 = t1; } } while (0)
+    LAP("pg_init");
     if (train) {
         int rc = do_train(ctx, train, model, ranks, genus_token);
         pg_shutdown(ctx);
@@ -248,8 +260,10 @@ int main(int argc, char **argv)
     if (pg_model_load(ctx, model, &md, &blob, &blen) != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx)); return 1; }
     taxonomy t;
     if (!blob || tax_from_blob((const char *)blob, blen, &t)) { fprintf(stderr, "rdp_classifier: %s has no taxonomy section\n", model); return 1; }
+    LAP("model load");
     pg_fasta fa;
     if (pg_fasta_read(q, &fa)) { fprintf(stderr, "rdp_classifier: cannot read %s\n", q); return 1; }
+    LAP("FASTA parse");
     FILE *fo = fopen(o, "w");
     if (!fo) { fprintf(stderr, "rdp_classifier: cannot write %s\n", o); return 1; }
     pg_result *res = (pg_result *)malloc(sizeof(pg_result) * (size_t)(fa.count + 1));
@@ -259,7 +273,23 @@ int main(int argc, char **argv)
     opts.min_boot_words = min_boot;
     opts.mode = strict ? 0 : 1;
     if (pg_classify(ctx, md, &sb, &opts, res, NULL) != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx)); return 1; }
+    LAP("pg_classify");
     static const char *FIX[6] = {"domain", "phylum", "class", "order", "family", "genus"};
+    /* Output is assembled from pieces prepared once per taxon ("\tname\trank\t") and once per vote
+     * count (the 101 possible confidences), so a line costs a few memcpy()s, not a dozen fprintf()s. */
+    char conf_tab[101][8];
+    for (int v = 0; v <= 100; v++) pg_fmt_conf(v, conf_tab[v]);
+    char **piece = (char **)malloc(sizeof(char *) * (size_t)t.nnodes);
+    size_t *piece_len = (size_t *)malloc(sizeof(size_t) * (size_t)t.nnodes);
+    for (int k = 0; k < t.nnodes; k++) {
+        size_t n = strlen(t.name[k]) + strlen(t.rank[k]) + 4;
+        piece[k] = (char *)malloc(n);
+        piece_len[k] = (size_t)snprintf(piece[k], n, "\t%s\t%s\t", t.name[k], t.rank[k]);
+    }
+    size_t ocap = (size_t)8 << 20, on = 0;
+    char *obuf = (char *)malloc(ocap);
+#define OUT_ROOM(need) do { if (on + (need) > ocap) { fwrite(obuf, 1, on, fo); on = 0; } } while (0)
+#define OUT_STR(s, n) do { memcpy(obuf + on, (s), (n)); on += (n); } while (0)
     for (int64_t i = 0; i < fa.count; i++) {
         const pg_result *r = &res[i];
         if (r->status) {
@@ -268,9 +298,11 @@ int main(int argc, char **argv)
         }
         int path[PG_MAX_DEPTH], np = 0;                   /* the genus' lineage, leaf first */
         for (int n = t.genus_node[r->genus]; n >= 0 && np < PG_MAX_DEPTH; n = t.parent[n]) path[np++] = n;
-        char conf[8];
-        if (ifmt == 2) fprintf(fo, "%s\t\t\t\t\t", fa.id[i]);
-        else fprintf(fo, "%s\t%s", fa.id[i], r->reversed ? "-" : "");
+        size_t idlen = strlen(fa.id[i]);
+        OUT_ROOM(idlen + 16 + (size_t)np * 256);
+        OUT_STR(fa.id[i], idlen);
+        if (ifmt == 2) OUT_STR("\t\t\t\t", 4);           /* with the piece's own leading TAB: five */
+        else { OUT_STR("\t", 1); if (r->reversed) OUT_STR("-", 1); }
         if (ifmt == 1) {
             for (int k = 0; k < 6; k++) {
                 int pick = -1;
@@ -280,20 +312,22 @@ int main(int argc, char **argv)
                     for (int j = np - 1; j >= 0 && pick < 0; j--)
                         if (strcmp(t.rank[path[j]], FIX[kk]) == 0) pick = j;
                 if (pick < 0) continue;
-                pg_fmt_conf(r->votes[t.depth[path[pick]]], conf);
-                fprintf(fo, "\t%s\t%s\t%s", t.name[path[pick]], FIX[k], conf);
+                const char *c = conf_tab[r->votes[t.depth[path[pick]]]];
+                on += (size_t)sprintf(obuf + on, "\t%s\t%s\t%s", t.name[path[pick]], FIX[k], c);
             }
         } else {
-            int first = 1;
             for (int j = np - 1; j >= 0; j--) {
                 if (ifmt == 2 && t.depth[path[j]] == 0) continue;        /* Root cells are blank in the 5-TAB layout */
-                pg_fmt_conf(r->votes[t.depth[path[j]]], conf);
-                fprintf(fo, "%s%s\t%s\t%s", (ifmt == 2 && first) ? "" : "\t", t.name[path[j]], t.rank[path[j]], conf);
-                first = 0;
+                const char *c = conf_tab[r->votes[t.depth[path[j]]]];
+                OUT_STR(piece[path[j]], piece_len[path[j]]);
+                OUT_STR(c, strlen(c));
             }
         }
-        fputc('\n', fo);
+        OUT_STR("\n", 1);
     }
+    fwrite(obuf, 1, on, fo);
+    free(obuf);
+    LAP("format + write");
     fclose(fo);
     free(res);
     pg_free(blob);
