@@ -197,8 +197,10 @@ __device__ __forceinline__ void pg_epilogue_finish(unsigned mask, bool leader, i
     s4 += c2 & 0xFFFFu; s5 += c2 >> 16; s6 += c3 & 0xFFFFu; s7 += c3 >> 16;           \
     c0 = c1 = c2 = c3 = 0u;
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK > 512) ? 1 : ((BLOCK > 320) ? 2 : 3))
+// MINB = CTAs/SM the register budget must allow (a 4- or 5-CTA budget for short reads was measured:
+// the spills cost more than the occupancy brings)
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
 k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
              const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
              const uint8_t *__restrict__ flags, const int32_t *__restrict__ order, int64_t read0,
@@ -584,15 +586,15 @@ k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, c
 
 // ------------------------------------------------------------------ host
 
-template <int BLOCK>
+template <int BLOCK, int MINB>
 static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, size_t smem, const uint16_t *d_words,
                     const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags, const int32_t *d_order,
                     int64_t read0, int min_boot, unsigned long long *d_champ, unsigned int *d_ncand,
                     unsigned long long *d_cand, const int32_t *d_guess)
 {
-    PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nreads_b, (unsigned)md->ntile64);
-    k_classify_q<BLOCK><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
+    k_classify_q<BLOCK, MINB><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
                                                           read0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->G,
                                                           md->vmax, d_champ, d_ncand, d_cand, d_guess);
     PG_LAUNCHED(ctx);
@@ -615,20 +617,11 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
                                                                   (int)nreads_b, read0, md->ntile64, d_guess);
         PG_LAUNCHED(ctx);
     }
-    // experiment hook: PG_Q_BLOCK overrides the block size of the small-read buckets
-    static int forced = -1;
-    if (forced < 0) { const char *e = getenv("PG_Q_BLOCK"); forced = e ? atoi(e) : 0; }
-    if (bk.block == 192 && forced == 256)
-        return launch_q<256>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
-    if (bk.block == 192 && forced == 320)
-        return launch_q<320>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
-    if (bk.block == 192 && forced == 160)
-        return launch_q<160>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
     if (bk.block == 192)
-        return launch_q<192>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
+        return launch_q<192, 3>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
     if (bk.block == 448)
-        return launch_q<448>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
-    return launch_q<832>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
+        return launch_q<448, 2>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
+    return launch_q<832, 1>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
 }
 
 // phase 2 for one bucket: strict re-check of survivors + vote; overflowing reads go to fb_list
