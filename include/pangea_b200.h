@@ -240,6 +240,28 @@ typedef struct {
  * prints the previous read's line again; the caller carries that over). */
 int pg_consensus(pg_ctx *ctx, const pg_consensus_in *in_host, int64_t *winner_host, int32_t *nmatch_host);
 
+/* ------------------------------------------------------------------ Trim join (widening: SURVEY.md 8(f) next-1)
+ * Replaces: `perl trim2.3.pl -a <read 1> [-b <read 2>] [-g gap] [-t truncate]`  (README.md:31-33;
+ * Trim/trim2.4.pl parse_qseq :169-242, trim_qseq :244-298, parse_fastq :467-521, trim_fastq :527-578):
+ * quality trim of Illumina QSEQ pairs or FASTQ records and the mateA + N x gap + mateB join that
+ * defines the reads entering Stage A.
+ */
+typedef struct {
+    int32_t gap;        /* -g, the script's default is 189                                        */
+    int32_t truncate;   /* -t, default 11 (QSEQ only)                                             */
+    int32_t reserved[6];/* the script's -qc / -lc cannot be parsed by its own getopts string:
+                           quality cutoff 20 and length cutoff 70 are constants of the contract  */
+} pg_trim_opts;
+
+/* a_host / b_host: the whole input files.  FASTQ ('@' first): b_host is ignored and `paired` says
+ * whether -b was given (the script then takes the second mate from the NEXT record of the same
+ * file); otherwise QSEQ pairs, line i of a with line i of b.  out_host receives the text of
+ * <prefix>_runblast.fasta; PG_ERANGE (needed size in *out_len) when out_cap is too small.
+ * reads_out (optional): the joined sequences, same order, already in the packed device read store
+ * for pg_classify_packed -- records the trim dropped are simply absent from both outputs. */
+int pg_trim_join(pg_ctx *ctx, const char *a_host, int64_t a_len, const char *b_host, int64_t b_len, int paired,
+                 const pg_trim_opts *opts, char *out_host, int64_t out_cap, int64_t *out_len, pg_reads **reads_out);
+
 #ifdef __cplusplus
 }
 #endif

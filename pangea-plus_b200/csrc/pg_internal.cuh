@@ -89,6 +89,9 @@ __host__ __device__ static inline int64_t pg_chunk_start(int64_t off_i, int64_t 
 int  pg_fail(const pg_ctx *ctx, int code, const char *fmt, ...);
 int  pg_scratch(pg_ctx *ctx, pg_ctx::Scratch *s, size_t bytes);
 int  pg_pinned(pg_ctx *ctx, size_t bytes);
+// d_out[0..n) = exclusive scan of d_in, d_out[n] = total; synchronises the stream
+int  pg_device_scan(pg_ctx *ctx, const int64_t *d_in, int64_t n, int64_t *d_out);
+int  pg_pack_launch(pg_ctx *ctx, const char *d_bytes, const int64_t *d_off, int64_t count, uint32_t *d_planes);
 
 #define PG_CUDA(ctx, call)                                                              \
     do {                                                                                \

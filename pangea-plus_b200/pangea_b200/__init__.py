@@ -54,6 +54,10 @@ class _Opts(C.Structure):
     _fields_ = [("min_boot_words", C.c_int32), ("mode", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
+class _TrimOpts(C.Structure):
+    _fields_ = [("gap", C.c_int32), ("truncate", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
 class _ConsensusIn(C.Structure):
     _fields_ = [
         ("nreads", C.c_int64),
@@ -145,6 +149,7 @@ def load_library() -> C.CDLL:
     lib.pg_tax_leaf.argtypes = [vp, vp, vp, i64, vp]
     lib.pg_tax_lineage.argtypes = [vp, vp, vp, i64, vp, i64, vp]
     lib.pg_consensus.argtypes = [vp, C.POINTER(_ConsensusIn), vp, vp]
+    lib.pg_trim_join.argtypes = [vp, C.c_char_p, i64, C.c_char_p, i64, C.c_int, C.POINTER(_TrimOpts), vp, i64, C.POINTER(i64), C.POINTER(vp)]
     lib.pg_tax_chain.argtypes = [vp, vp, vp, i64, i32, vp, vp]
     lib.pg_tax_node_record.argtypes = [vp, i32, vp]
     lib.pg_tax_name_records.argtypes = [vp, i32, vp, i32]
@@ -360,6 +365,25 @@ class Context:
         self._chk(self.lib.pg_boot_indices(self.h, n, min_boot_words, out.ctypes.data))
         return out
 
+
+    # ---- Trim join
+    def trim_join(self, a: bytes, b: bytes | None = None, paired: bool = False, gap: int = 189, truncate: int = 11,
+                  want_reads: bool = False):
+        opts = _TrimOpts(gap, truncate)
+        n = C.c_int64()
+        rh = C.c_void_p()
+        cap = 2 * (len(a) + (len(b) if b else 0)) + 4096
+        while True:
+            buf = C.create_string_buffer(cap)
+            rc = self.lib.pg_trim_join(self.h, a, len(a), b, len(b) if b else 0, 1 if paired else 0, C.byref(opts), buf, cap,
+                                       C.byref(n), C.byref(rh) if want_reads else None)
+            if rc == -6 and n.value > cap:
+                cap = n.value + 64
+                continue
+            self._chk(rc)
+            break
+        text = buf.raw[: n.value]
+        return (text, Reads(self, rh.value)) if want_reads else text
 
     # ---- Stage B
     def tax_load(self, directory) -> "Tax":

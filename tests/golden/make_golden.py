@@ -148,6 +148,22 @@ def main():
     (d / "blast_class.txt").write_text("\n".join(A3_BLAST) + "\n")
     (d / "rdp.txt").write_text("\n".join(A3_RDP) + "\n")
     run_reference_consensus(d / "blast_class.txt", d / "rdp.txt", d / "consensus.expected.txt")
+    # ---- Trim join: the real Trim/trim2.4.pl on seeded QSEQ pairs and FASTQ
+    sys.path.insert(0, str(REPO / "tests"))
+    import oracle_pipeline as op
+    from pangea_b200 import synth_trim as stt
+
+    d = HERE / "trim"
+    d.mkdir(exist_ok=True)
+    a, b = stt.make_qseq_pair(41, 40)
+    (d / "reads_A.qseq.txt").write_text(a)
+    (d / "reads_B.qseq.txt").write_text(b)
+    op.real_trim(d / "reads_A.qseq.txt", d / "reads_B.qseq.txt", 100, d / "qseq_g100.expected.fasta")
+    op.real_trim(d / "reads_A.qseq.txt", d / "reads_B.qseq.txt", None, d / "qseq_default.expected.fasta")
+    op.real_trim(d / "reads_A.qseq.txt", d / "reads_B.qseq.txt", 7, d / "qseq_g7_t5.expected.fasta", truncate=5)
+    (d / "reads.fastq").write_text(stt.make_fastq(42, 30))
+    op.real_trim(d / "reads.fastq", None, None, d / "fastq_single.expected.fasta")
+    op.real_trim(d / "reads.fastq", d / "reads.fastq", 25, d / "fastq_paired_g25.expected.fasta")
     print("golden fixtures regenerated under", HERE)
 
 

@@ -18,12 +18,13 @@ def lib():
     global _lib
     if _lib is None:
         so = ORACLE_DIR / "libpipeline_ref.so"
-        srcs = [ORACLE_DIR / "taxcollector_ref.c", ORACLE_DIR / "consensus_ref.c"]
+        srcs = [ORACLE_DIR / "taxcollector_ref.c", ORACLE_DIR / "consensus_ref.c", ORACLE_DIR / "trim_ref.c"]
         if not so.exists() or any(so.stat().st_mtime < s.stat().st_mtime for s in srcs):
             subprocess.run(["make", "-C", str(ORACLE_DIR), str(so)], check=True, capture_output=True)
         L = C.CDLL(str(so))
         L.txc_file.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
         L.cns_run.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64]
+        L.trim_run.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p]
         _lib = L
     return _lib
 
@@ -80,3 +81,27 @@ def group_lineages(class_file):
             by.append([])
         by[-1].append(f[1] if len(f) > 1 else "")
     return ids, by
+
+
+def oracle_trim(a, b, gap, truncate, out) -> int:
+    return lib().trim_run(str(a).encode(), str(b).encode() if b else None, gap, truncate, str(out).encode())
+
+
+def real_trim(a, b, gap, out, truncate=None):
+    """runs the reference's Trim/trim2.4.pl in a scratch cwd and copies its _runblast.fasta to `out`"""
+    a, out = Path(a).resolve(), Path(out).resolve()
+    with tempfile.TemporaryDirectory() as wd:
+        cmd = ["perl", str(REF / "Trim" / "trim2.4.pl"), "-a", str(a)]
+        if b:
+            cmd += ["-b", str(Path(b).resolve())]
+        if gap is not None:
+            cmd += ["-g", str(gap)]
+        if truncate is not None:
+            cmd += ["-t", str(truncate)]
+        r = subprocess.run(cmd, cwd=wd, capture_output=True, text=True, timeout=300)
+        shutil.copy(Path(wd) / "output_files" / "trim2" / (a.name + "_runblast.fasta"), out)
+        # the script also litters <dir of a>/singletons/
+        sd = a.parent / "singletons"
+        if sd.exists():
+            shutil.rmtree(sd, ignore_errors=True)
+        return r.stdout

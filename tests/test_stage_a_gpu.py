@@ -421,3 +421,25 @@ def test_config2_illumina_reads_full_size(ctx, baseline_model):
     # idempotence: classifying the same batch again gives the same records
     c = ctx.classify(gm, data, off, mode=1)
     assert c.tobytes() == b.tobytes()
+
+
+def test_config3_rdp_scale_genera(ctx):
+    """configs[3] in its genus dimension: a 10 000-genus model (157 genus blocks of 64, 313 table tiles).
+    Oracle parity on a sample in both modes; strict == certified on a larger batch."""
+    tr = synth.synth16s(0x3000000, 30000, 10000, length=600)
+    om = ora.Model(tr["data"], tr["off"], tr["genus"], tr["G"])
+    gm = ctx.train(tr["data"], tr["off"], tr["genus"], tr["G"])
+    gm.set_lineage(tr["anc"])
+    assert gm.certifiable
+    m, nw, M, N = gm.counts(dense=False)
+    rm, rnw, rM, rN = om.counts()
+    assert np.array_equal(nw, rnw) and np.array_equal(M, rM) and N == rN
+    data, off, src = synth.synth_reads(0x3000001, tr, 4096, paired=False)
+    reads = [data[off[i]:off[i + 1]].tobytes() for i in range(0, 4096, 32)]
+    check_against_oracle(ctx, gm, om, tr["anc"], reads, mode=1)
+    check_against_oracle(ctx, gm, om, tr["anc"], reads[:32], mode=0)
+    a, ba = ctx.classify(gm, data, off, mode=0, want_boot=True)
+    b, bb = ctx.classify(gm, data, off, mode=1, want_boot=True)
+    assert a.tobytes() == b.tobytes() and np.array_equal(ba, bb)
+    om.free()
+    gm.free()
