@@ -153,7 +153,12 @@ typedef struct {
     int32_t min_boot_words;   /* 0 = RDP 2.5 (k = n/8); later releases use 5            */
     int32_t mode;             /* 0 = strict (reference order);
                                  1 = certified (quantised pre-filter, strict re-check)  */
-    int32_t reserved[6];
+    int32_t cert_plan;        /* certified mode only, results never depend on it:
+                                 0 = default (best block + block lower bounds + items),
+                                 1 = every genus block with partial-sum pruning          */
+    int32_t light_max;        /* cert_plan 0: open (task, block) pairs per read above which the
+                                 read is redone under cert_plan 1; 0 = default, -1 = none */
+    int32_t reserved[4];
 } pg_classify_opts;
 
 /* 1 if the model's quantised table certifies every deficit (mode 1 is then the
@@ -162,6 +167,10 @@ int pg_model_certifiable(const pg_model *m);
 /* How the reads of the last pg_classify*() call were routed: through the certified
  * kernels, through the strict kernels, and handed back from certified to strict. */
 int pg_classify_stats(const pg_ctx *ctx, int64_t *certified_reads, int64_t *strict_reads, int64_t *handed_back);
+/* Certified-path detail of the last call: reads redone by the all-block kernel because the block
+ * lower bounds left too many (task, block) pairs open, and the number of such pairs ("items")
+ * evaluated exactly for the other reads. */
+int pg_classify_stats2(const pg_ctx *ctx, int64_t *heavy_reads, int64_t *items);
 
 /* K3-K5: word extraction + orientation, gather-sum + 100 bootstraps, argmax,
  * vote.  results: nreads records (host for pg_classify, device for *_dev).

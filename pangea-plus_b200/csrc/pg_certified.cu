@@ -58,17 +58,18 @@ __global__ void k_rowmax(const float *__restrict__ table, int G, int ntile, floa
     }
 }
 
-// one thread per (tile64, word, genus-in-tile): exact in double (difference of two
-// fp32 values, power-of-two scale), rounded DOWN.
-__global__ void k_quantise(const float *__restrict__ table, const float *__restrict__ rowmax, int G,
-                           size_t total, uint16_t *__restrict__ q, unsigned int *__restrict__ qmax)
+// one thread per (tile64, word, position-in-tile): exact in double (difference of two
+// fp32 values, power-of-two scale), rounded DOWN.  perm[] maps the table position to the genus.
+__global__ void k_quantise(const float *__restrict__ table, const float *__restrict__ rowmax,
+                           const int32_t *__restrict__ perm, int G, size_t total, uint16_t *__restrict__ q,
+                           unsigned int *__restrict__ qmax)
 {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int l = (int)(idx & 63);
     const int w = (int)((idx >> 6) & (PG_NWORDS - 1));
     const int t64 = (int)(idx >> 22);
-    const int g = t64 * 64 + l;
+    const int g = perm[t64 * 64 + l];
     unsigned int v = PG_Q_MAX;
     if (g < G) {
         const float x = table[((size_t)(g >> 5) * PG_NWORDS + w) * PG_GENUS_TILE + (g & 31)];
@@ -81,16 +82,54 @@ __global__ void k_quantise(const float *__restrict__ table, const float *__restr
     q[idx] = (uint16_t)v;
 }
 
+// one thread per (block, word): minimum deficit over the block's 64 positions (padding holds
+// PG_Q_MAX and never wins).  bm[(blk/32)][w][blk%32]: the 32 blocks of a group are one 64-byte row.
+__global__ void k_blockmin(const uint16_t *__restrict__ q, int ntile64, uint16_t *__restrict__ bm)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = (int)(idx & (PG_NWORDS - 1));
+    const int blk = (int)(idx >> 16);
+    const int ngroup = (ntile64 + 31) / 32;
+    if (blk >= ngroup * 32) return;
+    uint32_t m = 0xFFFFu;
+    if (blk < ntile64) {
+        const uint4 *row = reinterpret_cast<const uint4 *>(q + ((size_t)blk * PG_NWORDS + w) * 64);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint4 v = row[i];
+            const uint32_t a = __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w));
+            m = min(m, min(a & 0xFFFFu, a >> 16));
+        }
+    }
+    bm[((size_t)(blk >> 5) * PG_NWORDS + w) * 32 + (blk & 31)] = (uint16_t)m;
+}
+
+// table layout of certified mode: perm_host[p] = genus stored at position p (a permutation of 0..G-1)
+int pg_model_set_layout(pg_model *md, const int32_t *perm_host)
+{
+    pg_ctx *ctx = md->ctx;
+    const int ntile64 = (md->G + 63) / 64;
+    std::vector<int32_t> full((size_t)ntile64 * 64);
+    for (size_t p = 0; p < full.size(); p++) full[p] = p < (size_t)md->G ? (perm_host ? perm_host[p] : (int32_t)p) : 0x7FFFFFFF;
+    if (!md->d_perm) PG_CUDA(ctx, cudaMalloc(&md->d_perm, full.size() * 4));
+    PG_CUDA(ctx, cudaMemcpy(md->d_perm, full.data(), full.size() * 4, cudaMemcpyHostToDevice));
+    return PG_OK;
+}
+
 int pg_model_derive_quantised(pg_model *md)
 {
     pg_ctx *ctx = md->ctx;
     md->ntile64 = (md->G + 63) / 64;
+    md->ngroup = (md->ntile64 + 31) / 32;
     md->q_ok = false;
     const size_t cells = (size_t)md->ntile64 * PG_NWORDS * 64;
+    const size_t bmcells = (size_t)md->ngroup * PG_NWORDS * 32;
+    if (!md->d_perm) PG_TRY(pg_model_set_layout(md, NULL));
     if (!md->d_qtable) {
         cudaError_t e;
         if ((e = cudaMalloc(&md->d_qtable, cells * 2)) != cudaSuccess ||
-            (e = cudaMalloc(&md->d_rowmax, PG_NWORDS * 4)) != cudaSuccess) {
+            (e = cudaMalloc(&md->d_rowmax, PG_NWORDS * 4)) != cudaSuccess ||
+            (e = cudaMalloc(&md->d_bmtable, bmcells * 2)) != cudaSuccess) {
             (void)cudaGetLastError();
             return pg_fail(ctx, PG_ENOMEM, "quantised table allocation failed: %s", cudaGetErrorString(e));
         }
@@ -100,8 +139,10 @@ int pg_model_derive_quantised(pg_model *md)
     PG_CUDA(ctx, cudaMemsetAsync(d_stat, 0, 8, ctx->stream));
     k_rowmax<<<PG_NWORDS / 8, 256, 0, ctx->stream>>>(md->d_table, md->G, md->ntile, md->d_rowmax, d_stat);
     PG_LAUNCHED(ctx);
-    k_quantise<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(md->d_table, md->d_rowmax, md->G, cells,
-                                                                         md->d_qtable, d_stat + 1);
+    k_quantise<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(md->d_table, md->d_rowmax, md->d_perm, md->G,
+                                                                         cells, md->d_qtable, d_stat + 1);
+    PG_LAUNCHED(ctx);
+    k_blockmin<<<(unsigned)((bmcells + 255) / 256), 256, 0, ctx->stream>>>(md->d_qtable, md->ntile64, md->d_bmtable);
     PG_LAUNCHED(ctx);
     unsigned int stat[2];
     PG_CUDA(ctx, cudaMemcpyAsync(stat, d_stat, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -416,7 +457,276 @@ k_guess_block(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ 
     if (lane == 0) guess[read - read0] = best;
 }
 
+// ------------------------------------------------------------------ certified v2: block lower bounds
+//
+// The all-block kernel above spends most of its time proving, draw by draw, that a genus block
+// does NOT hold a replicate's winner.  v2 proves it from a 64-times smaller table instead:
+//   bm[w][blk] = min over the 64 genera of block blk of q[w][g]      (k_blockmin)
+//   LB(task, blk) = sum over the task's draws of bm[w_draw][blk]  <=  Sq(g)  for every g in blk.
+// If LB > champion + margin no genus of the block is the winner or a near-tie (same argument as
+// the partial-sum prune).  With the genera laid out in lineage order (pg_model_set_lineage) the
+// relatives of the read's genus share its block, and on the bench workload 98 % of the
+// (replicate, block) pairs are dismissed by the bound; the survivors ("items") are evaluated
+// exactly by k_light straight from L2.  Order of one bucket:
+//   k_guess_bm   warp per read: 32 sampled words x bm -> the block to run in full
+//   k_classify_q grid (reads, 1): that block in full; seeds the champion slots
+//   k_bound      CTA per (read, group of 32 blocks): LB of the 101 tasks -> items / heavy flag
+//   k_light      group of 8 lanes per item: exact sums of the item's block, champion update
+//   k_resolve    as before; reads flagged heavy (too many items) are redone by the all-block kernel.
+
+#define PG_LIGHT_MAX 768            // items per (read, group) above which the read is "heavy"
+#define PG_ITEM_NULL 0xFFFFu
+
+__global__ void __launch_bounds__(256)
+k_guess_bm(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
+           const int32_t *__restrict__ nwords, const int32_t *__restrict__ order, int nreads_b, int64_t read0,
+           int ntile64, int ngroup, int32_t *__restrict__ guess)
+{
+    const int lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (slot >= nreads_b) return;
+    const int64_t read = order[slot];
+    const int n = nwords[read];
+    uint32_t best = 0u;
+    if (n > 0) {
+        const uint16_t *w = words + off[read];
+        const int ns = n < 32 ? n : 32, stride = n / ns;
+        const uint32_t wv = lane < ns ? (uint32_t)__ldg(w + lane * stride) : 0u;
+        uint32_t bestkey = 0xFFFFFFFFu;
+        for (int grp = 0; grp < ngroup; grp++) {
+            uint32_t acc = 0u;
+            for (int j = 0; j < ns; j++) {
+                const uint32_t wj = __shfl_sync(0xffffffffu, wv, j);
+                acc += __ldg(bm + ((size_t)grp * PG_NWORDS + wj) * 32 + lane);
+            }
+            const uint32_t blk = (uint32_t)grp * 32u + lane;
+            const uint32_t key = (int)blk < ntile64 ? ((acc << 12) | blk) : 0xFFFFFFFFu;   // acc < 2^17, blk < 2^12
+            bestkey = min(bestkey, __reduce_min_sync(0xffffffffu, key));
+        }
+        best = bestkey & 0xFFFu;
+    }
+    if (lane == 0) guess[read - read0] = (int32_t)best;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
+        const int32_t *__restrict__ nwords, const uint8_t *__restrict__ flags, const int32_t *__restrict__ order,
+        int64_t read0, const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot,
+        int ntile64, double vmax, const unsigned long long *__restrict__ champ, const int32_t *__restrict__ guess,
+        unsigned long long *__restrict__ items, unsigned int *__restrict__ item_count, unsigned int item_cap,
+        uint8_t *__restrict__ heavy, unsigned int light_max)
+{
+    constexpr int NUNIT = BLOCK / 16;               // half-warps: one task each, lane = two blocks
+    extern __shared__ uint4 sB[];                   // (n+1) rows x 4 uint4 (32 blocks x 16 bit); row n is zero
+    __shared__ uint32_t s_list[PG_LIGHT_MAX];
+    __shared__ uint32_t s_full[32];
+    __shared__ unsigned int s_cnt, s_base;
+
+    const int tid = threadIdx.x;
+    const int64_t read = order[blockIdx.x];
+    if (flags[2 * read + 1]) return;
+    const int n = nwords[read];
+    if (n == 0) return;
+    const size_t rc = (size_t)(read - read0);
+    const int grp = blockIdx.y;
+    const uint16_t *w = words + off[read];
+    const uint16_t *tb = bm + (size_t)grp * PG_NWORDS * 32;
+    for (int c = tid; c < n * 4; c += BLOCK) pg_cp_async16(&sB[c], tb + (size_t)w[c >> 2] * 32 + (c & 3) * 8);
+    if (tid < 4) sB[n * 4 + tid] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 32) s_full[tid] = 0u;
+    if (tid == 0) s_cnt = 0u;
+    pg_cp_async_wait_all();
+    __syncthreads();
+
+    const int unit = tid >> 4, hl = tid & 15;
+    const int b0 = grp * 32 + 2 * hl;
+    const int best = guess[rc];
+    const bool ok0 = b0 < ntile64 && b0 != best, ok1 = b0 + 1 < ntile64 && b0 + 1 != best;
+    const char *base = reinterpret_cast<const char *>(sB) + hl * 4;
+    const unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
+#define PG_BROW(o) (*reinterpret_cast<const uint32_t *>(base + (o)))
+#define PG_SURVIVE(task, blk)                                                  \
+    {                                                                          \
+        const unsigned int pos = atomicAdd(&s_cnt, 1u);                        \
+        if (pos < PG_LIGHT_MAX) s_list[pos] = ((uint32_t)(task) << 16) | (uint32_t)(blk); \
+    }
+
+    // ---- task 0 (full sum): the units split the rows, shared-memory atomics combine them
+    {
+        uint32_t lo = 0u, hi = 0u, c = 0u;
+        int cnt = 0;
+        for (int j = unit; j < n; j += NUNIT) {
+            c += PG_BROW(j * 64);
+            if (++cnt == 16) { lo += c & 0xFFFFu; hi += c >> 16; c = 0u; cnt = 0; }
+        }
+        lo += c & 0xFFFFu;
+        hi += c >> 16;
+        atomicAdd(&s_full[2 * hl], lo);
+        atomicAdd(&s_full[2 * hl + 1], hi);
+    }
+
+    // ---- tasks 1..100: one replicate per half-warp
+    int k = n >> 3;
+    if (k < min_boot) k = min_boot;
+    const int nb = (k + 3) >> 2;
+    if (nb > 0) {
+        const uint4 *lists = reinterpret_cast<const uint4 *>(boot_pool + boot_off[n]);
+        const uint32_t margin = pg_margin(k, vmax);
+        for (int t = unit; t < PG_NUM_BOOT; t += NUNIT) {
+            const unsigned long long cv = __ldg(mychamp + 1 + t);
+            const uint4 *lp = lists + (size_t)(t >> 2) * nb * 4 + (t & 3);
+            uint32_t lo = 0u, hi = 0u, c = 0u;
+            int b = 0;
+            for (; b + 4 <= nb; b += 4) {           // 16 rows x 4095 < 2^16: one spill per four batches
+                const uint4 q0 = __ldg(lp + (b + 0) * 4), q1 = __ldg(lp + (b + 1) * 4);
+                const uint4 q2 = __ldg(lp + (b + 2) * 4), q3 = __ldg(lp + (b + 3) * 4);
+                c += PG_BROW(q0.x >> 1) + PG_BROW(q0.y >> 1) + PG_BROW(q0.z >> 1) + PG_BROW(q0.w >> 1);
+                c += PG_BROW(q1.x >> 1) + PG_BROW(q1.y >> 1) + PG_BROW(q1.z >> 1) + PG_BROW(q1.w >> 1);
+                c += PG_BROW(q2.x >> 1) + PG_BROW(q2.y >> 1) + PG_BROW(q2.z >> 1) + PG_BROW(q2.w >> 1);
+                c += PG_BROW(q3.x >> 1) + PG_BROW(q3.y >> 1) + PG_BROW(q3.z >> 1) + PG_BROW(q3.w >> 1);
+                lo += c & 0xFFFFu;
+                hi += c >> 16;
+                c = 0u;
+            }
+            for (; b < nb; b++) {
+                const uint4 q0 = __ldg(lp + b * 4);
+                c += PG_BROW(q0.x >> 1) + PG_BROW(q0.y >> 1) + PG_BROW(q0.z >> 1) + PG_BROW(q0.w >> 1);
+            }
+            lo += c & 0xFFFFu;
+            hi += c >> 16;
+            const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + margin;
+            if (ok0 && (unsigned long long)lo <= thr) PG_SURVIVE(1 + t, b0)
+            if (ok1 && (unsigned long long)hi <= thr) PG_SURVIVE(1 + t, b0 + 1)
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const int blk = grp * 32 + tid;
+        const unsigned long long cv = __ldg(mychamp);
+        const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + pg_margin(n, vmax);
+        if (blk < ntile64 && blk != best && (unsigned long long)s_full[tid] <= thr) PG_SURVIVE(0, blk)
+    }
+    __syncthreads();
+    const unsigned int cnt = s_cnt;
+    if (cnt == 0u) return;
+    if (tid == 0) {
+        unsigned int b = 0xFFFFFFFFu;
+        if (cnt <= light_max) {
+            b = atomicAdd(item_count, cnt);
+            if (b > item_cap || cnt > item_cap - b) {          // buffer full: blank what fits, redo the read
+                for (unsigned int i = b; i < item_cap && i < b + cnt; i++) items[i] = (unsigned long long)PG_ITEM_NULL << 16;
+                b = 0xFFFFFFFFu;
+            }
+        }
+        if (b == 0xFFFFFFFFu) heavy[rc] = 1;
+        s_base = b;
+    }
+    __syncthreads();
+    const unsigned int gb = s_base;
+    if (gb == 0xFFFFFFFFu) return;
+    for (unsigned int i = tid; i < cnt; i += BLOCK)
+        items[gb + i] = ((unsigned long long)rc << 32) | s_list[i];      // rc << 32 | task << 16 | block
+#undef PG_BROW
+#undef PG_SURVIVE
+}
+
+// One group of 8 lanes per item (read, block, task): the block's 64 exact sums straight from the
+// L2-resident table (an item is 60 rows of 128 bytes; staging the read's 486 rows would cost more),
+// stopping as soon as every partial sum is above champion + margin.
+__global__ void __launch_bounds__(256)
+k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
+        const int32_t *__restrict__ nwords, int64_t read0, const uint32_t *__restrict__ boot_pool,
+        const int32_t *__restrict__ boot_off, int min_boot, int G, double vmax,
+        const unsigned long long *__restrict__ items, const unsigned int *__restrict__ item_count,
+        unsigned int item_cap, unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand,
+        unsigned long long *__restrict__ cand)
+{
+    const int lane = threadIdx.x & 31, l = lane & 7;
+    const int gshift = lane & ~7;
+    const unsigned gmask = 0xFFu << gshift;
+    const unsigned int ngroups = gridDim.x * (blockDim.x >> 3);
+    unsigned int cnt = *item_count;
+    if (cnt > item_cap) cnt = item_cap;
+    for (unsigned int it = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); it < cnt; it += ngroups) {
+        const unsigned long long e = items[it];
+        const int task = (int)((e >> 16) & 0xFFFFu);
+        if (task == (int)PG_ITEM_NULL) continue;
+        const int blk = (int)(e & 0xFFFFu);
+        const size_t rc = (size_t)(e >> 32);
+        const int64_t read = read0 + (int64_t)rc;
+        const int n = nwords[read];
+        const uint16_t *w = words + off[read];
+        int k = n >> 3;
+        if (k < min_boot) k = min_boot;
+        const int nb = (k + 3) >> 2;
+        const int terms = task == 0 ? n : k;
+        const uint32_t margin = pg_margin(terms, vmax);
+        unsigned long long *slot = champ + rc * (PG_NUM_BOOT + 1) + task;
+        const unsigned long long cv = *reinterpret_cast<volatile unsigned long long *>(slot);
+        const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + margin;
+        const uint4 *tb = reinterpret_cast<const uint4 *>(qtable + (size_t)blk * PG_NWORDS * 64) + l;
+        uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u, s4 = 0u, s5 = 0u, s6 = 0u, s7 = 0u;
+        bool pruned = false;
+        const uint4 *lp = reinterpret_cast<const uint4 *>(boot_pool + boot_off[n]) +
+                          (task > 0 ? (size_t)((task - 1) >> 2) * nb * 4 + ((task - 1) & 3) : 0);
+        const int nstep = task == 0 ? (n + 7) >> 3 : (nb + 1) >> 1;
+        for (int st = 0; st < nstep; st++) {
+            // row indices of this step's 8 draws (index n = padding = no row)
+            uint32_t r[8];
+            if (task == 0) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) r[u] = (uint32_t)min(st * 8 + u, n);
+            } else {
+                const uint4 qa = __ldg(lp + (size_t)(2 * st) * 4);
+                uint4 qb = make_uint4((uint32_t)n * PG_ROW_PITCH, (uint32_t)n * PG_ROW_PITCH, (uint32_t)n * PG_ROW_PITCH,
+                                      (uint32_t)n * PG_ROW_PITCH);
+                if (2 * st + 1 < nb) qb = __ldg(lp + (size_t)(2 * st + 1) * 4);
+                r[0] = qa.x / PG_ROW_PITCH; r[1] = qa.y / PG_ROW_PITCH; r[2] = qa.z / PG_ROW_PITCH; r[3] = qa.w / PG_ROW_PITCH;
+                r[4] = qb.x / PG_ROW_PITCH; r[5] = qb.y / PG_ROW_PITCH; r[6] = qb.z / PG_ROW_PITCH; r[7] = qb.w / PG_ROW_PITCH;
+            }
+            uint32_t wi[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) wi[u] = (int)r[u] < n ? (uint32_t)__ldg(w + r[u]) : 0xFFFFFFFFu;
+            uint4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                v[u] = wi[u] != 0xFFFFFFFFu ? __ldg(tb + (size_t)wi[u] * 8) : make_uint4(0u, 0u, 0u, 0u);
+            uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
+#pragma unroll
+            for (int u = 0; u < 8; u++) { PG_QADD4(v[u]) }
+            PG_QSPILL()
+            const uint32_t smin = min(min(min(s0, s1), min(s2, s3)), min(min(s4, s5), min(s6, s7)));
+            const unsigned over = __ballot_sync(gmask, (unsigned long long)smin > thr);
+            if (((over >> gshift) & 0xFFu) == 0xFFu) { pruned = true; break; }
+        }
+        if (pruned) continue;
+        const uint32_t sums[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
+        const uint32_t gbase = (uint32_t)blk * 64u;
+        PgPending pend;
+        pg_epilogue_begin<8>(gmask, l == 0, sums, gbase + (uint32_t)l * 8u, gbase, G, slot, pend);
+        pg_epilogue_finish<8>(gmask, l == 0, gshift, sums, gbase + (uint32_t)l * 8u, gbase, G, task, margin, pend,
+                              ncand + rc, cand + rc * PG_CANDCAP);
+    }
+}
+
+// heavy reads start over with the all-block kernel: clear their champion slots and lists
+__global__ void k_reset_reads(const int32_t *__restrict__ list, int cnt, int64_t read0,
+                              unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand)
+{
+    const int i = blockIdx.x;
+    if (i >= cnt) return;
+    const size_t rc = (size_t)(list[i] - read0);
+    for (int t = threadIdx.x; t <= PG_NUM_BOOT; t += blockDim.x) champ[rc * (PG_NUM_BOOT + 1) + t] = PG_CHAMP_INIT;
+    if (threadIdx.x == 0) ncand[rc] = 0u;
+}
+
 // ------------------------------------------------------------------ phase 2
+
+__device__ __forceinline__ int pg_pos2genus(const int32_t *__restrict__ perm, uint32_t pos, int G)
+{
+    return pos < (uint32_t)G ? perm[pos] : 0;       // real genera occupy positions 0..G-1
+}
 
 // strict fp32 sum of genus g over the task's rows, in the reference's order
 __device__ float pg_strict_sum(const float *__restrict__ table, const uint16_t *sw, int n, int k, int nb,
@@ -448,7 +758,8 @@ k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, c
           const unsigned long long *__restrict__ champ, const unsigned int *__restrict__ ncand,
           const unsigned long long *__restrict__ cand, const int32_t *__restrict__ anc, int depth,
           pg_result *__restrict__ results, int32_t *__restrict__ boot_winners, int *__restrict__ fb_count,
-          int32_t *__restrict__ fb_list)
+          int32_t *__restrict__ fb_list, const int32_t *__restrict__ perm, const uint8_t *__restrict__ heavy,
+          int *__restrict__ hv_count, int32_t *__restrict__ hv_list)
 {
     extern __shared__ unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -470,6 +781,10 @@ k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, c
         return;
     }
     const size_t rc = (size_t)(read - read0);
+    if (heavy && heavy[rc]) {                                   // too many items: the all-block kernel redoes it
+        if (lane == 0) hv_list[atomicAdd(hv_count, 1)] = (int32_t)read;
+        return;
+    }
     const unsigned int nc = ncand[rc];
     if (nc > PG_CANDCAP) {                                      // too many near-ties: strict kernels take it
         if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int32_t)read;
@@ -488,7 +803,7 @@ k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, c
     const bool trivial_rep = (nb == 0 || n == 0);               // k == 0: all sums 0 -> genus 0
 
     for (int t = lane; t <= PG_NUM_BOOT; t += 32)
-        winners[t] = (n == 0 || (t > 0 && trivial_rep)) ? 0 : (int)(uint32_t)mychamp[t];
+        winners[t] = (n == 0 || (t > 0 && trivial_rep)) ? 0 : pg_pos2genus(perm, (uint32_t)mychamp[t], G);   // table position -> genus
     if (lane < 4) need[lane] = 0u;
     __syncwarp();
     if (n > 0) {
@@ -525,6 +840,7 @@ k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, c
                     match = true;
                     g = (uint32_t)ch;
                 }
+                if (match) g = (uint32_t)pg_pos2genus(perm, g, G);    // ties resolve on the genus index, not the position
                 const unsigned int bal = __ballot_sync(0xffffffffu, match);
                 if (match) {
                     const float a = pg_strict_sum(table, sw, n, k, nb, list, t, g);
@@ -587,13 +903,13 @@ k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, c
 // ------------------------------------------------------------------ host
 
 template <int BLOCK, int MINB>
-static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, size_t smem, const uint16_t *d_words,
+static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, unsigned nblk_y, size_t smem, const uint16_t *d_words,
                     const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags, const int32_t *d_order,
                     int64_t read0, int min_boot, unsigned long long *d_champ, unsigned int *d_ncand,
                     unsigned long long *d_cand, const int32_t *d_guess)
 {
     PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(nreads_b, (unsigned)md->ntile64);
+    dim3 grid(nreads_b, nblk_y);
     k_classify_q<BLOCK, MINB><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
                                                           read0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->G,
                                                           md->vmax, d_champ, d_ncand, d_cand, d_guess);
@@ -601,35 +917,62 @@ static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, size_t s
     return PG_OK;
 }
 
-// phase 1 for one bucket (timed by the caller as the dominant kernel)
+// phase 1 for one bucket (timed by the caller).  version 2 = best block + lower bounds + items
+// (reads with too many items are flagged in cb.heavy); version 1 = every block, partial-sum pruning.
 int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsigned nreads_b, int nmax,
                         const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
                         const uint8_t *d_flags, const int32_t *d_order, int64_t read0, int min_boot,
-                        unsigned long long *d_champ, unsigned int *d_ncand, unsigned long long *d_cand,
-                        int32_t *d_guess)
+                        const PgCertBufs &cb, int version)
 {
     const size_t smem = (size_t)(nmax + 1) * 128;
     static int noprune = -1;                            // PG_NO_PRUNE=1: every block in full (A/B switch for profiling)
     if (noprune < 0) { const char *e = getenv("PG_NO_PRUNE"); noprune = (e && atoi(e)) ? 1 : 0; }
-    if (noprune || md->ntile64 < 2) d_guess = NULL;
-    if (d_guess) {
+    int32_t *d_guess = cb.guess;
+    if (noprune || md->ntile64 < 2) { d_guess = NULL; version = 1; }
+    unsigned nblk_y = (unsigned)md->ntile64;
+    if (d_guess && version == 2) {
+        k_guess_bm<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_bmtable, d_words, d_off, d_nwords, d_order,
+                                                               (int)nreads_b, read0, md->ntile64, md->ngroup, d_guess);
+        PG_LAUNCHED(ctx);
+        nblk_y = 1;                                     // grid row 0 = the guessed block, in full
+    } else if (d_guess) {
         k_guess_block<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_order,
                                                                   (int)nreads_b, read0, md->ntile64, d_guess);
         PG_LAUNCHED(ctx);
     }
+    int rc;
     if (bk.block == 192)
-        return launch_q<192, 3>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
-    if (bk.block == 448)
-        return launch_q<448, 2>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
-    return launch_q<832, 1>(ctx, md, nreads_b, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, d_champ, d_ncand, d_cand, d_guess);
+        rc = launch_q<192, 3>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
+    else if (bk.block == 448)
+        rc = launch_q<448, 2>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
+    else
+        rc = launch_q<832, 1>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
+    PG_TRY(rc);
+    if (!(d_guess && version == 2)) return PG_OK;
+
+    int light_max = cb.light_max == 0 ? PG_LIGHT_MAX : (cb.light_max < 0 ? 0 : cb.light_max);
+    if (light_max > PG_LIGHT_MAX) light_max = PG_LIGHT_MAX;
+    PG_CUDA(ctx, cudaMemsetAsync(cb.counters + 2, 0, 4, ctx->stream));
+    const size_t bsmem = (size_t)(nmax + 1) * 64;
+    PG_CUDA(ctx, cudaFuncSetAttribute(k_bound<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    k_bound<128><<<dim3(nreads_b, (unsigned)md->ngroup), 128, bsmem, ctx->stream>>>(
+        md->d_bmtable, d_words, d_off, d_nwords, d_flags, d_order, read0, ctx->d_boot_pool, ctx->d_boot_off, min_boot,
+        md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.counters + 2, cb.item_cap, cb.heavy,
+        (unsigned int)light_max);
+    PG_LAUNCHED(ctx);
+    k_light<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, read0, ctx->d_boot_pool,
+                                                        ctx->d_boot_off, min_boot, md->G, md->vmax, cb.items,
+                                                        cb.counters + 2, cb.item_cap, cb.champ, cb.ncand, cb.cand);
+    PG_LAUNCHED(ctx);
+    return PG_OK;
 }
 
-// phase 2 for one bucket: strict re-check of survivors + vote; overflowing reads go to fb_list
+// phase 2 for one bucket: strict re-check of survivors + vote; overflowing reads go to cb.fb_list,
+// heavy reads (use_heavy) to cb.hv_list
 int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, const uint16_t *d_words,
                         const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags,
-                        const int32_t *d_order, int64_t read0, int min_boot, const unsigned long long *d_champ,
-                        const unsigned int *d_ncand, const unsigned long long *d_cand, pg_result *d_results,
-                        int32_t *d_boot_winners, int *d_fb_count, int32_t *d_fb_list)
+                        const int32_t *d_order, int64_t read0, int min_boot, const PgCertBufs &cb, bool use_heavy,
+                        pg_result *d_results, int32_t *d_boot_winners)
 {
     constexpr int WARPS = 4;
     const size_t per_warp = (((size_t)nmax * 2 + 15) & ~(size_t)15) + (PG_NUM_BOOT + 1) * 4 + 16;
@@ -637,8 +980,17 @@ int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int 
     PG_CUDA(ctx, cudaFuncSetAttribute(k_resolve<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_resolve<WARPS><<<(nreads_b + WARPS - 1) / WARPS, 32 * WARPS, smem, ctx->stream>>>(
         md->d_table, d_words, d_off, d_nwords, d_flags, d_order, (int)nreads_b, read0, nmax, ctx->d_boot_pool,
-        ctx->d_boot_off, min_boot, md->G, md->vmax, d_champ, d_ncand, d_cand, md->d_anc, md->depth, d_results,
-        d_boot_winners, d_fb_count, d_fb_list);
+        ctx->d_boot_off, min_boot, md->G, md->vmax, cb.champ, cb.ncand, cb.cand, md->d_anc, md->depth, d_results,
+        d_boot_winners, (int *)cb.counters, cb.fb_list, md->d_perm, use_heavy ? cb.heavy : NULL,
+        (int *)cb.counters + 1, cb.hv_list);
+    PG_LAUNCHED(ctx);
+    return PG_OK;
+}
+
+// heavy reads: back to square one for the all-block kernel
+int pg_certified_reset(pg_ctx *ctx, const int32_t *d_list, int cnt, int64_t read0, const PgCertBufs &cb)
+{
+    k_reset_reads<<<cnt, 128, 0, ctx->stream>>>(d_list, cnt, read0, cb.champ, cb.ncand);
     PG_LAUNCHED(ctx);
     return PG_OK;
 }

@@ -229,13 +229,12 @@ static int launch_strict(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, uns
 int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsigned nreads_b, int nmax,
                         const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
                         const uint8_t *d_flags, const int32_t *d_order, int64_t read0, int min_boot,
-                        unsigned long long *d_champ, unsigned int *d_ncand, unsigned long long *d_cand,
-                        int32_t *d_guess);
+                        const PgCertBufs &cb, int version);
 int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, const uint16_t *d_words,
                         const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags,
-                        const int32_t *d_order, int64_t read0, int min_boot, const unsigned long long *d_champ,
-                        const unsigned int *d_ncand, const unsigned long long *d_cand, pg_result *d_results,
-                        int32_t *d_boot_winners, int *d_fb_count, int32_t *d_fb_list);   // pg_certified.cu
+                        const int32_t *d_order, int64_t read0, int min_boot, const PgCertBufs &cb, bool use_heavy,
+                        pg_result *d_results, int32_t *d_boot_winners);
+int pg_certified_reset(pg_ctx *ctx, const int32_t *d_list, int cnt, int64_t read0, const PgCertBufs &cb);   // pg_certified.cu
 #define PG_CANDCAP 128
 
 static int ensure_boot_lists(pg_ctx *ctx, const std::vector<int> &need_n, int min_boot)
@@ -333,6 +332,7 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
 
     const bool certified = (mode == 1) && md->q_ok;
     ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
+    ctx->st_heavy = ctx->st_items = 0;
     // certified mode walks the 20 genus blocks of a chunk one after the other (tile-major grid);
     // the chunk's word ids, champion slots and near-tie lists should stay in the 126 MB L2
     // across those passes, so the chunk is kept small (2^14 reads: 16 MB + 13 MB + 17 MB worst case; measured best)
@@ -345,21 +345,31 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
     PG_TRY(pg_scratch(ctx, &ctx->s_order, (size_t)cmax * 4));
     unsigned long long *d_best = (unsigned long long *)ctx->s_best.p;
     int32_t *d_order = (int32_t *)ctx->s_order.p;
-    unsigned long long *d_champ = NULL, *d_cand = NULL;
-    unsigned int *d_ncand = NULL;
-    int *d_fbc = NULL;
-    int32_t *d_fbl = NULL;
+    PgCertBufs cb;
+    memset(&cb, 0, sizeof cb);
+    static int env_v1 = -1;                             // PG_CERT_V1=1: the all-block kernel for every read (A/B switch)
+    if (env_v1 < 0) { const char *e = getenv("PG_CERT_V1"); env_v1 = (e && atoi(e)) ? 1 : 0; }
+    const int cert_version = (env_v1 || (opts && opts->cert_plan == 1)) ? 1 : 2;
+    if (opts && (opts->cert_plan < 0 || opts->cert_plan > 1)) return pg_fail(ctx, PG_EINVAL, "unknown cert_plan %d", opts->cert_plan);
+    cb.light_max = opts ? opts->light_max : 0;
     if (certified) {
         PG_TRY(pg_scratch(ctx, &ctx->s_champ, (size_t)cmax * nkeys * 8));
         PG_TRY(pg_scratch(ctx, &ctx->s_ncand, (size_t)cmax * 4));
         PG_TRY(pg_scratch(ctx, &ctx->s_candl, (size_t)cmax * PG_CANDCAP * 8));
         PG_TRY(pg_scratch(ctx, &ctx->s_fb, (size_t)cmax * 4 + 16));
-        d_champ = (unsigned long long *)ctx->s_champ.p;
-        d_ncand = (unsigned int *)ctx->s_ncand.p;
-        d_cand = (unsigned long long *)ctx->s_candl.p;
-        d_fbc = (int *)ctx->s_fb.p;
-        d_fbl = (int32_t *)ctx->s_fb.p + 4;
         PG_TRY(pg_scratch(ctx, &ctx->s_guess, (size_t)cmax * 4));
+        cb.item_cap = (unsigned int)(cmax * 64 < 4096 ? 4096 : cmax * 64);
+        PG_TRY(pg_scratch(ctx, &ctx->s_items, (size_t)cb.item_cap * 8));
+        PG_TRY(pg_scratch(ctx, &ctx->s_heavy, (size_t)cmax * 5 + 64));
+        cb.champ = (unsigned long long *)ctx->s_champ.p;
+        cb.ncand = (unsigned int *)ctx->s_ncand.p;
+        cb.cand = (unsigned long long *)ctx->s_candl.p;
+        cb.counters = (unsigned int *)ctx->s_fb.p;
+        cb.fb_list = (int32_t *)ctx->s_fb.p + 4;
+        cb.guess = (int32_t *)ctx->s_guess.p;
+        cb.items = (unsigned long long *)ctx->s_items.p;
+        cb.hv_list = (int32_t *)ctx->s_heavy.p;
+        cb.heavy = (uint8_t *)((int32_t *)ctx->s_heavy.p + cmax);
     }
     const int wpb = 8;
 
@@ -387,9 +397,10 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
         PG_CUDA(ctx, cudaMemcpyAsync(d_order, h_order + c0, (size_t)cn * 4, cudaMemcpyHostToDevice, ctx->stream));
         PG_CUDA(ctx, cudaMemsetAsync(d_best, 0, (size_t)cn * nkeys * 8, ctx->stream));
         if (certified) {
-            PG_CUDA(ctx, cudaMemsetAsync(d_champ, 0xFF, (size_t)cn * nkeys * 8, ctx->stream));
-            PG_CUDA(ctx, cudaMemsetAsync(d_ncand, 0, (size_t)cn * 4, ctx->stream));
-            PG_CUDA(ctx, cudaMemsetAsync(d_fbc, 0, 16, ctx->stream));
+            PG_CUDA(ctx, cudaMemsetAsync(cb.champ, 0xFF, (size_t)cn * nkeys * 8, ctx->stream));
+            PG_CUDA(ctx, cudaMemsetAsync(cb.ncand, 0, (size_t)cn * 4, ctx->stream));
+            PG_CUDA(ctx, cudaMemsetAsync(cb.counters, 0, 16, ctx->stream));
+            PG_CUDA(ctx, cudaMemsetAsync(cb.heavy, 0, (size_t)cn, ctx->stream));
         }
 
         // one bucket of reads through the strict kernels (also the certified path's fallback)
@@ -434,11 +445,11 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
                 cudaEvent_t e0 = take_event(ctx), e1 = take_event(ctx);
                 PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
                 PG_TRY(pg_certified_phase1(ctx, md, bk, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords, d_flags, ord,
-                                           c0, min_boot, d_champ, d_ncand, d_cand, (int32_t *)ctx->s_guess.p));
+                                           c0, min_boot, cb, cert_version));
                 PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
                 ctx->ev_pending.push_back(std::make_pair(e0, e1));
                 PG_TRY(pg_certified_phase2(ctx, md, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords, d_flags, ord, c0,
-                                           min_boot, d_champ, d_ncand, d_cand, d_results, d_boot_winners, d_fbc, d_fbl));
+                                           min_boot, cb, cert_version == 2, d_results, d_boot_winners));
             } else {
                 ctx->st_strict += bcount[b];
                 PG_TRY(run_strict(bk, ord, (unsigned)bcount[b], nmax, true));
@@ -446,17 +457,12 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
         }
 
         if (certified) {
-            // reads whose near-tie list overflowed are redone by the strict kernels
-            int nfb = 0;
-            PG_CUDA(ctx, cudaMemcpyAsync(&nfb, d_fbc, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            if (nfb > 0) {
-                ctx->st_handed_back += nfb;
-                std::vector<int32_t> fb((size_t)nfb), sorted((size_t)nfb);
-                PG_CUDA(ctx, cudaMemcpyAsync(fb.data(), d_fbl, (size_t)nfb * 4, cudaMemcpyDeviceToHost, ctx->stream));
-                PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                int64_t fcount[16] = {0}, fstart[16], fmaxn[16] = {0}, ffill[16];
-                for (int32_t r : fb) {
+            // sort a list of reads (host copy) by bucket and upload it to d_order
+            int64_t fcount[16], fstart[16], fmaxn[16];
+            auto bucket_list = [&](const std::vector<int32_t> &lst, std::vector<int32_t> &sorted) -> int {
+                int64_t ffill[16];
+                for (int b = 0; b < 16; b++) fcount[b] = fmaxn[b] = 0;
+                for (int32_t r : lst) {
                     int n = h_n[r], b = 0;
                     while (kBuckets[b].nmax < n) b++;
                     fcount[b]++;
@@ -464,12 +470,55 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
                 }
                 int64_t a2 = 0;
                 for (int b = 0; b < kNumBuckets; b++) { fstart[b] = ffill[b] = a2; a2 += fcount[b]; }
-                for (int32_t r : fb) {
+                sorted.resize(lst.size());
+                for (int32_t r : lst) {
                     int n = h_n[r], b = 0;
                     while (kBuckets[b].nmax < n) b++;
                     sorted[(size_t)ffill[b]++] = r;
                 }
-                PG_CUDA(ctx, cudaMemcpyAsync(d_order, sorted.data(), (size_t)nfb * 4, cudaMemcpyHostToDevice, ctx->stream));
+                PG_CUDA(ctx, cudaMemcpyAsync(d_order, sorted.data(), sorted.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                return PG_OK;
+            };
+            unsigned int cnts[4] = {0, 0, 0, 0};
+            PG_CUDA(ctx, cudaMemcpyAsync(cnts, cb.counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+            PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->st_items += cnts[2];
+            std::vector<int32_t> lst, sorted, fb;
+            if (cnts[0] > 0) {                                  // near-tie list overflowed: strict kernels (below)
+                fb.resize((size_t)cnts[0]);
+                PG_CUDA(ctx, cudaMemcpyAsync(fb.data(), cb.fb_list, fb.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            if (cnts[1] > 0) {
+                // reads with too many surviving (task, block) items: the all-block kernel does them from scratch
+                const int nhv = (int)cnts[1];
+                ctx->st_heavy += nhv;
+                lst.resize((size_t)nhv);
+                PG_CUDA(ctx, cudaMemcpyAsync(lst.data(), cb.hv_list, (size_t)nhv * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                PG_TRY(bucket_list(lst, sorted));
+                PG_TRY(pg_certified_reset(ctx, d_order, nhv, c0, cb));
+                PG_CUDA(ctx, cudaMemsetAsync(cb.counters, 0, 4, ctx->stream));
+                for (int b = 0; b < kNumBuckets; b++) {
+                    if (!fcount[b]) continue;
+                    PG_TRY(pg_certified_phase1(ctx, md, kBuckets[b], (unsigned)fcount[b], (int)fmaxn[b], d_words, d_off, d_nwords,
+                                               d_flags, d_order + fstart[b], c0, min_boot, cb, 1));
+                    PG_TRY(pg_certified_phase2(ctx, md, (unsigned)fcount[b], (int)fmaxn[b], d_words, d_off, d_nwords, d_flags,
+                                               d_order + fstart[b], c0, min_boot, cb, false, d_results, d_boot_winners));
+                }
+                unsigned int more = 0;
+                PG_CUDA(ctx, cudaMemcpyAsync(&more, cb.counters, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // also: `sorted` is a stack vector
+                if (more > 0) {
+                    const size_t at = fb.size();
+                    fb.resize(at + more);
+                    PG_CUDA(ctx, cudaMemcpy(fb.data() + at, cb.fb_list, (size_t)more * 4, cudaMemcpyDeviceToHost));
+                }
+            }
+            if (!fb.empty()) {
+                const int nfb = (int)fb.size();
+                ctx->st_handed_back += nfb;
+                PG_TRY(bucket_list(fb, sorted));
                 for (int b = 0; b < kNumBuckets; b++)
                     if (fcount[b])
                         PG_TRY(run_strict(kBuckets[b], d_order + fstart[b], (unsigned)fcount[b], (int)fmaxn[b], false));

@@ -96,3 +96,17 @@ __device__ __forceinline__ void pg_cp_async_wait_all()
 // Reads are bucketed by word count so each launch sizes its shared memory (and so
 // its CTAs/SM) for the reads it actually carries.
 struct Bucket { int nmax; int lpr; int block; };
+
+// device buffers of certified mode (one chunk of reads)
+struct PgCertBufs {
+    unsigned long long *champ;       // [reads][101] champion slots: sum << 32 | table position
+    unsigned int       *ncand;       // [reads]
+    unsigned long long *cand;        // [reads][PG_CANDCAP] near-tie lists
+    int32_t            *guess;       // [reads] block run in full
+    unsigned long long *items;       // [item_cap] (read, block, task) still to evaluate exactly
+    unsigned int        item_cap;
+    int                 light_max;   // pg_classify_opts.light_max
+    unsigned int       *counters;    // [0] strict fallbacks, [1] heavy reads, [2] items
+    uint8_t            *heavy;       // [reads] flag
+    int32_t            *fb_list, *hv_list;
+};

@@ -43,6 +43,7 @@ extern "C" pg_ctx *pg_init(int device)
     }
     pg_ctx *ctx = new pg_ctx();
     ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
     ctx->err[0] = 0;
     ctx->launches = 0;
     ctx->d_boot_pool = NULL;
@@ -52,6 +53,7 @@ extern "C" pg_ctx *pg_init(int device)
     ctx->classify_ms = 0.0;
     ctx->classify_launches = 0;
     ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
+    ctx->st_heavy = ctx->st_items = 0;
     memset(&ctx->s_words, 0, sizeof(pg_ctx::Scratch) * pg_ctx::kNumScratch);
     ctx->h_pin = NULL;
     ctx->h_pin_cap = 0;
@@ -92,6 +94,14 @@ extern "C" int pg_sync(pg_ctx *ctx)
     if (!ctx) return PG_EINVAL;
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+
+extern "C" int pg_classify_stats2(const pg_ctx *ctx, int64_t *heavy_reads, int64_t *items)
+{
+    if (!ctx) return PG_EINVAL;
+    if (heavy_reads) *heavy_reads = ctx->st_heavy;
+    if (items) *items = ctx->st_items;
     return PG_OK;
 }
 

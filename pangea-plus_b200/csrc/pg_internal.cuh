@@ -15,6 +15,7 @@
 
 struct pg_ctx {
     int          device;
+    int          sm_count;
     cudaStream_t stream;
     cudaStream_t own_stream;
     mutable char err[512];
@@ -40,8 +41,9 @@ struct pg_ctx {
         void  *p;
         size_t cap;
     } s_words, s_nwords, s_flags, s_best, s_order, s_results, s_boot, s_bytes, s_off, s_cand,
-      s_champ, s_ncand, s_candl, s_fb, s_guess;
-    static const int kNumScratch = 15;
+      s_champ, s_ncand, s_candl, s_fb, s_guess, s_items, s_heavy;
+    static const int kNumScratch = 17;
+    int64_t st_heavy, st_items;                        // certified v2: reads redone by the all-block kernel, light items
     // pinned host staging
     void  *h_pin;
     size_t h_pin_cap;
@@ -65,6 +67,11 @@ struct pg_model {
     uint16_t *d_qtable;         // [ntile64][65536][64]
     float   *d_rowmax;          // [65536]
     int      ntile64;
+    // certified v2: genera are laid out in the quantised table in LINEAGE order (relatives share a
+    // 64-genus block), and every block has a per-word minimum used as a lower bound of all its genera
+    int32_t  *d_perm;           // [ntile64*64] table position -> genus index (>= G: padding)
+    uint16_t *d_bmtable;        // [ngroup][65536][32]   min over the 64 genera of block (group*32 + i)
+    int      ngroup;            // ceil(ntile64 / 32)
     double   vmax;              // max |table entry| over real genera (fp32 error bound)
     bool     q_ok;              // every deficit fits the 12-bit field: certificates are valid
     bool     committed;

@@ -51,7 +51,8 @@ class _SeqBatch(C.Structure):
 
 
 class _Opts(C.Structure):
-    _fields_ = [("min_boot_words", C.c_int32), ("mode", C.c_int32), ("reserved", C.c_int32 * 6)]
+    _fields_ = [("min_boot_words", C.c_int32), ("mode", C.c_int32), ("cert_plan", C.c_int32),
+                ("light_max", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class _TrimOpts(C.Structure):
@@ -119,6 +120,7 @@ def load_library() -> C.CDLL:
     lib.pg_model_genera.argtypes = [vp]
     lib.pg_model_certifiable.argtypes = [vp]
     lib.pg_classify_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    lib.pg_classify_stats2.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.pg_model_sequences.restype = i64
     lib.pg_model_sequences.argtypes = [vp]
     lib.pg_model_counts.argtypes = [vp, vp, vp, vp, C.POINTER(i64)]
@@ -298,7 +300,9 @@ class Context:
     def classify_stats(self):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
         self._chk(self.lib.pg_classify_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"certified": a.value, "strict": b.value, "handed_back": c.value}
+        d, e = C.c_int64(), C.c_int64()
+        self._chk(self.lib.pg_classify_stats2(self.h, C.byref(d), C.byref(e)))
+        return {"certified": a.value, "strict": b.value, "handed_back": c.value, "heavy": d.value, "items": e.value}
 
     def kernel_time_reset(self) -> None:
         self._chk(self.lib.pg_kernel_time_reset(self.h))
@@ -336,18 +340,18 @@ class Context:
         return Reads(self, h.value)
 
     def classify(self, model: Model, data: np.ndarray, off: np.ndarray, mode: int = 0, min_boot_words: int = 0,
-                 want_boot: bool = False, out: np.ndarray | None = None):
+                 want_boot: bool = False, out: np.ndarray | None = None, cert_plan: int = 0, light_max: int = 0):
         n = len(off) - 1
         sb = _SeqBatch(_ptr(data), _ptr(off), n)
-        opts = _Opts(min_boot_words, mode)
+        opts = _Opts(min_boot_words, mode, cert_plan, light_max)
         res = out if out is not None else np.zeros(n, RESULT_DTYPE)
         boot = np.zeros((n, PG_NUM_BOOT), np.int32) if want_boot else None
         self._chk(self.lib.pg_classify(self.h, model.h, C.byref(sb), C.byref(opts), _ptr(res), _ptr(boot)))
         return (res, boot) if want_boot else res
 
     def classify_packed(self, model: Model, reads: Reads, results_dev, boot_dev=None, mode: int = 0,
-                        min_boot_words: int = 0) -> None:
-        opts = _Opts(min_boot_words, mode)
+                        min_boot_words: int = 0, cert_plan: int = 0, light_max: int = 0) -> None:
+        opts = _Opts(min_boot_words, mode, cert_plan, light_max)
         self._chk(self.lib.pg_classify_packed(self.h, model.h, reads.h, C.byref(opts), _ptr(results_dev), _ptr(boot_dev)))
 
     def extract_words(self, model: Model, data: np.ndarray, off: np.ndarray):

@@ -443,3 +443,52 @@ def test_config3_rdp_scale_genera(ctx):
     assert a.tobytes() == b.tobytes() and np.array_equal(ba, bb)
     om.free()
     gm.free()
+
+
+# ------------------------------------------------------------------ certified plans (block lower bounds)
+
+def test_certified_plans_agree(ctx, baseline_model):
+    """The certified path's work plans differ only in how they prove genera irrelevant: the default plan
+    (best block + block lower bounds + items), the same with every read with an open item sent back to the
+    all-block kernel (light_max = -1), and the all-block kernel alone (cert_plan = 1) must return the strict
+    kernels' records byte for byte."""
+    tr, om, gm = baseline_model
+    data, off, src = synth.synth_reads(0x251, tr, 6000, paired=True)
+    want, wb = ctx.classify(gm, data, off, mode=0, want_boot=True)
+    got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True)
+    st = ctx.classify_stats()
+    assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb)
+    assert st["certified"] == 6000 and st["items"] > 0, st
+    assert st["heavy"] < 600, st                         # the bound dismisses nearly every block on this workload
+    got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True, light_max=-1)
+    st = ctx.classify_stats()
+    assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb)
+    assert st["heavy"] > 0 and st["items"] == 0, st
+    got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True, light_max=3)
+    st = ctx.classify_stats()
+    assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb)
+    assert st["heavy"] > 0 and st["items"] > 0, st
+    got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True, cert_plan=1)
+    st = ctx.classify_stats()
+    assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb)
+    assert st["heavy"] == 0 and st["items"] == 0, st
+
+
+def test_certified_without_lineage(ctx):
+    """no lineage -> the quantised table keeps the genus order of the training file (relatives scattered
+    over the blocks, weak bounds, many items); results are the same and match the oracle."""
+    tr = synth.synth16s(seed=31, seqs=900, genera=300, length=900)
+    om = ora.Model(tr["data"], tr["off"], tr["genus"], tr["G"])
+    gm = ctx.train(tr["data"], tr["off"], tr["genus"], tr["G"])
+    data, off, src = synth.synth_reads(5, tr, 1500, paired=True)
+    a, ba = ctx.classify(gm, data, off, mode=0, want_boot=True)
+    b, bb = ctx.classify(gm, data, off, mode=1, want_boot=True)
+    assert a.tobytes() == b.tobytes() and np.array_equal(ba, bb)
+    ref = om.classify(data[: off[200]], off[:201])
+    assert np.array_equal(b["genus"][:200], ref["genus"]) and np.array_equal(bb[:200], ref["boot"])
+    gm.set_lineage(tr["anc"])                            # re-lays the table out; results must not move
+    c, bc = ctx.classify(gm, data, off, mode=1, want_boot=True)
+    assert np.array_equal(c["genus"], b["genus"]) and np.array_equal(bc, bb)
+    assert np.array_equal(bits(c["score"]), bits(b["score"]))
+    om.free()
+    gm.free()
