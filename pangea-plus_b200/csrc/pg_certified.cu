@@ -244,7 +244,7 @@ template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
              const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
-             const uint8_t *__restrict__ flags, const int32_t *__restrict__ order, int64_t read0,
+             const uint8_t *__restrict__ flags, const int32_t *__restrict__ order, int64_t slot0,
              const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot, int G,
              double vmax, unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand,
              unsigned long long *__restrict__ cand, const int32_t *__restrict__ guess)
@@ -259,7 +259,7 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
     if (flags[2 * read + 1]) return;                // short read (A2)
     const int n = nwords[read];
     if (n == 0) return;                             // no word: phase 2 writes genus 0 directly
-    const size_t rc = (size_t)(read - read0);
+    const size_t rc = (size_t)slot0 + blockIdx.x;   // slot = position in the chunk's order array
     // Branch and bound over genus blocks: grid row 0 takes the read's most promising block
     // (k_guess_block) and runs it in full, which seeds the champion slots; every other block
     // then stops a replicate as soon as ALL its 64 partial sums exceed champion + margin --
@@ -429,7 +429,7 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
 __global__ void __launch_bounds__(256)
 k_guess_block(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
               const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
-              const int32_t *__restrict__ order, int nreads_b, int64_t read0, int ntile64, int32_t *__restrict__ guess)
+              const int32_t *__restrict__ order, int nreads_b, int64_t slot0, int ntile64, int32_t *__restrict__ guess)
 {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -454,7 +454,7 @@ k_guess_block(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ 
             if (v < bestv) { bestv = v; best = b; }
         }
     }
-    if (lane == 0) guess[read - read0] = best;
+    if (lane == 0) guess[slot0 + slot] = best;
 }
 
 // ------------------------------------------------------------------ certified v2: block lower bounds
@@ -479,7 +479,7 @@ k_guess_block(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ 
 
 __global__ void __launch_bounds__(256)
 k_guess_bm(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
-           const int32_t *__restrict__ nwords, const int32_t *__restrict__ order, int nreads_b, int64_t read0,
+           const int32_t *__restrict__ nwords, const int32_t *__restrict__ order, int nreads_b, int64_t slot0,
            int ntile64, int ngroup, int32_t *__restrict__ guess)
 {
     const int lane = threadIdx.x & 31;
@@ -505,19 +505,19 @@ k_guess_bm(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, 
         }
         best = bestkey & 0xFFFu;
     }
-    if (lane == 0) guess[read - read0] = (int32_t)best;
+    if (lane == 0) guess[slot0 + slot] = (int32_t)best;
 }
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
         const int32_t *__restrict__ nwords, const uint8_t *__restrict__ flags, const int32_t *__restrict__ order,
-        int64_t read0, const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot,
+        int64_t slot0, const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot,
         int ntile64, double vmax, const unsigned long long *__restrict__ champ, const int32_t *__restrict__ guess,
         unsigned long long *__restrict__ items, unsigned int *__restrict__ item_count, unsigned int item_cap,
         uint8_t *__restrict__ heavy, unsigned int light_max)
 {
-    constexpr int NUNIT = BLOCK / 16;               // half-warps: one task each, lane = two blocks
+    constexpr int NUNIT = BLOCK / 8;                // quarter-warps: one task each, lane = four blocks (one LDS.64 per draw)
     extern __shared__ uint4 sB[];                   // (n+1) rows x 4 uint4 (32 blocks x 16 bit); row n is zero
     __shared__ uint32_t s_list[PG_LIGHT_MAX];
     __shared__ uint32_t s_full[32];
@@ -528,7 +528,7 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     if (flags[2 * read + 1]) return;
     const int n = nwords[read];
     if (n == 0) return;
-    const size_t rc = (size_t)(read - read0);
+    const size_t rc = (size_t)slot0 + blockIdx.x;
     const int grp = blockIdx.y;
     const uint16_t *w = words + off[read];
     const uint16_t *tb = bm + (size_t)grp * PG_NWORDS * 32;
@@ -539,13 +539,17 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     pg_cp_async_wait_all();
     __syncthreads();
 
-    const int unit = tid >> 4, hl = tid & 15;
-    const int b0 = grp * 32 + 2 * hl;
+    const int unit = tid >> 3, hl = tid & 7;
+    const int b0 = grp * 32 + 4 * hl;
     const int best = guess[rc];
-    const bool ok0 = b0 < ntile64 && b0 != best, ok1 = b0 + 1 < ntile64 && b0 + 1 != best;
-    const char *base = reinterpret_cast<const char *>(sB) + hl * 4;
+    bool ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) ok[i] = b0 + i < ntile64 && b0 + i != best;
+    const char *base = reinterpret_cast<const char *>(sB) + hl * 8;
     const unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
-#define PG_BROW(o) (*reinterpret_cast<const uint32_t *>(base + (o)))
+#define PG_BROW(o) (*reinterpret_cast<const uint2 *>(base + (o)))
+#define PG_BADD(o) { const uint2 v_ = PG_BROW(o); cx += v_.x; cy += v_.y; }
+#define PG_BSPILL() { s[0] += cx & 0xFFFFu; s[1] += cx >> 16; s[2] += cy & 0xFFFFu; s[3] += cy >> 16; cx = cy = 0u; }
 #define PG_SURVIVE(task, blk)                                                  \
     {                                                                          \
         const unsigned int pos = atomicAdd(&s_cnt, 1u);                        \
@@ -554,19 +558,18 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
 
     // ---- task 0 (full sum): the units split the rows, shared-memory atomics combine them
     {
-        uint32_t lo = 0u, hi = 0u, c = 0u;
+        uint32_t s[4] = {0u, 0u, 0u, 0u}, cx = 0u, cy = 0u;
         int cnt = 0;
         for (int j = unit; j < n; j += NUNIT) {
-            c += PG_BROW(j * 64);
-            if (++cnt == 16) { lo += c & 0xFFFFu; hi += c >> 16; c = 0u; cnt = 0; }
+            PG_BADD(j * 64)
+            if (++cnt == 16) { PG_BSPILL() cnt = 0; }
         }
-        lo += c & 0xFFFFu;
-        hi += c >> 16;
-        atomicAdd(&s_full[2 * hl], lo);
-        atomicAdd(&s_full[2 * hl + 1], hi);
+        PG_BSPILL()
+#pragma unroll
+        for (int i = 0; i < 4; i++) atomicAdd(&s_full[4 * hl + i], s[i]);
     }
 
-    // ---- tasks 1..100: one replicate per half-warp
+    // ---- tasks 1..100: one replicate per quarter-warp
     int k = n >> 3;
     if (k < min_boot) k = min_boot;
     const int nb = (k + 3) >> 2;
@@ -576,28 +579,26 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         for (int t = unit; t < PG_NUM_BOOT; t += NUNIT) {
             const unsigned long long cv = __ldg(mychamp + 1 + t);
             const uint4 *lp = lists + (size_t)(t >> 2) * nb * 4 + (t & 3);
-            uint32_t lo = 0u, hi = 0u, c = 0u;
+            uint32_t s[4] = {0u, 0u, 0u, 0u}, cx = 0u, cy = 0u;
             int b = 0;
             for (; b + 4 <= nb; b += 4) {           // 16 rows x 4095 < 2^16: one spill per four batches
                 const uint4 q0 = __ldg(lp + (b + 0) * 4), q1 = __ldg(lp + (b + 1) * 4);
                 const uint4 q2 = __ldg(lp + (b + 2) * 4), q3 = __ldg(lp + (b + 3) * 4);
-                c += PG_BROW(q0.x >> 1) + PG_BROW(q0.y >> 1) + PG_BROW(q0.z >> 1) + PG_BROW(q0.w >> 1);
-                c += PG_BROW(q1.x >> 1) + PG_BROW(q1.y >> 1) + PG_BROW(q1.z >> 1) + PG_BROW(q1.w >> 1);
-                c += PG_BROW(q2.x >> 1) + PG_BROW(q2.y >> 1) + PG_BROW(q2.z >> 1) + PG_BROW(q2.w >> 1);
-                c += PG_BROW(q3.x >> 1) + PG_BROW(q3.y >> 1) + PG_BROW(q3.z >> 1) + PG_BROW(q3.w >> 1);
-                lo += c & 0xFFFFu;
-                hi += c >> 16;
-                c = 0u;
+                PG_BADD(q0.x >> 1) PG_BADD(q0.y >> 1) PG_BADD(q0.z >> 1) PG_BADD(q0.w >> 1)
+                PG_BADD(q1.x >> 1) PG_BADD(q1.y >> 1) PG_BADD(q1.z >> 1) PG_BADD(q1.w >> 1)
+                PG_BADD(q2.x >> 1) PG_BADD(q2.y >> 1) PG_BADD(q2.z >> 1) PG_BADD(q2.w >> 1)
+                PG_BADD(q3.x >> 1) PG_BADD(q3.y >> 1) PG_BADD(q3.z >> 1) PG_BADD(q3.w >> 1)
+                PG_BSPILL()
             }
             for (; b < nb; b++) {
                 const uint4 q0 = __ldg(lp + b * 4);
-                c += PG_BROW(q0.x >> 1) + PG_BROW(q0.y >> 1) + PG_BROW(q0.z >> 1) + PG_BROW(q0.w >> 1);
+                PG_BADD(q0.x >> 1) PG_BADD(q0.y >> 1) PG_BADD(q0.z >> 1) PG_BADD(q0.w >> 1)
             }
-            lo += c & 0xFFFFu;
-            hi += c >> 16;
+            PG_BSPILL()
             const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + margin;
-            if (ok0 && (unsigned long long)lo <= thr) PG_SURVIVE(1 + t, b0)
-            if (ok1 && (unsigned long long)hi <= thr) PG_SURVIVE(1 + t, b0 + 1)
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (ok[i] && (unsigned long long)s[i] <= thr) PG_SURVIVE(1 + t, b0 + i)
         }
     }
     __syncthreads();
@@ -628,6 +629,8 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     for (unsigned int i = tid; i < cnt; i += BLOCK)
         items[gb + i] = ((unsigned long long)rc << 32) | s_list[i];      // rc << 32 | task << 16 | block
 #undef PG_BROW
+#undef PG_BADD
+#undef PG_BSPILL
 #undef PG_SURVIVE
 }
 
@@ -636,11 +639,12 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
 // stopping as soon as every partial sum is above champion + margin.
 __global__ void __launch_bounds__(256)
 k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
-        const int32_t *__restrict__ nwords, int64_t read0, const uint32_t *__restrict__ boot_pool,
+        const int32_t *__restrict__ nwords, const int32_t *__restrict__ order_base,
+        const uint32_t *__restrict__ boot_pool,
         const int32_t *__restrict__ boot_off, int min_boot, int G, double vmax,
         const unsigned long long *__restrict__ items, const unsigned int *__restrict__ item_count,
         unsigned int item_cap, unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand,
-        unsigned long long *__restrict__ cand)
+        unsigned long long *__restrict__ cand, unsigned int *__restrict__ items_total)
 {
     const int lane = threadIdx.x & 31, l = lane & 7;
     const int gshift = lane & ~7;
@@ -648,13 +652,14 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
     const unsigned int ngroups = gridDim.x * (blockDim.x >> 3);
     unsigned int cnt = *item_count;
     if (cnt > item_cap) cnt = item_cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(items_total, cnt);
     for (unsigned int it = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); it < cnt; it += ngroups) {
         const unsigned long long e = items[it];
         const int task = (int)((e >> 16) & 0xFFFFu);
         if (task == (int)PG_ITEM_NULL) continue;
         const int blk = (int)(e & 0xFFFFu);
         const size_t rc = (size_t)(e >> 32);
-        const int64_t read = read0 + (int64_t)rc;
+        const int64_t read = order_base[rc];
         const int n = nwords[read];
         const uint16_t *w = words + off[read];
         int k = n >> 3;
@@ -710,17 +715,6 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
     }
 }
 
-// heavy reads start over with the all-block kernel: clear their champion slots and lists
-__global__ void k_reset_reads(const int32_t *__restrict__ list, int cnt, int64_t read0,
-                              unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand)
-{
-    const int i = blockIdx.x;
-    if (i >= cnt) return;
-    const size_t rc = (size_t)(list[i] - read0);
-    for (int t = threadIdx.x; t <= PG_NUM_BOOT; t += blockDim.x) champ[rc * (PG_NUM_BOOT + 1) + t] = PG_CHAMP_INIT;
-    if (threadIdx.x == 0) ncand[rc] = 0u;
-}
-
 // ------------------------------------------------------------------ phase 2
 
 __device__ __forceinline__ int pg_pos2genus(const int32_t *__restrict__ perm, uint32_t pos, int G)
@@ -753,7 +747,7 @@ template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS)
 k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
           const int32_t *__restrict__ nwords, const uint8_t *__restrict__ flags, const int32_t *__restrict__ order,
-          int nreads_b, int64_t read0, int nmax, const uint32_t *__restrict__ boot_pool,
+          int nreads_b, int64_t slot0, int nmax, const uint32_t *__restrict__ boot_pool,
           const int32_t *__restrict__ boot_off, int min_boot, int G, double vmax,
           const unsigned long long *__restrict__ champ, const unsigned int *__restrict__ ncand,
           const unsigned long long *__restrict__ cand, const int32_t *__restrict__ anc, int depth,
@@ -780,7 +774,7 @@ k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, c
             for (int r = lane; r < PG_NUM_BOOT; r += 32) boot_winners[read * PG_NUM_BOOT + r] = -1;
         return;
     }
-    const size_t rc = (size_t)(read - read0);
+    const size_t rc = (size_t)slot0 + slot;
     if (heavy && heavy[rc]) {                                   // too many items: the all-block kernel redoes it
         if (lane == 0) hv_list[atomicAdd(hv_count, 1)] = (int32_t)read;
         return;
@@ -905,13 +899,13 @@ k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, c
 template <int BLOCK, int MINB>
 static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, unsigned nblk_y, size_t smem, const uint16_t *d_words,
                     const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags, const int32_t *d_order,
-                    int64_t read0, int min_boot, unsigned long long *d_champ, unsigned int *d_ncand,
+                    int64_t slot0, int min_boot, unsigned long long *d_champ, unsigned int *d_ncand,
                     unsigned long long *d_cand, const int32_t *d_guess)
 {
     PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nreads_b, nblk_y);
     k_classify_q<BLOCK, MINB><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
-                                                          read0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->G,
+                                                          slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->G,
                                                           md->vmax, d_champ, d_ncand, d_cand, d_guess);
     PG_LAUNCHED(ctx);
     return PG_OK;
@@ -921,7 +915,7 @@ static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, unsigned
 // (reads with too many items are flagged in cb.heavy); version 1 = every block, partial-sum pruning.
 int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsigned nreads_b, int nmax,
                         const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
-                        const uint8_t *d_flags, const int32_t *d_order, int64_t read0, int min_boot,
+                        const uint8_t *d_flags, const int32_t *d_order, int64_t slot0, int min_boot,
                         const PgCertBufs &cb, int version)
 {
     const size_t smem = (size_t)(nmax + 1) * 128;
@@ -932,21 +926,21 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     unsigned nblk_y = (unsigned)md->ntile64;
     if (d_guess && version == 2) {
         k_guess_bm<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_bmtable, d_words, d_off, d_nwords, d_order,
-                                                               (int)nreads_b, read0, md->ntile64, md->ngroup, d_guess);
+                                                               (int)nreads_b, slot0, md->ntile64, md->ngroup, d_guess);
         PG_LAUNCHED(ctx);
         nblk_y = 1;                                     // grid row 0 = the guessed block, in full
     } else if (d_guess) {
         k_guess_block<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_order,
-                                                                  (int)nreads_b, read0, md->ntile64, d_guess);
+                                                                  (int)nreads_b, slot0, md->ntile64, d_guess);
         PG_LAUNCHED(ctx);
     }
     int rc;
     if (bk.block == 192)
-        rc = launch_q<192, 3>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
+        rc = launch_q<192, 3>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
     else if (bk.block == 448)
-        rc = launch_q<448, 2>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
+        rc = launch_q<448, 2>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
     else
-        rc = launch_q<832, 1>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, read0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
+        rc = launch_q<832, 1>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
     PG_TRY(rc);
     if (!(d_guess && version == 2)) return PG_OK;
 
@@ -954,15 +948,15 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     if (light_max > PG_LIGHT_MAX) light_max = PG_LIGHT_MAX;
     PG_CUDA(ctx, cudaMemsetAsync(cb.counters + 2, 0, 4, ctx->stream));
     const size_t bsmem = (size_t)(nmax + 1) * 64;
-    PG_CUDA(ctx, cudaFuncSetAttribute(k_bound<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-    k_bound<128><<<dim3(nreads_b, (unsigned)md->ngroup), 128, bsmem, ctx->stream>>>(
-        md->d_bmtable, d_words, d_off, d_nwords, d_flags, d_order, read0, ctx->d_boot_pool, ctx->d_boot_off, min_boot,
+    PG_CUDA(ctx, cudaFuncSetAttribute(k_bound<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    k_bound<160><<<dim3(nreads_b, (unsigned)md->ngroup), 160, bsmem, ctx->stream>>>(
+        md->d_bmtable, d_words, d_off, d_nwords, d_flags, d_order, slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot,
         md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.counters + 2, cb.item_cap, cb.heavy,
         (unsigned int)light_max);
     PG_LAUNCHED(ctx);
-    k_light<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, read0, ctx->d_boot_pool,
+    k_light<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_order - slot0, ctx->d_boot_pool,
                                                         ctx->d_boot_off, min_boot, md->G, md->vmax, cb.items,
-                                                        cb.counters + 2, cb.item_cap, cb.champ, cb.ncand, cb.cand);
+                                                        cb.counters + 2, cb.item_cap, cb.champ, cb.ncand, cb.cand, cb.counters + 3);
     PG_LAUNCHED(ctx);
     return PG_OK;
 }
@@ -971,7 +965,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
 // heavy reads (use_heavy) to cb.hv_list
 int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, const uint16_t *d_words,
                         const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags,
-                        const int32_t *d_order, int64_t read0, int min_boot, const PgCertBufs &cb, bool use_heavy,
+                        const int32_t *d_order, int64_t slot0, int min_boot, const PgCertBufs &cb, bool use_heavy,
                         pg_result *d_results, int32_t *d_boot_winners)
 {
     constexpr int WARPS = 4;
@@ -979,7 +973,7 @@ int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int 
     const size_t smem = per_warp * WARPS;
     PG_CUDA(ctx, cudaFuncSetAttribute(k_resolve<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_resolve<WARPS><<<(nreads_b + WARPS - 1) / WARPS, 32 * WARPS, smem, ctx->stream>>>(
-        md->d_table, d_words, d_off, d_nwords, d_flags, d_order, (int)nreads_b, read0, nmax, ctx->d_boot_pool,
+        md->d_table, d_words, d_off, d_nwords, d_flags, d_order, (int)nreads_b, slot0, nmax, ctx->d_boot_pool,
         ctx->d_boot_off, min_boot, md->G, md->vmax, cb.champ, cb.ncand, cb.cand, md->d_anc, md->depth, d_results,
         d_boot_winners, (int *)cb.counters, cb.fb_list, md->d_perm, use_heavy ? cb.heavy : NULL,
         (int *)cb.counters + 1, cb.hv_list);
@@ -987,10 +981,3 @@ int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int 
     return PG_OK;
 }
 
-// heavy reads: back to square one for the all-block kernel
-int pg_certified_reset(pg_ctx *ctx, const int32_t *d_list, int cnt, int64_t read0, const PgCertBufs &cb)
-{
-    k_reset_reads<<<cnt, 128, 0, ctx->stream>>>(d_list, cnt, read0, cb.champ, cb.ncand);
-    PG_LAUNCHED(ctx);
-    return PG_OK;
-}

@@ -20,6 +20,7 @@
 // fastest, so all CTAs in flight gather from the same 65536 x 128 B table slab,
 // which stays resident in L2.
 #include "pg_classify_common.cuh"
+#include <algorithm>
 
 // ------------------------------------------------------------------ K4 strict
 
@@ -36,7 +37,7 @@ template <int LPR, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK > 512) ? 1 : ((BLOCK > 256) ? 2 : 5))
 k_classify_strict(const float *__restrict__ table, const uint16_t *__restrict__ words,
                   const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
-                  const int32_t *__restrict__ order, int64_t read0,
+                  const int32_t *__restrict__ order, int64_t slot0,
                   const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off,
                   int min_boot, unsigned long long *__restrict__ best)
 {
@@ -52,7 +53,7 @@ k_classify_strict(const float *__restrict__ table, const uint16_t *__restrict__ 
     const int gbase = blockIdx.y * TG;
     const float *tbase = table + ((size_t)(gbase >> 5) * PG_NWORDS) * PG_GENUS_TILE + (gbase & 31);
     const uint16_t *w = words + off[read];
-    unsigned long long *mybest = best + (size_t)(read - read0) * (PG_NUM_BOOT + 1);
+    unsigned long long *mybest = best + ((size_t)slot0 + blockIdx.x) * (PG_NUM_BOOT + 1);   // slot = position in the chunk's order array
 
     // ---- A4: stage the read's rows for this genus block
     for (int c = tid; c < n * LPR; c += BLOCK) {
@@ -136,7 +137,7 @@ k_classify_strict(const float *__restrict__ table, const uint16_t *__restrict__ 
 // One warp per read: decode the 101 winners, count for every lineage level of
 // the determined genus the replicates whose winner shares that ancestor.
 __global__ void __launch_bounds__(256)
-k_vote(const unsigned long long *__restrict__ best, int64_t nreads, int64_t read0,
+k_vote(const unsigned long long *__restrict__ best, int64_t nreads, int64_t slot0,
        const int32_t *__restrict__ order, const int32_t *__restrict__ nwords, const uint8_t *__restrict__ flags,
        const int32_t *__restrict__ anc, int depth, pg_result *__restrict__ results,
        int32_t *__restrict__ boot_winners)
@@ -144,7 +145,7 @@ k_vote(const unsigned long long *__restrict__ best, int64_t nreads, int64_t read
     const int lane = threadIdx.x & 31;
     const int64_t ic = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (ic >= nreads) return;
-    const int64_t i = order ? (int64_t)order[ic] : read0 + ic;
+    const int64_t i = (int64_t)order[ic];
     pg_result *res = results + i;
     uint32_t *raw = reinterpret_cast<uint32_t *>(res);          // 16 x uint32
     if (flags[2 * i + 1]) {                                     // A2: short read
@@ -153,7 +154,7 @@ k_vote(const unsigned long long *__restrict__ best, int64_t nreads, int64_t read
             for (int r = lane; r < PG_NUM_BOOT; r += 32) boot_winners[i * PG_NUM_BOOT + r] = -1;
         return;
     }
-    const unsigned long long *b = best + (size_t)(i - read0) * (PG_NUM_BOOT + 1);
+    const unsigned long long *b = best + (size_t)(slot0 + ic) * (PG_NUM_BOOT + 1);
     const unsigned long long key0 = b[0];
     const int genus = (int)(0xFFFFFFFFu - (uint32_t)key0);
     const float score = pg_unord((uint32_t)(key0 >> 32));
@@ -214,27 +215,27 @@ static const Bucket &bucket_of(int n)
 template <int LPR, int BLOCK>
 static int launch_strict(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, unsigned nblocks_g, size_t smem,
                          const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
-                         const int32_t *d_order, int64_t read0, int min_boot, unsigned long long *d_best)
+                         const int32_t *d_order, int64_t slot0, int min_boot, unsigned long long *d_best)
 {
     // per device, so set it on every launch (a few microseconds)
     PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_strict<LPR, BLOCK>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nreads_b, nblocks_g);
     k_classify_strict<LPR, BLOCK><<<grid, BLOCK, smem, ctx->stream>>>(
-        md->d_table, d_words, d_off, d_nwords, d_order, read0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, d_best);
+        md->d_table, d_words, d_off, d_nwords, d_order, slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, d_best);
     PG_LAUNCHED(ctx);
     return PG_OK;
 }
 
 int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsigned nreads_b, int nmax,
                         const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
-                        const uint8_t *d_flags, const int32_t *d_order, int64_t read0, int min_boot,
+                        const uint8_t *d_flags, const int32_t *d_order, int64_t slot0, int min_boot,
                         const PgCertBufs &cb, int version);
 int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, const uint16_t *d_words,
                         const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags,
-                        const int32_t *d_order, int64_t read0, int min_boot, const PgCertBufs &cb, bool use_heavy,
+                        const int32_t *d_order, int64_t slot0, int min_boot, const PgCertBufs &cb, bool use_heavy,
                         pg_result *d_results, int32_t *d_boot_winners);
-int pg_certified_reset(pg_ctx *ctx, const int32_t *d_list, int cnt, int64_t read0, const PgCertBufs &cb);   // pg_certified.cu
+int pg_certified_reset(pg_ctx *ctx, const int32_t *d_list, int cnt, int64_t slot0, const PgCertBufs &cb);   // pg_certified.cu
 #define PG_CANDCAP 128
 
 static int ensure_boot_lists(pg_ctx *ctx, const std::vector<int> &need_n, int min_boot)
@@ -356,11 +357,11 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
         PG_TRY(pg_scratch(ctx, &ctx->s_champ, (size_t)cmax * nkeys * 8));
         PG_TRY(pg_scratch(ctx, &ctx->s_ncand, (size_t)cmax * 4));
         PG_TRY(pg_scratch(ctx, &ctx->s_candl, (size_t)cmax * PG_CANDCAP * 8));
-        PG_TRY(pg_scratch(ctx, &ctx->s_fb, (size_t)cmax * 4 + 16));
+        PG_TRY(pg_scratch(ctx, &ctx->s_fb, (size_t)count * 4 + 16));
         PG_TRY(pg_scratch(ctx, &ctx->s_guess, (size_t)cmax * 4));
         cb.item_cap = (unsigned int)(cmax * 64 < 4096 ? 4096 : cmax * 64);
         PG_TRY(pg_scratch(ctx, &ctx->s_items, (size_t)cb.item_cap * 8));
-        PG_TRY(pg_scratch(ctx, &ctx->s_heavy, (size_t)cmax * 5 + 64));
+        PG_TRY(pg_scratch(ctx, &ctx->s_heavy, (size_t)count * 4 + (size_t)cmax + 64));
         cb.champ = (unsigned long long *)ctx->s_champ.p;
         cb.ncand = (unsigned int *)ctx->s_ncand.p;
         cb.cand = (unsigned long long *)ctx->s_candl.p;
@@ -369,161 +370,149 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
         cb.guess = (int32_t *)ctx->s_guess.p;
         cb.items = (unsigned long long *)ctx->s_items.p;
         cb.hv_list = (int32_t *)ctx->s_heavy.p;
-        cb.heavy = (uint8_t *)((int32_t *)ctx->s_heavy.p + cmax);
+        cb.heavy = (uint8_t *)((int32_t *)ctx->s_heavy.p + count);
+        PG_CUDA(ctx, cudaMemsetAsync(cb.counters, 0, 16, ctx->stream));
     }
     const int wpb = 8;
 
-    for (int64_t c0 = 0; c0 < count; c0 += CHUNK) {
-        const int64_t cn = count - c0 < CHUNK ? count - c0 : CHUNK;
-        // counting sort of the chunk's reads by bucket (stable: keeps read order inside a bucket)
-        int64_t bcount[16] = {0}, bstart[16], bmaxn[16] = {0};
-        for (int64_t i = c0; i < c0 + cn; i++) {
-            int n = h_n[i], b = 0;
+    // A "slot" is a position in the order array of the chunk in flight; the per-read scratch
+    // (champion slots, near-tie lists, strict keys, guesses) is indexed by slot.
+    int64_t bcount[16], bstart[16], bmaxn[16];
+    // stable counting sort of a list of reads by bucket -> h_dst, bucket extents in bcount/bstart/bmaxn
+    auto bucket_sort = [&](const int32_t *src, int64_t base, int64_t cn, int32_t *h_dst) {
+        int64_t fill[16];
+        for (int b = 0; b < 16; b++) bcount[b] = bmaxn[b] = 0;
+        for (int64_t i = 0; i < cn; i++) {
+            const int32_t r = src ? src[i] : (int32_t)(base + i);
+            int n = h_n[r], b = 0;
             while (kBuckets[b].nmax < n) b++;
             bcount[b]++;
             if (n > bmaxn[b]) bmaxn[b] = n;
         }
         int64_t acc = 0;
-        for (int b = 0; b < kNumBuckets; b++) { bstart[b] = acc; acc += bcount[b]; }
-        {
-            int64_t fill[16];
-            for (int b = 0; b < kNumBuckets; b++) fill[b] = bstart[b];
-            for (int64_t i = c0; i < c0 + cn; i++) {
-                int n = h_n[i], b = 0;
-                while (kBuckets[b].nmax < n) b++;
-                h_order[c0 + fill[b]++] = (int32_t)i;
-            }
+        for (int b = 0; b < kNumBuckets; b++) { bstart[b] = fill[b] = acc; acc += bcount[b]; }
+        for (int64_t i = 0; i < cn; i++) {
+            const int32_t r = src ? src[i] : (int32_t)(base + i);
+            int n = h_n[r], b = 0;
+            while (kBuckets[b].nmax < n) b++;
+            h_dst[fill[b]++] = r;
         }
-        PG_CUDA(ctx, cudaMemcpyAsync(d_order, h_order + c0, (size_t)cn * 4, cudaMemcpyHostToDevice, ctx->stream));
-        PG_CUDA(ctx, cudaMemsetAsync(d_best, 0, (size_t)cn * nkeys * 8, ctx->stream));
-        if (certified) {
+    };
+    // one bucket of reads through the strict kernels (also the certified path's last resort)
+    auto run_strict = [&](const Bucket &bk, const int32_t *ord, int64_t slot0, unsigned cnt, int nmax, bool timed) -> int {
+        cudaEvent_t e0 = NULL, e1 = NULL;
+        if (timed) {
+            e0 = take_event(ctx); e1 = take_event(ctx);
+            PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+        }
+        const int TG = 4 * bk.lpr;
+        const unsigned ngb = (unsigned)((md->G + TG - 1) / TG);
+        const size_t smem = (size_t)(nmax + 1) * bk.lpr * 16;
+        int rc;
+        if (bk.lpr == 8 && bk.block == 192)
+            rc = launch_strict<8, 192>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, slot0, min_boot, d_best);
+        else if (bk.lpr == 8 && bk.block == 448)
+            rc = launch_strict<8, 448>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, slot0, min_boot, d_best);
+        else if (bk.lpr == 8)
+            rc = launch_strict<8, 832>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, slot0, min_boot, d_best);
+        else if (bk.lpr == 4)
+            rc = launch_strict<4, 832>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, slot0, min_boot, d_best);
+        else
+            rc = launch_strict<2, 832>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, slot0, min_boot, d_best);
+        PG_TRY(rc);
+        if (timed) {
+            PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+            ctx->ev_pending.push_back(std::make_pair(e0, e1));
+        }
+        k_vote<<<(cnt + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(d_best, cnt, slot0, ord, d_nwords, d_flags, md->d_anc,
+                                                                  md->depth, d_results, d_boot_winners);
+        PG_LAUNCHED(ctx);
+        return PG_OK;
+    };
+    // one pass over a set of reads (a chunk of the batch, or a list): plan 2 / plan 1 / strict.
+    // Nothing here waits for the device: fallback lists grow on the device and are read once, below.
+    auto run_pass = [&](const int32_t *h_list, int64_t cn, int plan, bool timed) -> int {
+        PG_CUDA(ctx, cudaMemcpyAsync(d_order, h_list, (size_t)cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        bool need_best = plan == 0 || !certified;           // strict keys: also for buckets the certified kernels do not take
+        for (int b = 0; b < kNumBuckets; b++)
+            if (bcount[b] && kBuckets[b].lpr != 8) need_best = true;
+        if (need_best) PG_CUDA(ctx, cudaMemsetAsync(d_best, 0, (size_t)cn * nkeys * 8, ctx->stream));
+        if (plan != 0 && certified) {
             PG_CUDA(ctx, cudaMemsetAsync(cb.champ, 0xFF, (size_t)cn * nkeys * 8, ctx->stream));
             PG_CUDA(ctx, cudaMemsetAsync(cb.ncand, 0, (size_t)cn * 4, ctx->stream));
-            PG_CUDA(ctx, cudaMemsetAsync(cb.counters, 0, 16, ctx->stream));
             PG_CUDA(ctx, cudaMemsetAsync(cb.heavy, 0, (size_t)cn, ctx->stream));
         }
-
-        // one bucket of reads through the strict kernels (also the certified path's fallback)
-        auto run_strict = [&](const Bucket &bk, const int32_t *ord, unsigned cnt, int nmax, bool timed) -> int {
-            cudaEvent_t e0 = NULL, e1 = NULL;
-            if (timed) {
-                e0 = take_event(ctx); e1 = take_event(ctx);
-                PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-            }
-            const int TG = 4 * bk.lpr;
-            const unsigned ngb = (unsigned)((md->G + TG - 1) / TG);
-            const size_t smem = (size_t)(nmax + 1) * bk.lpr * 16;
-            int rc;
-            if (bk.lpr == 8 && bk.block == 192)
-                rc = launch_strict<8, 192>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
-            else if (bk.lpr == 8 && bk.block == 448)
-                rc = launch_strict<8, 448>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
-            else if (bk.lpr == 8)
-                rc = launch_strict<8, 832>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
-            else if (bk.lpr == 4)
-                rc = launch_strict<4, 832>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
-            else
-                rc = launch_strict<2, 832>(ctx, md, cnt, ngb, smem, d_words, d_off, d_nwords, ord, c0, min_boot, d_best);
-            PG_TRY(rc);
-            if (timed) {
-                PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
-                ctx->ev_pending.push_back(std::make_pair(e0, e1));
-            }
-            k_vote<<<(cnt + wpb - 1) / wpb, wpb * 32, 0, ctx->stream>>>(d_best, cnt, c0, ord, d_nwords, d_flags, md->d_anc,
-                                                                      md->depth, d_results, d_boot_winners);
-            PG_LAUNCHED(ctx);
-            return PG_OK;
-        };
-
         for (int b = 0; b < kNumBuckets; b++) {
             if (!bcount[b]) continue;
             const Bucket &bk = kBuckets[b];
             const int nmax = (int)bmaxn[b];
             const int32_t *ord = d_order + bstart[b];
-            if (certified && bk.lpr == 8) {
-                ctx->st_certified += bcount[b];
-                cudaEvent_t e0 = take_event(ctx), e1 = take_event(ctx);
-                PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+            if (certified && plan != 0 && bk.lpr == 8) {
+                if (timed) ctx->st_certified += bcount[b];
+                cudaEvent_t e0 = NULL, e1 = NULL;
+                if (timed) {
+                    e0 = take_event(ctx); e1 = take_event(ctx);
+                    PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+                }
                 PG_TRY(pg_certified_phase1(ctx, md, bk, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords, d_flags, ord,
-                                           c0, min_boot, cb, cert_version));
-                PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
-                ctx->ev_pending.push_back(std::make_pair(e0, e1));
-                PG_TRY(pg_certified_phase2(ctx, md, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords, d_flags, ord, c0,
-                                           min_boot, cb, cert_version == 2, d_results, d_boot_winners));
+                                           bstart[b], min_boot, cb, plan));
+                if (timed) {
+                    PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+                    ctx->ev_pending.push_back(std::make_pair(e0, e1));
+                }
+                PG_TRY(pg_certified_phase2(ctx, md, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords, d_flags, ord,
+                                           bstart[b], min_boot, cb, plan == 2, d_results, d_boot_winners));
             } else {
-                ctx->st_strict += bcount[b];
-                PG_TRY(run_strict(bk, ord, (unsigned)bcount[b], nmax, true));
+                if (timed) ctx->st_strict += bcount[b];
+                PG_TRY(run_strict(bk, ord, bstart[b], (unsigned)bcount[b], nmax, timed));
             }
         }
+        return PG_OK;
+    };
 
-        if (certified) {
-            // sort a list of reads (host copy) by bucket and upload it to d_order
-            int64_t fcount[16], fstart[16], fmaxn[16];
-            auto bucket_list = [&](const std::vector<int32_t> &lst, std::vector<int32_t> &sorted) -> int {
-                int64_t ffill[16];
-                for (int b = 0; b < 16; b++) fcount[b] = fmaxn[b] = 0;
-                for (int32_t r : lst) {
-                    int n = h_n[r], b = 0;
-                    while (kBuckets[b].nmax < n) b++;
-                    fcount[b]++;
-                    if (n > fmaxn[b]) fmaxn[b] = n;
-                }
-                int64_t a2 = 0;
-                for (int b = 0; b < kNumBuckets; b++) { fstart[b] = ffill[b] = a2; a2 += fcount[b]; }
-                sorted.resize(lst.size());
-                for (int32_t r : lst) {
-                    int n = h_n[r], b = 0;
-                    while (kBuckets[b].nmax < n) b++;
-                    sorted[(size_t)ffill[b]++] = r;
-                }
-                PG_CUDA(ctx, cudaMemcpyAsync(d_order, sorted.data(), sorted.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-                return PG_OK;
-            };
-            unsigned int cnts[4] = {0, 0, 0, 0};
-            PG_CUDA(ctx, cudaMemcpyAsync(cnts, cb.counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    for (int64_t c0 = 0; c0 < count; c0 += CHUNK) {
+        const int64_t cn = count - c0 < CHUNK ? count - c0 : CHUNK;
+        bucket_sort(NULL, c0, cn, h_order + c0);
+        PG_TRY(run_pass(h_order + c0, cn, certified ? cert_version : 0, true));
+    }
+
+    if (certified) {
+        // Deferred work, read once for the whole batch:
+        //   heavy reads (plan 2 left too many (task, block) pairs open) -> plan 1, the all-block kernel;
+        //   reads whose near-tie list overflowed (in either plan)        -> the strict kernels.
+        unsigned int cnts[4] = {0, 0, 0, 0};
+        PG_CUDA(ctx, cudaMemcpyAsync(cnts, cb.counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->st_items = cnts[3];
+        ctx->st_heavy = cnts[1];
+        std::vector<int32_t> lst, sorted;
+        if (cnts[1] > 0) {
+            lst.resize(cnts[1]);
+            sorted.resize(cnts[1]);
+            PG_CUDA(ctx, cudaMemcpyAsync(lst.data(), cb.hv_list, lst.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
             PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            ctx->st_items += cnts[2];
-            std::vector<int32_t> lst, sorted, fb;
-            if (cnts[0] > 0) {                                  // near-tie list overflowed: strict kernels (below)
-                fb.resize((size_t)cnts[0]);
-                PG_CUDA(ctx, cudaMemcpyAsync(fb.data(), cb.fb_list, fb.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-                PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            std::sort(lst.begin(), lst.end());                   // device order is arbitrary; keep runs reproducible
+            for (size_t p0 = 0; p0 < lst.size(); p0 += (size_t)CHUNK) {
+                const int64_t cn = (int64_t)(lst.size() - p0 < (size_t)CHUNK ? lst.size() - p0 : (size_t)CHUNK);
+                bucket_sort(lst.data() + p0, 0, cn, sorted.data() + p0);
+                PG_TRY(run_pass(sorted.data() + p0, cn, 1, false));
             }
-            if (cnts[1] > 0) {
-                // reads with too many surviving (task, block) items: the all-block kernel does them from scratch
-                const int nhv = (int)cnts[1];
-                ctx->st_heavy += nhv;
-                lst.resize((size_t)nhv);
-                PG_CUDA(ctx, cudaMemcpyAsync(lst.data(), cb.hv_list, (size_t)nhv * 4, cudaMemcpyDeviceToHost, ctx->stream));
-                PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                PG_TRY(bucket_list(lst, sorted));
-                PG_TRY(pg_certified_reset(ctx, d_order, nhv, c0, cb));
-                PG_CUDA(ctx, cudaMemsetAsync(cb.counters, 0, 4, ctx->stream));
-                for (int b = 0; b < kNumBuckets; b++) {
-                    if (!fcount[b]) continue;
-                    PG_TRY(pg_certified_phase1(ctx, md, kBuckets[b], (unsigned)fcount[b], (int)fmaxn[b], d_words, d_off, d_nwords,
-                                               d_flags, d_order + fstart[b], c0, min_boot, cb, 1));
-                    PG_TRY(pg_certified_phase2(ctx, md, (unsigned)fcount[b], (int)fmaxn[b], d_words, d_off, d_nwords, d_flags,
-                                               d_order + fstart[b], c0, min_boot, cb, false, d_results, d_boot_winners));
-                }
-                unsigned int more = 0;
-                PG_CUDA(ctx, cudaMemcpyAsync(&more, cb.counters, 4, cudaMemcpyDeviceToHost, ctx->stream));
-                PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // also: `sorted` is a stack vector
-                if (more > 0) {
-                    const size_t at = fb.size();
-                    fb.resize(at + more);
-                    PG_CUDA(ctx, cudaMemcpy(fb.data() + at, cb.fb_list, (size_t)more * 4, cudaMemcpyDeviceToHost));
-                }
+            PG_CUDA(ctx, cudaMemcpyAsync(cnts, cb.counters, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // `sorted` is read by the copies above
+        }
+        if (cnts[0] > 0) {
+            ctx->st_handed_back = cnts[0];
+            lst.resize(cnts[0]);
+            sorted.resize(cnts[0]);
+            PG_CUDA(ctx, cudaMemcpyAsync(lst.data(), cb.fb_list, lst.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            std::sort(lst.begin(), lst.end());
+            for (size_t p0 = 0; p0 < lst.size(); p0 += (size_t)CHUNK) {
+                const int64_t cn = (int64_t)(lst.size() - p0 < (size_t)CHUNK ? lst.size() - p0 : (size_t)CHUNK);
+                bucket_sort(lst.data() + p0, 0, cn, sorted.data() + p0);
+                PG_TRY(run_pass(sorted.data() + p0, cn, 0, false));
             }
-            if (!fb.empty()) {
-                const int nfb = (int)fb.size();
-                ctx->st_handed_back += nfb;
-                PG_TRY(bucket_list(fb, sorted));
-                for (int b = 0; b < kNumBuckets; b++)
-                    if (fcount[b])
-                        PG_TRY(run_strict(kBuckets[b], d_order + fstart[b], (unsigned)fcount[b], (int)fmaxn[b], false));
-                PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // `sorted` is a stack vector
-            }
+            PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // `sorted` is a stack vector
         }
     }
     return PG_OK;
