@@ -303,6 +303,7 @@ def main():
     launches = ctx.launch_count() - l0
     kms, klaunch = ctx.kernel_time()
     clocks = sampler.stop() if rank == 0 else None
+    route = ctx.classify_stats()                 # routing of the last step's reads inside the library
 
     for i in range(min(args.warmup, 2)):
         step_e2e(i)
@@ -331,10 +332,12 @@ def main():
                                            f"inputs per step ({args.reads * L / 1e6:.0f} MB ASCII, "
                                            f"{args.reads * n_words * 2 / 1e6:.0f} MB word ids) exceed the 126 MB L2; batches alternate"),
                            mode="strict" if args.mode == 0 else "certified", parallelism=f"reads sharded x{world}",
-                           median_words=n_words),
+                           median_words=n_words, routing_last_step=route),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(reads_per_launch), "peak_source": peak_src,
-                         "kernel": "k_classify_q" if args.mode == 1 else "k_classify_strict", "kernel_ms_per_launch": kms / max(klaunch, 1),
+                         "kernel": ("certified phase 1 = k_guess_bm + k_classify_q (best block) + k_bound + k_light, timed as one group"
+                                    if args.mode == 1 else "k_classify_strict"),
+                         "kernel_ms_per_launch": kms / max(klaunch, 1),
                          "kernel_share_of_step": kms / ms if ms > 0 else None,
                          "algorithmic_bytes_per_read": bpr, "reads_per_launch": reads_per_launch},
             "e2e": {"value": e2e_value, "unit": "reads/s", "ms_per_step": ms_e2e / args.steps,

@@ -24,6 +24,7 @@
 // Phase 2 (k_resolve): one warp per read; strict re-check of survivors, then the A9 vote.
 // Reads whose list overflows are handed back to the strict kernels.
 #include "pg_classify_common.cuh"
+#include <algorithm>
 
 #define PG_Q_SCALE 128.0            // units per nat
 #define PG_Q_MAX   4095             // 12-bit field: 16 rows x 4095 < 65536
@@ -104,31 +105,104 @@ __global__ void k_blockmin(const uint16_t *__restrict__ q, int ntile64, uint16_t
     bm[((size_t)(blk >> 5) * PG_NWORDS + w) * 32 + (blk & 31)] = (uint16_t)m;
 }
 
-// table layout of certified mode: perm_host[p] = genus stored at position p (a permutation of 0..G-1)
-int pg_model_set_layout(pg_model *md, const int32_t *perm_host)
+// Table layout of certified mode.  pos_host[p] = genus stored at table position p, or -1 for padding;
+// npos is a multiple of 64 (one 64-position block per 128-byte row segment).  NULL = the genus order of
+// the training file.  The quantised tables are rebuilt by pg_model_derive_quantised().
+int pg_model_set_layout(pg_model *md, const int32_t *pos_host, int npos)
 {
     pg_ctx *ctx = md->ctx;
-    const int ntile64 = (md->G + 63) / 64;
-    std::vector<int32_t> full((size_t)ntile64 * 64);
-    for (size_t p = 0; p < full.size(); p++) full[p] = p < (size_t)md->G ? (perm_host ? perm_host[p] : (int32_t)p) : 0x7FFFFFFF;
-    if (!md->d_perm) PG_CUDA(ctx, cudaMalloc(&md->d_perm, full.size() * 4));
+    if (!pos_host) npos = ((md->G + 63) / 64) * 64;
+    const int nblk = npos / 64;
+    std::vector<int32_t> full((size_t)npos);
+    std::vector<unsigned long long> mask((size_t)nblk, 0ULL);
+    for (int p = 0; p < npos; p++) {
+        const int32_t g = pos_host ? pos_host[p] : (p < md->G ? p : -1);
+        full[(size_t)p] = g >= 0 ? g : 0x7FFFFFFF;
+        if (g >= 0) mask[(size_t)(p >> 6)] |= 1ULL << (p & 63);
+    }
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nblk != md->ntile64) {                           // a different block count: the tables are re-allocated
+        cudaFree(md->d_perm); cudaFree(md->d_blockmask); cudaFree(md->d_qtable); cudaFree(md->d_bmtable);
+        md->d_perm = NULL; md->d_blockmask = NULL; md->d_qtable = NULL; md->d_bmtable = NULL;
+    }
+    md->ntile64 = nblk;
+    md->ngroup = (nblk + 31) / 32;
+    if (!md->d_perm) {
+        PG_CUDA(ctx, cudaMalloc(&md->d_perm, full.size() * 4));
+        PG_CUDA(ctx, cudaMalloc(&md->d_blockmask, mask.size() * 8));
+    }
     PG_CUDA(ctx, cudaMemcpy(md->d_perm, full.data(), full.size() * 4, cudaMemcpyHostToDevice));
+    PG_CUDA(ctx, cudaMemcpy(md->d_blockmask, mask.data(), mask.size() * 8, cudaMemcpyHostToDevice));
     return PG_OK;
+}
+
+// Lineage-aligned layout: genera in depth-first lineage order, cut into blocks of at most 64 so that a
+// clade is split only when it does not fit one block.  The relatives of a read's genus then share its
+// block, and the blocks next to it hold other clades whose lower bound (k_bound) dismisses them.
+int pg_model_layout_from_lineage(pg_model *md, const int32_t *anc, int depth)
+{
+    const int G = md->G;
+    std::vector<int32_t> order((size_t)G);
+    for (int g = 0; g < G; g++) order[(size_t)g] = g;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        const int32_t *ra = anc + (size_t)a * depth, *rb = anc + (size_t)b * depth;
+        for (int d = 0; d < depth; d++)
+            if (ra[d] != rb[d]) return ra[d] < rb[d];
+        return false;
+    });
+    // units: maximal clades of at most 64 genera (ranges of `order`), found top-down
+    std::vector<std::pair<int, int>> units, stack;
+    std::vector<int> level;
+    stack.push_back(std::make_pair(0, G));
+    level.push_back(0);
+    while (!stack.empty()) {
+        const std::pair<int, int> r = stack.back();
+        const int lv = level.back();
+        stack.pop_back();
+        level.pop_back();
+        if (r.second - r.first <= 64 || lv >= depth) {
+            for (int s0 = r.first; s0 < r.second; s0 += 64) units.push_back(std::make_pair(s0, s0 + 64 < r.second ? s0 + 64 : r.second));
+            continue;
+        }
+        // children at this level, pushed in reverse so they pop in order
+        std::vector<std::pair<int, int>> kids;
+        int i = r.first;
+        while (i < r.second) {
+            int j = i + 1;
+            while (j < r.second && anc[(size_t)order[(size_t)j] * depth + lv] == anc[(size_t)order[(size_t)i] * depth + lv]) j++;
+            kids.push_back(std::make_pair(i, j));
+            i = j;
+        }
+        for (size_t c = kids.size(); c-- > 0;) { stack.push_back(kids[c]); level.push_back(lv + 1); }
+    }
+    std::sort(units.begin(), units.end());
+    // greedy packing of consecutive units into blocks of <= 64
+    std::vector<int32_t> pos;
+    int fill = 0;
+    for (const std::pair<int, int> &u : units) {
+        const int len = u.second - u.first;
+        if (fill + len > 64) {
+            pos.resize(((pos.size() + 63) / 64) * 64, -1);
+            fill = 0;
+        }
+        for (int i = u.first; i < u.second; i++) pos.push_back(order[(size_t)i]);
+        fill += len;
+    }
+    pos.resize(((pos.size() + 63) / 64) * 64, -1);
+    return pg_model_set_layout(md, pos.data(), (int)pos.size());
 }
 
 int pg_model_derive_quantised(pg_model *md)
 {
     pg_ctx *ctx = md->ctx;
-    md->ntile64 = (md->G + 63) / 64;
-    md->ngroup = (md->ntile64 + 31) / 32;
     md->q_ok = false;
+    if (!md->d_perm) PG_TRY(pg_model_set_layout(md, NULL, 0));
     const size_t cells = (size_t)md->ntile64 * PG_NWORDS * 64;
     const size_t bmcells = (size_t)md->ngroup * PG_NWORDS * 32;
-    if (!md->d_perm) PG_TRY(pg_model_set_layout(md, NULL));
+    if (!md->d_rowmax) PG_CUDA(ctx, cudaMalloc(&md->d_rowmax, PG_NWORDS * 4));
     if (!md->d_qtable) {
         cudaError_t e;
         if ((e = cudaMalloc(&md->d_qtable, cells * 2)) != cudaSuccess ||
-            (e = cudaMalloc(&md->d_rowmax, PG_NWORDS * 4)) != cudaSuccess ||
             (e = cudaMalloc(&md->d_bmtable, bmcells * 2)) != cudaSuccess) {
             (void)cudaGetLastError();
             return pg_fail(ctx, PG_ENOMEM, "quantised table allocation failed: %s", cudaGetErrorString(e));
@@ -181,7 +255,8 @@ __device__ __forceinline__ void pg_emit(unsigned int *ncand, unsigned long long 
 //           leader posts it to the (read, task) champion slot with a 64-bit atomicMin.
 //   finish: with the slot's previous value, append near-ties of the running minimum to
 //           the read's list; the displaced champion stays listed if it is still close.
-// sums[i] belongs to genus genus0+i; `mask` = the lanes sharing this task.
+// sums[i] belongs to table position genus0+i, bit i of vbits says whether a genus lives there
+// (padding positions never compete); `mask` = the lanes sharing this task.
 struct PgPending {
     unsigned long long old;      // leader only: value the slot held before our atomicMin
     uint32_t bkey;               // block minimum: sum << 6 | genus - gbase
@@ -190,14 +265,14 @@ struct PgPending {
 
 template <int NV>
 __device__ __forceinline__ void pg_epilogue_begin(unsigned mask, bool leader, const uint32_t *sums, uint32_t genus0,
-                                                  uint32_t gbase, int G, unsigned long long *champ_slot,
+                                                  uint32_t gbase, uint32_t vbits, unsigned long long *champ_slot,
                                                   PgPending &p)
 {
     uint32_t lkey = 0xFFFFFFFFu;
 #pragma unroll
     for (int i = 0; i < NV; i++) {
         const uint32_t g = genus0 + i;
-        const uint32_t key = (int)g < G ? ((sums[i] << 6) | (g - gbase)) : 0xFFFFFFFFu;
+        const uint32_t key = ((vbits >> i) & 1u) ? ((sums[i] << 6) | (g - gbase)) : 0xFFFFFFFFu;
         lkey = min(lkey, key);
     }
     p.lmin = lkey >> 6;
@@ -209,7 +284,7 @@ __device__ __forceinline__ void pg_epilogue_begin(unsigned mask, bool leader, co
 
 template <int NV>
 __device__ __forceinline__ void pg_epilogue_finish(unsigned mask, bool leader, int leader_lane, const uint32_t *sums,
-                                                   uint32_t genus0, uint32_t gbase, int G, int task,
+                                                   uint32_t genus0, uint32_t gbase, uint32_t vbits, int task,
                                                    uint32_t margin, const PgPending &p, unsigned int *ncand,
                                                    unsigned long long *cand)
 {
@@ -222,7 +297,7 @@ __device__ __forceinline__ void pg_epilogue_finish(unsigned mask, bool leader, i
 #pragma unroll
         for (int i = 0; i < NV; i++) {
             const uint32_t g = genus0 + i;
-            if ((int)g < G && (unsigned long long)sums[i] <= thr && !(took && g == bg)) pg_emit(ncand, cand, task, g, sums[i]);
+            if (((vbits >> i) & 1u) && (unsigned long long)sums[i] <= thr && !(took && g == bg)) pg_emit(ncand, cand, task, g, sums[i]);
         }
     }
     // the displaced champion stays a candidate if it is within the margin of the new one
@@ -245,7 +320,8 @@ __global__ void __launch_bounds__(BLOCK, MINB)
 k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
              const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
              const uint8_t *__restrict__ flags, const int32_t *__restrict__ order, int64_t slot0,
-             const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot, int G,
+             const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot,
+             const unsigned long long *__restrict__ blockmask,
              double vmax, unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand,
              unsigned long long *__restrict__ cand, const int32_t *__restrict__ guess)
 {
@@ -273,6 +349,7 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
         prune_on = blockIdx.y != 0;
     }
     const int gbase = blk * 64;
+    const unsigned long long bmask = blockmask[blk];           // which of the block's 64 positions hold a genus
     const uint16_t *tbase = qtable + (size_t)blk * PG_NWORDS * 64;
     const uint16_t *w = words + off[read];
     unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
@@ -314,8 +391,9 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
         hi += c >> 16;
         const uint32_t sums[2] = {lo, hi};
         PgPending pp;
-        pg_epilogue_begin<2>(0xffffffffu, tid == 0, sums, (uint32_t)(gbase + 2 * tid), (uint32_t)gbase, G, mychamp, pp);
-        pg_epilogue_finish<2>(0xffffffffu, tid == 0, 0, sums, (uint32_t)(gbase + 2 * tid), (uint32_t)gbase, G, 0,
+        const uint32_t vb2 = (uint32_t)(bmask >> (2 * tid)) & 3u;
+        pg_epilogue_begin<2>(0xffffffffu, tid == 0, sums, (uint32_t)(gbase + 2 * tid), (uint32_t)gbase, vb2, mychamp, pp);
+        pg_epilogue_finish<2>(0xffffffffu, tid == 0, 0, sums, (uint32_t)(gbase + 2 * tid), (uint32_t)gbase, vb2, 0,
                               margin_full, pp, mync, mycand);
         return;
     }
@@ -336,6 +414,7 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
 
     const int leader_lane = (lane / LPR) * LPR;
     const uint32_t genus0 = (uint32_t)(gbase + l * 8);
+    const uint32_t vb8 = (uint32_t)(bmask >> (8 * l)) & 0xFFu;
     PgPending pend;
     uint32_t psum[8];
     int ptask = -1;
@@ -403,18 +482,18 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
         }
         // the previous replicate's atomic has had a whole main loop to come back
         if (ptask >= 0)
-            pg_epilogue_finish<8>(gmask, l == 0, leader_lane, psum, genus0, (uint32_t)gbase, G, 1 + ptask, margin, pend,
+            pg_epilogue_finish<8>(gmask, l == 0, leader_lane, psum, genus0, (uint32_t)gbase, vb8, 1 + ptask, margin, pend,
                                   mync, mycand);
         ptask = -1;
         if (active) {                                   // not pruned: this block may hold the winner or a near-tie
             psum[0] = s0; psum[1] = s1; psum[2] = s2; psum[3] = s3;
             psum[4] = s4; psum[5] = s5; psum[6] = s6; psum[7] = s7;
             ptask = task;
-            pg_epilogue_begin<8>(gmask, l == 0, psum, genus0, (uint32_t)gbase, G, mychamp + 1 + task, pend);
+            pg_epilogue_begin<8>(gmask, l == 0, psum, genus0, (uint32_t)gbase, vb8, mychamp + 1 + task, pend);
         }
     }
     if (ptask >= 0)
-        pg_epilogue_finish<8>(gmask, l == 0, leader_lane, psum, genus0, (uint32_t)gbase, G, 1 + ptask, margin, pend, mync,
+        pg_epilogue_finish<8>(gmask, l == 0, leader_lane, psum, genus0, (uint32_t)gbase, vb8, 1 + ptask, margin, pend, mync,
                               mycand);
 #undef PG_LD4P
 #undef PG_PRUNE_CHECK
@@ -540,6 +619,7 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     __syncthreads();
 
     const int unit = tid >> 3, hl = tid & 7;
+    const unsigned qmask = 0xFFu << (tid & 24);
     const int b0 = grp * 32 + 4 * hl;
     const int best = guess[rc];
     bool ok[4];
@@ -579,26 +659,39 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         for (int t = unit; t < PG_NUM_BOOT; t += NUNIT) {
             const unsigned long long cv = __ldg(mychamp + 1 + t);
             const uint4 *lp = lists + (size_t)(t >> 2) * nb * 4 + (t & 3);
+            const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + margin;
             uint32_t s[4] = {0u, 0u, 0u, 0u}, cx = 0u, cy = 0u;
             int b = 0;
+            bool open = true;                       // some block of this unit may still be within the threshold
+            // The four units of a warp walk in lockstep (a settled unit just stops loading): partial sums only
+            // grow, so once every block of a unit is above the threshold its task is settled.
             for (; b + 4 <= nb; b += 4) {           // 16 rows x 4095 < 2^16: one spill per four batches
-                const uint4 q0 = __ldg(lp + (b + 0) * 4), q1 = __ldg(lp + (b + 1) * 4);
-                const uint4 q2 = __ldg(lp + (b + 2) * 4), q3 = __ldg(lp + (b + 3) * 4);
-                PG_BADD(q0.x >> 1) PG_BADD(q0.y >> 1) PG_BADD(q0.z >> 1) PG_BADD(q0.w >> 1)
-                PG_BADD(q1.x >> 1) PG_BADD(q1.y >> 1) PG_BADD(q1.z >> 1) PG_BADD(q1.w >> 1)
-                PG_BADD(q2.x >> 1) PG_BADD(q2.y >> 1) PG_BADD(q2.z >> 1) PG_BADD(q2.w >> 1)
-                PG_BADD(q3.x >> 1) PG_BADD(q3.y >> 1) PG_BADD(q3.z >> 1) PG_BADD(q3.w >> 1)
-                PG_BSPILL()
+                if (open) {
+                    const uint4 q0 = __ldg(lp + (b + 0) * 4), q1 = __ldg(lp + (b + 1) * 4);
+                    const uint4 q2 = __ldg(lp + (b + 2) * 4), q3 = __ldg(lp + (b + 3) * 4);
+                    PG_BADD(q0.x >> 1) PG_BADD(q0.y >> 1) PG_BADD(q0.z >> 1) PG_BADD(q0.w >> 1)
+                    PG_BADD(q1.x >> 1) PG_BADD(q1.y >> 1) PG_BADD(q1.z >> 1) PG_BADD(q1.w >> 1)
+                    PG_BADD(q2.x >> 1) PG_BADD(q2.y >> 1) PG_BADD(q2.z >> 1) PG_BADD(q2.w >> 1)
+                    PG_BADD(q3.x >> 1) PG_BADD(q3.y >> 1) PG_BADD(q3.z >> 1) PG_BADD(q3.w >> 1)
+                    PG_BSPILL()
+                }
+                bool mine = false;
+#pragma unroll
+                for (int i = 0; i < 4; i++) mine |= ok[i] && (unsigned long long)s[i] <= thr;
+                const unsigned vote = __ballot_sync(0xffffffffu, mine && open);
+                open = (vote & qmask) != 0u;
+                if (vote == 0u) break;
             }
-            for (; b < nb; b++) {
-                const uint4 q0 = __ldg(lp + b * 4);
-                PG_BADD(q0.x >> 1) PG_BADD(q0.y >> 1) PG_BADD(q0.z >> 1) PG_BADD(q0.w >> 1)
+            if (open) {
+                for (; b < nb; b++) {
+                    const uint4 q0 = __ldg(lp + b * 4);
+                    PG_BADD(q0.x >> 1) PG_BADD(q0.y >> 1) PG_BADD(q0.z >> 1) PG_BADD(q0.w >> 1)
+                }
             }
             PG_BSPILL()
-            const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + margin;
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                if (ok[i] && (unsigned long long)s[i] <= thr) PG_SURVIVE(1 + t, b0 + i)
+                if (open && ok[i] && (unsigned long long)s[i] <= thr) PG_SURVIVE(1 + t, b0 + i)
         }
     }
     __syncthreads();
@@ -641,8 +734,8 @@ __global__ void __launch_bounds__(256)
 k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
         const int32_t *__restrict__ nwords, const int32_t *__restrict__ order_base,
         const uint32_t *__restrict__ boot_pool,
-        const int32_t *__restrict__ boot_off, int min_boot, int G, double vmax,
-        const unsigned long long *__restrict__ items, const unsigned int *__restrict__ item_count,
+        const int32_t *__restrict__ boot_off, int min_boot, const unsigned long long *__restrict__ blockmask,
+        double vmax, const unsigned long long *__restrict__ items, const unsigned int *__restrict__ item_count,
         unsigned int item_cap, unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand,
         unsigned long long *__restrict__ cand, unsigned int *__restrict__ items_total)
 {
@@ -709,17 +802,19 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
         const uint32_t sums[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
         const uint32_t gbase = (uint32_t)blk * 64u;
         PgPending pend;
-        pg_epilogue_begin<8>(gmask, l == 0, sums, gbase + (uint32_t)l * 8u, gbase, G, slot, pend);
-        pg_epilogue_finish<8>(gmask, l == 0, gshift, sums, gbase + (uint32_t)l * 8u, gbase, G, task, margin, pend,
+        const uint32_t vb8 = (uint32_t)(__ldg(blockmask + blk) >> (8 * l)) & 0xFFu;
+        pg_epilogue_begin<8>(gmask, l == 0, sums, gbase + (uint32_t)l * 8u, gbase, vb8, slot, pend);
+        pg_epilogue_finish<8>(gmask, l == 0, gshift, sums, gbase + (uint32_t)l * 8u, gbase, vb8, task, margin, pend,
                               ncand + rc, cand + rc * PG_CANDCAP);
     }
 }
 
 // ------------------------------------------------------------------ phase 2
 
-__device__ __forceinline__ int pg_pos2genus(const int32_t *__restrict__ perm, uint32_t pos, int G)
+__device__ __forceinline__ int pg_pos2genus(const int32_t *__restrict__ perm, uint32_t pos, int npos, int G)
 {
-    return pos < (uint32_t)G ? perm[pos] : 0;       // real genera occupy positions 0..G-1
+    const int g = pos < (uint32_t)npos ? perm[pos] : G;     // padding positions hold a value >= G
+    return g < G ? g : 0;
 }
 
 // strict fp32 sum of genus g over the task's rows, in the reference's order
@@ -743,6 +838,41 @@ __device__ float pg_strict_sum(const float *__restrict__ table, const uint16_t *
     return a;
 }
 
+// the same sum by the whole warp: the gathers are spread over the lanes (8 in flight per lane), the adds
+// stay one chain in the reference's order (shuffle + FADD per term); every lane ends with the result
+__device__ float pg_strict_sum_warp(const float *__restrict__ table, const uint16_t *sw, int n, int k, int nb,
+                                    const uint32_t *__restrict__ list, int task, uint32_t g, int lane)
+{
+    const float *tb = table + ((size_t)(g >> 5) * PG_NWORDS) * PG_GENUS_TILE + (g & 31);
+    const int terms = task == 0 ? n : k;
+    const int t1 = task > 0 ? task - 1 : 0;
+    const uint32_t *lp = list + ((size_t)(t1 / 4) * nb * 4 + (t1 % 4)) * 4;
+    float a = 0.f;
+    for (int base = 0; base < terms; base += 256) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int j = base + u * 32 + lane;
+            v[u] = 0.f;
+            if (j < terms) {
+                const uint32_t r = task == 0 ? (uint32_t)j : __ldg(lp + (size_t)(j >> 2) * 16 + (j & 3)) / PG_ROW_PITCH;
+                v[u] = __ldg(tb + (size_t)sw[r] * PG_GENUS_TILE);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int j0 = base + u * 32;
+            if (j0 + 32 <= terms) {
+#pragma unroll
+                for (int l = 0; l < 32; l++) a = __fadd_rn(a, __shfl_sync(0xffffffffu, v[u], l));
+            } else if (j0 < terms) {
+                for (int l = 0; j0 + l < terms; l++) a = __fadd_rn(a, __shfl_sync(0xffffffffu, v[u], l));
+            }
+        }
+    }
+    return a;
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS)
 k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
@@ -752,7 +882,7 @@ k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, c
           const unsigned long long *__restrict__ champ, const unsigned int *__restrict__ ncand,
           const unsigned long long *__restrict__ cand, const int32_t *__restrict__ anc, int depth,
           pg_result *__restrict__ results, int32_t *__restrict__ boot_winners, int *__restrict__ fb_count,
-          int32_t *__restrict__ fb_list, const int32_t *__restrict__ perm, const uint8_t *__restrict__ heavy,
+          int32_t *__restrict__ fb_list, const int32_t *__restrict__ perm, int npos, const uint8_t *__restrict__ heavy,
           int *__restrict__ hv_count, int32_t *__restrict__ hv_list)
 {
     extern __shared__ unsigned char smem_raw[];
@@ -797,7 +927,7 @@ k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, c
     const bool trivial_rep = (nb == 0 || n == 0);               // k == 0: all sums 0 -> genus 0
 
     for (int t = lane; t <= PG_NUM_BOOT; t += 32)
-        winners[t] = (n == 0 || (t > 0 && trivial_rep)) ? 0 : pg_pos2genus(perm, (uint32_t)mychamp[t], G);   // table position -> genus
+        winners[t] = (n == 0 || (t > 0 && trivial_rep)) ? 0 : pg_pos2genus(perm, (uint32_t)mychamp[t], npos, G);   // table position -> genus
     if (lane < 4) need[lane] = 0u;
     __syncwarp();
     if (n > 0) {
@@ -834,10 +964,22 @@ k_resolve(const float *__restrict__ table, const uint16_t *__restrict__ words, c
                     match = true;
                     g = (uint32_t)ch;
                 }
-                if (match) g = (uint32_t)pg_pos2genus(perm, g, G);    // ties resolve on the genus index, not the position
+                if (match) g = (uint32_t)pg_pos2genus(perm, g, npos, G);    // ties resolve on the genus index, not the position
                 const unsigned int bal = __ballot_sync(0xffffffffu, match);
+                float a = 0.f;
+                if (__popc(bal) <= 6) {
+                    // few survivors (the usual case): the warp sums them one after the other
+                    unsigned int todo = bal;
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const float r = pg_strict_sum_warp(table, sw, n, k, nb, list, t, __shfl_sync(0xffffffffu, g, src), lane);
+                        if (lane == src) a = r;
+                    }
+                } else if (match) {
+                    a = pg_strict_sum(table, sw, n, k, nb, list, t, g);      // many: one survivor per lane
+                }
                 if (match) {
-                    const float a = pg_strict_sum(table, sw, n, k, nb, list, t, g);
                     const uint32_t ob = pg_ord(a);
                     const uint32_t gm = __reduce_max_sync(bal, ob);
                     const uint32_t gi = __reduce_min_sync(bal, ob == gm ? g : 0xFFFFFFFFu);
@@ -905,7 +1047,7 @@ static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, unsigned
     PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nreads_b, nblk_y);
     k_classify_q<BLOCK, MINB><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
-                                                          slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->G,
+                                                          slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->d_blockmask,
                                                           md->vmax, d_champ, d_ncand, d_cand, d_guess);
     PG_LAUNCHED(ctx);
     return PG_OK;
@@ -955,7 +1097,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
         (unsigned int)light_max);
     PG_LAUNCHED(ctx);
     k_light<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_order - slot0, ctx->d_boot_pool,
-                                                        ctx->d_boot_off, min_boot, md->G, md->vmax, cb.items,
+                                                        ctx->d_boot_off, min_boot, md->d_blockmask, md->vmax, cb.items,
                                                         cb.counters + 2, cb.item_cap, cb.champ, cb.ncand, cb.cand, cb.counters + 3);
     PG_LAUNCHED(ctx);
     return PG_OK;
@@ -975,7 +1117,7 @@ int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int 
     k_resolve<WARPS><<<(nreads_b + WARPS - 1) / WARPS, 32 * WARPS, smem, ctx->stream>>>(
         md->d_table, d_words, d_off, d_nwords, d_flags, d_order, (int)nreads_b, slot0, nmax, ctx->d_boot_pool,
         ctx->d_boot_off, min_boot, md->G, md->vmax, cb.champ, cb.ncand, cb.cand, md->d_anc, md->depth, d_results,
-        d_boot_winners, (int *)cb.counters, cb.fb_list, md->d_perm, use_heavy ? cb.heavy : NULL,
+        d_boot_winners, (int *)cb.counters, cb.fb_list, md->d_perm, md->ntile64 * 64, use_heavy ? cb.heavy : NULL,
         (int *)cb.counters + 1, cb.hv_list);
     PG_LAUNCHED(ctx);
     return PG_OK;

@@ -66,10 +66,11 @@ struct pg_model {
     // 2^-7 nat, 64 genera per 128-byte row segment
     uint16_t *d_qtable;         // [ntile64][65536][64]
     float   *d_rowmax;          // [65536]
-    int      ntile64;
+    int      ntile64;           // 64-position blocks of the quantised table (>= ceil(G/64): clade-aligned blocks are padded)
     // certified v2: genera are laid out in the quantised table in LINEAGE order (relatives share a
     // 64-genus block), and every block has a per-word minimum used as a lower bound of all its genera
     int32_t  *d_perm;           // [ntile64*64] table position -> genus index (>= G: padding)
+    unsigned long long *d_blockmask;   // [ntile64] bit i: position blk*64+i holds a genus
     uint16_t *d_bmtable;        // [ngroup][65536][32]   min over the 64 genera of block (group*32 + i)
     int      ngroup;            // ceil(ntile64 / 32)
     double   vmax;              // max |table entry| over real genera (fp32 error bound)

@@ -173,14 +173,14 @@ extern "C" void pg_model_free(pg_model *md)
     cudaFree(md->d_m); cudaFree(md->d_table); cudaFree(md->d_nw); cudaFree(md->d_M);
     cudaFree(md->d_N); cudaFree(md->d_logPrior); cudaFree(md->d_Pw); cudaFree(md->d_logLeave);
     cudaFree(md->d_anc); cudaFree(md->d_qtable); cudaFree(md->d_rowmax);
-    cudaFree(md->d_perm); cudaFree(md->d_bmtable);
+    cudaFree(md->d_perm); cudaFree(md->d_bmtable); cudaFree(md->d_blockmask);
     delete md;
 }
 
 extern "C" int pg_model_create(pg_ctx *ctx, int G, pg_model **out) { return model_alloc(ctx, G, out); }
 
 int pg_model_derive_quantised(pg_model *md);   // pg_certified.cu
-int pg_model_set_layout(pg_model *md, const int32_t *perm_host);
+int pg_model_layout_from_lineage(pg_model *md, const int32_t *anc, int depth);
 
 extern "C" int pg_model_commit(pg_model *md)
 {
@@ -287,18 +287,7 @@ extern "C" int pg_model_set_lineage(pg_model *md, const int32_t *anc_host, int d
     // Certified mode lays the genera out in lineage order, so that the relatives of a read's genus
     // share its 64-genus block and every other block is dismissed by its lower bound
     // (pg_certified.cu).  Results do not depend on the layout; ties resolve on the genus index.
-    {
-        const int G = md->G;
-        std::vector<int32_t> perm((size_t)G);
-        for (int g = 0; g < G; g++) perm[(size_t)g] = g;
-        std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) {
-            const int32_t *ra = anc_host + (size_t)a * depth, *rb = anc_host + (size_t)b * depth;
-            for (int d = 0; d < depth; d++)
-                if (ra[d] != rb[d]) return ra[d] < rb[d];
-            return false;
-        });
-        PG_TRY(pg_model_set_layout(md, perm.data()));
-    }
+    PG_TRY(pg_model_layout_from_lineage(md, anc_host, depth));
     if (md->committed) PG_TRY(pg_model_derive_quantised(md));
     return PG_OK;
 }
