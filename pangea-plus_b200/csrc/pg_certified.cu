@@ -268,13 +268,18 @@ __device__ __forceinline__ void pg_epilogue_begin(unsigned mask, bool leader, co
                                                   uint32_t gbase, uint32_t vbits, unsigned long long *champ_slot,
                                                   PgPending &p)
 {
-    uint32_t lkey = 0xFFFFFFFFu;
+    const uint32_t loff = genus0 - gbase;
+    uint32_t k[NV];
 #pragma unroll
-    for (int i = 0; i < NV; i++) {
-        const uint32_t g = genus0 + i;
-        const uint32_t key = ((vbits >> i) & 1u) ? ((sums[i] << 6) | (g - gbase)) : 0xFFFFFFFFu;
-        lkey = min(lkey, key);
+    for (int i = 0; i < NV; i++) k[i] = (sums[i] << 6) + loff + i;
+    if (vbits != (1u << NV) - 1u) {                            // padding positions never compete
+#pragma unroll
+        for (int i = 0; i < NV; i++)
+            if (!((vbits >> i) & 1u)) k[i] = 0xFFFFFFFFu;
     }
+    uint32_t lkey = k[0];
+#pragma unroll
+    for (int i = 1; i < NV; i++) lkey = min(lkey, k[i]);
     p.lmin = lkey >> 6;
     p.bkey = __reduce_min_sync(mask, lkey);
     p.old = 0;
@@ -288,21 +293,27 @@ __device__ __forceinline__ void pg_epilogue_finish(unsigned mask, bool leader, i
                                                    uint32_t margin, const PgPending &p, unsigned int *ncand,
                                                    unsigned long long *cand)
 {
+    // sums stay below 2^26 (7 000 terms x 4 095), so everything but the slot itself is 32-bit arithmetic
     const unsigned long long old = __shfl_sync(mask, p.old, leader_lane);
     const uint32_t bm = p.bkey >> 6, bg = gbase + (p.bkey & 63u);
-    const unsigned long long mine = ((unsigned long long)bm << 32) | bg;
-    const bool took = mine < old;                              // this block holds the new champion
-    const unsigned long long thr = ((took ? mine : old) >> 32) + margin;
-    if ((unsigned long long)p.lmin <= thr) {
+    const uint32_t osum = (uint32_t)(old >> 32), opos = (uint32_t)old;       // empty slot: 0xFFFFFFFF / 0xFFFFFFFF
+    const bool took = bm < osum || (bm == osum && bg < opos);                 // this block holds the new champion
+    const uint32_t thr = (took ? bm : osum) + margin;
+    if (p.lmin <= thr) {
+        // usually only the champion's own lane gets here, and finds nothing but the champion itself
+        uint32_t hit = 0u;
 #pragma unroll
-        for (int i = 0; i < NV; i++) {
-            const uint32_t g = genus0 + i;
-            if (((vbits >> i) & 1u) && (unsigned long long)sums[i] <= thr && !(took && g == bg)) pg_emit(ncand, cand, task, g, sums[i]);
+        for (int i = 0; i < NV; i++) hit |= (sums[i] <= thr ? 1u : 0u) << i;
+        hit &= vbits;
+        if (took && bg - genus0 < (uint32_t)NV) hit &= ~(1u << (bg - genus0));
+        if (hit) {
+#pragma unroll
+            for (int i = 0; i < NV; i++)
+                if ((hit >> i) & 1u) pg_emit(ncand, cand, task, genus0 + i, sums[i]);
         }
     }
     // the displaced champion stays a candidate if it is within the margin of the new one
-    if (leader && took && old != PG_CHAMP_INIT && (old >> 32) <= (unsigned long long)bm + margin)
-        pg_emit(ncand, cand, task, (uint32_t)old, (uint32_t)(old >> 32));
+    if (leader && took && old != PG_CHAMP_INIT && osum <= bm + margin) pg_emit(ncand, cand, task, opos, osum);
 }
 
 // ------------------------------------------------------------------ phase 1
@@ -315,7 +326,7 @@ __device__ __forceinline__ void pg_epilogue_finish(unsigned mask, bool leader, i
 
 // MINB = CTAs/SM the register budget must allow (a 4- or 5-CTA budget for short reads was measured:
 // the spills cost more than the occupancy brings)
-template <int BLOCK, int MINB>
+template <int BLOCK, int MINB, bool PRUNE>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
              const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
@@ -341,12 +352,13 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
     // then stops a replicate as soon as ALL its 64 partial sums exceed champion + margin --
     // deficits are non-negative, so a partial sum is a lower bound of the final one and no
     // genus of the block can be the winner or a near-tie any more.
+    // PRUNE = false (grid of one row): only the guessed block, in full -- the first pass of plan 2.
     int blk = blockIdx.y;
     bool prune_on = false;
     if (guess) {
         const int gs = guess[rc];
         blk = (blockIdx.y == 0) ? gs : (((int)blockIdx.y - 1 < gs) ? (int)blockIdx.y - 1 : (int)blockIdx.y);
-        prune_on = blockIdx.y != 0;
+        prune_on = PRUNE && blockIdx.y != 0;
     }
     const int gbase = blk * 64;
     const unsigned long long bmask = blockmask[blk];           // which of the block's 64 positions hold a genus
@@ -1044,11 +1056,18 @@ static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, unsigned
                     int64_t slot0, int min_boot, unsigned long long *d_champ, unsigned int *d_ncand,
                     unsigned long long *d_cand, const int32_t *d_guess)
 {
-    PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(nreads_b, nblk_y);
-    k_classify_q<BLOCK, MINB><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
-                                                          slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->d_blockmask,
-                                                          md->vmax, d_champ, d_ncand, d_cand, d_guess);
+    if (nblk_y > 1) {
+        PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_classify_q<BLOCK, MINB, true><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
+                                                              slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->d_blockmask,
+                                                              md->vmax, d_champ, d_ncand, d_cand, d_guess);
+    } else {
+        PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_classify_q<BLOCK, MINB, false><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
+                                                              slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->d_blockmask,
+                                                              md->vmax, d_champ, d_ncand, d_cand, d_guess);
+    }
     PG_LAUNCHED(ctx);
     return PG_OK;
 }
@@ -1076,10 +1095,12 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
                                                                   (int)nreads_b, slot0, md->ntile64, d_guess);
         PG_LAUNCHED(ctx);
     }
+    static int qblock = -1;                             // PG_Q_BLOCK=448: experiment switch for the first bucket
+    if (qblock < 0) { const char *e = getenv("PG_Q_BLOCK"); qblock = e ? atoi(e) : 0; }
     int rc;
-    if (bk.block == 192)
+    if (bk.block == 192 && qblock != 448)
         rc = launch_q<192, 3>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
-    else if (bk.block == 448)
+    else if (bk.block == 448 || bk.block == 192)
         rc = launch_q<448, 2>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
     else
         rc = launch_q<832, 1>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
