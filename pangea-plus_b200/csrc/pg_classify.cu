@@ -302,84 +302,106 @@ static cudaEvent_t take_event(pg_ctx *ctx)
     return ev;
 }
 
-// words/nwords/flags already on the device for `count` reads; classify + vote.
-static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off, int64_t count,
-                          const uint16_t *d_words, const int32_t *d_nwords, const uint8_t *d_flags,
-                          const pg_classify_opts *opts, pg_result *d_results, int32_t *d_boot_winners)
-{
-    const int min_boot = opts ? opts->min_boot_words : 0;
-    const int mode = opts ? opts->mode : 0;
-    if (min_boot < 0 || min_boot > 64) return pg_fail(ctx, PG_EINVAL, "min_boot_words out of range");
-    if (mode != 0 && mode != 1) return pg_fail(ctx, PG_EINVAL, "unknown classify mode %d", mode);
-    if (count == 0) return PG_OK;
-    if (count > 0x7fffffffLL) return pg_fail(ctx, PG_ERANGE, "more than 2^31-1 reads in one batch");
-
-    // n per read -> host, bucket the reads
-    PG_TRY(pg_pinned(ctx, (size_t)count * 8));
-    int32_t *h_n = (int32_t *)ctx->h_pin;
-    int32_t *h_order = h_n + count;
-    PG_CUDA(ctx, cudaMemcpyAsync(h_n, d_nwords, (size_t)count * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-
-    std::vector<char> seen(PG_MAX_WORDS + 1, 0);
-    std::vector<int> need;
-    for (int64_t i = 0; i < count; i++) {
-        int n = h_n[i];
-        if (n > PG_MAX_WORDS)
-            return pg_fail(ctx, PG_ERANGE, "read %lld has %d good words; the limit is %d", (long long)i, n, PG_MAX_WORDS);
-        if (!seen[n]) { seen[n] = 1; need.push_back(n); }
-    }
-    PG_TRY(ensure_boot_lists(ctx, need, min_boot));
-
-    const bool certified = (mode == 1) && md->q_ok;
-    ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
-    ctx->st_heavy = ctx->st_items = 0;
-    // certified mode walks the 20 genus blocks of a chunk one after the other (tile-major grid);
-    // the chunk's word ids, champion slots and near-tie lists should stay in the 126 MB L2
-    // across those passes, so the chunk is kept small (2^14 reads: 16 MB + 13 MB + 17 MB worst case; measured best)
-    static int64_t chunk_override = -1;
-    if (chunk_override < 0) { const char *e = getenv("PG_CHUNK_LOG2"); chunk_override = e ? atoi(e) : 0; }
-    const int64_t CHUNK = certified ? ((int64_t)1 << (chunk_override ? chunk_override : 14)) : (1 << 20);
-    const int nkeys = PG_NUM_BOOT + 1;
-    const int64_t cmax = count < CHUNK ? count : CHUNK;
-    PG_TRY(pg_scratch(ctx, &ctx->s_best, (size_t)cmax * nkeys * 8));
-    PG_TRY(pg_scratch(ctx, &ctx->s_order, (size_t)cmax * 4));
-    unsigned long long *d_best = (unsigned long long *)ctx->s_best.p;
-    int32_t *d_order = (int32_t *)ctx->s_order.p;
+// ------------------------------------------------------------------ host orchestration
+//
+// A batch is classified range by range (a range = one chunk of reads).  Nothing in the steady state
+// waits for the device except the 4-byte-per-read word counts the host needs to bucket a range, and
+// those are fetched one range ahead, so the host enqueues range i while the device still works on
+// range i-1.  Fallback lists (heavy reads, overflowing near-tie lists) grow on the device across the
+// whole batch and are dealt with once, in finish().
+struct ClassifyJob {
+    pg_ctx *ctx;
+    const pg_model *md;
+    const int64_t *d_off;
+    int64_t count;
+    const uint16_t *d_words;
+    const int32_t *d_nwords;
+    const uint8_t *d_flags;
+    pg_result *d_results;
+    int32_t *d_boot_winners;
+    int min_boot, mode, cert_version, nkeys;
+    bool certified;
+    int64_t CHUNK, cmax;
+    unsigned long long *d_best;
+    int32_t *d_order;
     PgCertBufs cb;
-    memset(&cb, 0, sizeof cb);
-    static int env_v1 = -1;                             // PG_CERT_V1=1: the all-block kernel for every read (A/B switch)
-    if (env_v1 < 0) { const char *e = getenv("PG_CERT_V1"); env_v1 = (e && atoi(e)) ? 1 : 0; }
-    const int cert_version = (env_v1 || (opts && opts->cert_plan == 1)) ? 1 : 2;
-    if (opts && (opts->cert_plan < 0 || opts->cert_plan > 1)) return pg_fail(ctx, PG_EINVAL, "unknown cert_plan %d", opts->cert_plan);
-    cb.light_max = opts ? opts->light_max : 0;
-    if (certified) {
-        PG_TRY(pg_scratch(ctx, &ctx->s_champ, (size_t)cmax * nkeys * 8));
-        PG_TRY(pg_scratch(ctx, &ctx->s_ncand, (size_t)cmax * 4));
-        PG_TRY(pg_scratch(ctx, &ctx->s_candl, (size_t)cmax * PG_CANDCAP * 8));
-        PG_TRY(pg_scratch(ctx, &ctx->s_fb, (size_t)count * 4 + 16));
-        PG_TRY(pg_scratch(ctx, &ctx->s_guess, (size_t)cmax * 4));
-        cb.item_cap = (unsigned int)(cmax * 64 < 4096 ? 4096 : cmax * 64);
-        PG_TRY(pg_scratch(ctx, &ctx->s_items, (size_t)cb.item_cap * 8));
-        PG_TRY(pg_scratch(ctx, &ctx->s_heavy, (size_t)count * 4 + (size_t)cmax + 64));
-        cb.champ = (unsigned long long *)ctx->s_champ.p;
-        cb.ncand = (unsigned int *)ctx->s_ncand.p;
-        cb.cand = (unsigned long long *)ctx->s_candl.p;
-        cb.counters = (unsigned int *)ctx->s_fb.p;
-        cb.fb_list = (int32_t *)ctx->s_fb.p + 4;
-        cb.guess = (int32_t *)ctx->s_guess.p;
-        cb.items = (unsigned long long *)ctx->s_items.p;
-        cb.hv_list = (int32_t *)ctx->s_heavy.p;
-        cb.heavy = (uint8_t *)((int32_t *)ctx->s_heavy.p + count);
-        PG_CUDA(ctx, cudaMemsetAsync(cb.counters, 0, 16, ctx->stream));
-    }
-    const int wpb = 8;
-
-    // A "slot" is a position in the order array of the chunk in flight; the per-read scratch
-    // (champion slots, near-tie lists, strict keys, guesses) is indexed by slot.
+    int32_t *h_n, *h_order;
+    std::vector<char> seen;
+    std::vector<int32_t> redone;                 // reads whose records were rewritten by finish()
     int64_t bcount[16], bstart[16], bmaxn[16];
+
+    int begin(pg_ctx *c, const pg_model *m, const int64_t *off, int64_t cnt, const uint16_t *words, const int32_t *nwords,
+              const uint8_t *flags, const pg_classify_opts *opts, pg_result *results, int32_t *boot_winners)
+    {
+        ctx = c; md = m; d_off = off; count = cnt; d_words = words; d_nwords = nwords; d_flags = flags;
+        d_results = results; d_boot_winners = boot_winners;
+        min_boot = opts ? opts->min_boot_words : 0;
+        mode = opts ? opts->mode : 0;
+        nkeys = PG_NUM_BOOT + 1;
+        if (min_boot < 0 || min_boot > 64) return pg_fail(ctx, PG_EINVAL, "min_boot_words out of range");
+        if (mode != 0 && mode != 1) return pg_fail(ctx, PG_EINVAL, "unknown classify mode %d", mode);
+        if (opts && (opts->cert_plan < 0 || opts->cert_plan > 1)) return pg_fail(ctx, PG_EINVAL, "unknown cert_plan %d", opts->cert_plan);
+        if (count > 0x7fffffffLL) return pg_fail(ctx, PG_ERANGE, "more than 2^31-1 reads in one batch");
+        certified = (mode == 1) && md->q_ok;
+        static int env_v1 = -1;                         // PG_CERT_V1=1: the all-block kernel for every read (A/B switch)
+        if (env_v1 < 0) { const char *e = getenv("PG_CERT_V1"); env_v1 = (e && atoi(e)) ? 1 : 0; }
+        cert_version = (env_v1 || (opts && opts->cert_plan == 1)) ? 1 : 2;
+        ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
+        ctx->st_heavy = ctx->st_items = 0;
+        // Chunk of reads per pass.  Plan 1 walks every genus block of a chunk (tile-major grid) and wants the
+        // chunk's word ids, champion slots and near-tie lists L2-resident across those passes (2^14 measured
+        // best); plan 2 touches a read's data once per kernel and prefers fewer, larger launches (2^16).
+        static int64_t chunk_override = -1;
+        if (chunk_override < 0) { const char *e = getenv("PG_CHUNK_LOG2"); chunk_override = e ? atoi(e) : 0; }
+        CHUNK = !certified ? ((int64_t)1 << 20) : ((int64_t)1 << (chunk_override ? chunk_override : (cert_version == 1 ? 14 : 16)));
+        cmax = count < CHUNK ? count : CHUNK;
+        if (cmax < 1) cmax = 1;
+        PG_TRY(pg_pinned(ctx, (size_t)count * 8 + 64));
+        h_n = (int32_t *)ctx->h_pin;
+        h_order = h_n + count;
+        seen.assign(PG_MAX_WORDS + 1, 0);
+        redone.clear();
+        PG_TRY(pg_scratch(ctx, &ctx->s_best, (size_t)cmax * nkeys * 8));
+        PG_TRY(pg_scratch(ctx, &ctx->s_order, (size_t)cmax * 4));
+        d_best = (unsigned long long *)ctx->s_best.p;
+        d_order = (int32_t *)ctx->s_order.p;
+        memset(&cb, 0, sizeof cb);
+        cb.light_max = opts ? opts->light_max : 0;
+        if (certified) {
+            PG_TRY(pg_scratch(ctx, &ctx->s_champ, (size_t)cmax * nkeys * 8));
+            PG_TRY(pg_scratch(ctx, &ctx->s_ncand, (size_t)cmax * 4));
+            PG_TRY(pg_scratch(ctx, &ctx->s_candl, (size_t)cmax * PG_CANDCAP * 8));
+            PG_TRY(pg_scratch(ctx, &ctx->s_fb, (size_t)count * 4 + 16));
+            PG_TRY(pg_scratch(ctx, &ctx->s_guess, (size_t)cmax * 4));
+            cb.item_cap = (unsigned int)(cmax * 64 < 4096 ? 4096 : cmax * 64);
+            PG_TRY(pg_scratch(ctx, &ctx->s_items, (size_t)cb.item_cap * 8));
+            PG_TRY(pg_scratch(ctx, &ctx->s_heavy, (size_t)count * 4 + (size_t)cmax + 64));
+            cb.champ = (unsigned long long *)ctx->s_champ.p;
+            cb.ncand = (unsigned int *)ctx->s_ncand.p;
+            cb.cand = (unsigned long long *)ctx->s_candl.p;
+            cb.counters = (unsigned int *)ctx->s_fb.p;
+            cb.fb_list = (int32_t *)ctx->s_fb.p + 4;
+            cb.guess = (int32_t *)ctx->s_guess.p;
+            cb.items = (unsigned long long *)ctx->s_items.p;
+            cb.hv_list = (int32_t *)ctx->s_heavy.p;
+            cb.heavy = (uint8_t *)((int32_t *)ctx->s_heavy.p + count);
+            PG_CUDA(ctx, cudaMemsetAsync(cb.counters, 0, 16, ctx->stream));
+        }
+        return PG_OK;
+    }
+
+    // word counts of reads [r0, r1) to the host, asynchronously; *ev fires when they have landed
+    int fetch_counts(int64_t r0, int64_t r1, cudaEvent_t *ev)
+    {
+        PG_CUDA(ctx, cudaMemcpyAsync(h_n + r0, d_nwords + r0, (size_t)(r1 - r0) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        *ev = take_event(ctx);
+        PG_CUDA(ctx, cudaEventRecord(*ev, ctx->stream));
+        return PG_OK;
+    }
+
     // stable counting sort of a list of reads by bucket -> h_dst, bucket extents in bcount/bstart/bmaxn
-    auto bucket_sort = [&](const int32_t *src, int64_t base, int64_t cn, int32_t *h_dst) {
+    void bucket_sort(const int32_t *src, int64_t base, int64_t cn, int32_t *h_dst)
+    {
         int64_t fill[16];
         for (int b = 0; b < 16; b++) bcount[b] = bmaxn[b] = 0;
         for (int64_t i = 0; i < cn; i++) {
@@ -397,9 +419,12 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
             while (kBuckets[b].nmax < n) b++;
             h_dst[fill[b]++] = r;
         }
-    };
+    }
+
     // one bucket of reads through the strict kernels (also the certified path's last resort)
-    auto run_strict = [&](const Bucket &bk, const int32_t *ord, int64_t slot0, unsigned cnt, int nmax, bool timed) -> int {
+    int run_strict(const Bucket &bk, const int32_t *ord, int64_t slot0, unsigned cnt, int nmax, bool timed)
+    {
+        const int wpb = 8;
         cudaEvent_t e0 = NULL, e1 = NULL;
         if (timed) {
             e0 = take_event(ctx); e1 = take_event(ctx);
@@ -428,10 +453,13 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
                                                                   md->depth, d_results, d_boot_winners);
         PG_LAUNCHED(ctx);
         return PG_OK;
-    };
-    // one pass over a set of reads (a chunk of the batch, or a list): plan 2 / plan 1 / strict.
-    // Nothing here waits for the device: fallback lists grow on the device and are read once, below.
-    auto run_pass = [&](const int32_t *h_list, int64_t cn, int plan, bool timed) -> int {
+    }
+
+    // one pass over a set of reads (a chunk of the batch, or a list): plan 2 / plan 1 / strict (plan 0).
+    // A "slot" is a position in the order array of the pass; the per-read scratch (champion slots,
+    // near-tie lists, strict keys, guesses) is indexed by slot.
+    int run_pass(const int32_t *h_list, int64_t cn, int plan, bool timed)
+    {
         PG_CUDA(ctx, cudaMemcpyAsync(d_order, h_list, (size_t)cn * 4, cudaMemcpyHostToDevice, ctx->stream));
         bool need_best = plan == 0 || !certified;           // strict keys: also for buckets the certified kernels do not take
         for (int b = 0; b < kNumBuckets; b++)
@@ -468,18 +496,39 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
             }
         }
         return PG_OK;
-    };
-
-    for (int64_t c0 = 0; c0 < count; c0 += CHUNK) {
-        const int64_t cn = count - c0 < CHUNK ? count - c0 : CHUNK;
-        bucket_sort(NULL, c0, cn, h_order + c0);
-        PG_TRY(run_pass(h_order + c0, cn, certified ? cert_version : 0, true));
     }
 
-    if (certified) {
-        // Deferred work, read once for the whole batch:
-        //   heavy reads (plan 2 left too many (task, block) pairs open) -> plan 1, the all-block kernel;
-        //   reads whose near-tie list overflowed (in either plan)        -> the strict kernels.
+    // enqueue the classification of reads [r0, r1); their word counts must have landed (fetch_counts)
+    int range(int64_t r0, int64_t r1, cudaEvent_t counts_ready)
+    {
+        PG_CUDA(ctx, cudaEventSynchronize(counts_ready));
+        ctx->ev_free.push_back(counts_ready);
+        std::vector<int> need;
+        for (int64_t i = r0; i < r1; i++) {
+            const int n = h_n[i];
+            if (n > PG_MAX_WORDS)
+                return pg_fail(ctx, PG_ERANGE, "read %lld has %d good words; the limit is %d", (long long)i, n, PG_MAX_WORDS);
+            if (!seen[n]) { seen[n] = 1; need.push_back(n); }
+        }
+        if (!need.empty()) PG_TRY(ensure_boot_lists(ctx, need, min_boot));
+        for (int64_t c0 = r0; c0 < r1; c0 += CHUNK) {
+            const int64_t cn = r1 - c0 < CHUNK ? r1 - c0 : CHUNK;
+            bucket_sort(NULL, c0, cn, h_order + c0);
+            PG_TRY(run_pass(h_order + c0, cn, certified ? cert_version : 0, true));
+        }
+        return PG_OK;
+    }
+
+    // Deferred work, read once for the whole batch:
+    //   heavy reads (plan 2 left too many (task, block) pairs open) -> plan 1, the all-block kernel;
+    //   reads whose near-tie list overflowed (in either plan)        -> the strict kernels.
+    // Leaves the stream synchronised; `redone` lists the reads whose records were rewritten here.
+    int finish()
+    {
+        if (!certified) {
+            PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            return PG_OK;
+        }
         unsigned int cnts[4] = {0, 0, 0, 0};
         PG_CUDA(ctx, cudaMemcpyAsync(cnts, cb.counters, 16, cudaMemcpyDeviceToHost, ctx->stream));
         PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -492,8 +541,10 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
             PG_CUDA(ctx, cudaMemcpyAsync(lst.data(), cb.hv_list, lst.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
             PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             std::sort(lst.begin(), lst.end());                   // device order is arbitrary; keep runs reproducible
-            for (size_t p0 = 0; p0 < lst.size(); p0 += (size_t)CHUNK) {
-                const int64_t cn = (int64_t)(lst.size() - p0 < (size_t)CHUNK ? lst.size() - p0 : (size_t)CHUNK);
+            redone.insert(redone.end(), lst.begin(), lst.end());
+            const int64_t step = cert_version == 1 ? CHUNK : (int64_t)1 << 14;
+            for (size_t p0 = 0; p0 < lst.size(); p0 += (size_t)step) {
+                const int64_t cn = (int64_t)(lst.size() - p0 < (size_t)step ? lst.size() - p0 : (size_t)step);
                 bucket_sort(lst.data() + p0, 0, cn, sorted.data() + p0);
                 PG_TRY(run_pass(sorted.data() + p0, cn, 1, false));
             }
@@ -507,6 +558,7 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
             PG_CUDA(ctx, cudaMemcpyAsync(lst.data(), cb.fb_list, lst.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
             PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             std::sort(lst.begin(), lst.end());
+            redone.insert(redone.end(), lst.begin(), lst.end());
             for (size_t p0 = 0; p0 < lst.size(); p0 += (size_t)CHUNK) {
                 const int64_t cn = (int64_t)(lst.size() - p0 < (size_t)CHUNK ? lst.size() - p0 : (size_t)CHUNK);
                 bucket_sort(lst.data() + p0, 0, cn, sorted.data() + p0);
@@ -514,10 +566,20 @@ static int classify_words(pg_ctx *ctx, const pg_model *md, const int64_t *d_off,
             }
             PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // `sorted` is a stack vector
         }
+        return PG_OK;
     }
-    return PG_OK;
-}
 
+    // ranges of the batch: a short first one (its preparation cannot overlap anything), then chunks
+    int64_t next_range(int64_t r0) const
+    {
+        const int64_t first = CHUNK < 16384 ? CHUNK : 16384;
+        const int64_t r1 = r0 == 0 ? first : r0 + CHUNK;
+        return r1 < count ? r1 : count;
+    }
+};
+
+// packed reads on the device -> records on the device.  Word extraction of range i+1 is queued ahead of
+// the classification of range i.
 static int classify_planes(pg_ctx *ctx, const pg_model *md, const uint32_t *d_planes, const int64_t *d_off,
                            int64_t count, int64_t total_bytes, const pg_classify_opts *opts,
                            pg_result *d_results, int32_t *d_boot_winners)
@@ -528,8 +590,23 @@ static int classify_planes(pg_ctx *ctx, const pg_model *md, const uint32_t *d_pl
     uint16_t *d_words = (uint16_t *)ctx->s_words.p;
     int32_t *d_nwords = (int32_t *)ctx->s_nwords.p;
     uint8_t *d_flags = (uint8_t *)ctx->s_flags.p;
-    PG_TRY(pg_extract_launch(ctx, md, d_planes, d_off, count, d_words, d_nwords, d_flags));
-    return classify_words(ctx, md, d_off, count, d_words, d_nwords, d_flags, opts, d_results, d_boot_winners);
+    if (count == 0) return PG_OK;
+    ClassifyJob job;
+    PG_TRY(job.begin(ctx, md, d_off, count, d_words, d_nwords, d_flags, opts, d_results, d_boot_winners));
+    auto prepare = [&](int64_t r0, int64_t r1, cudaEvent_t *ev) -> int {
+        PG_TRY(pg_extract_launch(ctx, md, d_planes + 3 * r0, d_off + r0, r1 - r0, d_words, d_nwords + r0, d_flags + 2 * r0));
+        return job.fetch_counts(r0, r1, ev);
+    };
+    cudaEvent_t ev_cur = NULL, ev_next = NULL;
+    int64_t r0 = 0, r1 = job.next_range(0);
+    PG_TRY(prepare(r0, r1, &ev_cur));
+    while (r0 < count) {
+        const int64_t r2 = job.next_range(r1);
+        if (r1 < count) PG_TRY(prepare(r1, r2, &ev_next));
+        PG_TRY(job.range(r0, r1, ev_cur));
+        r0 = r1; r1 = r2; ev_cur = ev_next; ev_next = NULL;
+    }
+    return job.finish();
 }
 
 extern "C" int pg_classify_packed(pg_ctx *ctx, const pg_model *md, const pg_reads *reads,
@@ -542,6 +619,18 @@ extern "C" int pg_classify_packed(pg_ctx *ctx, const pg_model *md, const pg_read
                            results_dev, boot_winners_dev);
 }
 
+// records of the listed reads, gathered for one small copy to the host
+static __global__ void k_gather_words(const uint32_t *__restrict__ src, int words_per_rec, const int32_t *__restrict__ list,
+                                      int cnt, uint32_t *__restrict__ out)
+{
+    const int i = blockIdx.x;
+    if (i >= cnt) return;
+    const uint32_t *s = src + (size_t)list[i] * words_per_rec;
+    for (int w = threadIdx.x; w < words_per_rec; w += blockDim.x) out[(size_t)i * words_per_rec + w] = s[w];
+}
+
+// Host ASCII in, host records out.  Three things overlap: the upload of range i+1 (copy stream), the
+// kernels of range i (compute stream) and the download of the records of range i-1 (copy stream).
 extern "C" int pg_classify(pg_ctx *ctx, const pg_model *md, const pg_seqbatch *reads, const pg_classify_opts *opts,
                            pg_result *results_host, int32_t *boot_winners_host)
 {
@@ -552,25 +641,96 @@ extern "C" int pg_classify(pg_ctx *ctx, const pg_model *md, const pg_seqbatch *r
     const int64_t n = reads->count;
     if (n == 0) return PG_OK;
     const int64_t total = reads->off[n];
-    // upload ASCII + offsets, pack on the device
     PG_TRY(pg_scratch(ctx, &ctx->s_bytes, (size_t)total + 64));
     PG_TRY(pg_scratch(ctx, &ctx->s_off, (size_t)(n + 1) * 8));
     const size_t nch = (size_t)(total >> 5) + n + 2;
     PG_TRY(pg_scratch(ctx, &ctx->s_cand, nch * 12));
     PG_TRY(pg_scratch(ctx, &ctx->s_results, (size_t)n * sizeof(pg_result) + (boot_winners_host ? (size_t)n * 400 : 0)));
+    PG_TRY(pg_scratch(ctx, &ctx->s_words, (size_t)total * 2 + 64));
+    PG_TRY(pg_scratch(ctx, &ctx->s_nwords, (size_t)n * 4 + 64));
+    PG_TRY(pg_scratch(ctx, &ctx->s_flags, (size_t)n * 2 + 64));
     char *d_bytes = (char *)ctx->s_bytes.p;
     int64_t *d_off = (int64_t *)ctx->s_off.p;
     uint32_t *d_planes = (uint32_t *)ctx->s_cand.p;
     pg_result *d_res = (pg_result *)ctx->s_results.p;
     int32_t *d_bw = boot_winners_host ? (int32_t *)(d_res + n) : NULL;
-    PG_CUDA(ctx, cudaMemcpyAsync(d_bytes, reads->bytes, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
-    PG_CUDA(ctx, cudaMemcpyAsync(d_off, reads->off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    PG_TRY(pg_pack_launch(ctx, d_bytes, d_off, n, d_planes));
-    PG_TRY(classify_planes(ctx, md, d_planes, d_off, n, total, opts, d_res, d_bw));
-    PG_CUDA(ctx, cudaMemcpyAsync(results_host, d_res, (size_t)n * sizeof(pg_result), cudaMemcpyDeviceToHost, ctx->stream));
-    if (d_bw)
-        PG_CUDA(ctx, cudaMemcpyAsync(boot_winners_host, d_bw, (size_t)n * 400, cudaMemcpyDeviceToHost, ctx->stream));
-    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint16_t *d_words = (uint16_t *)ctx->s_words.p;
+    int32_t *d_nwords = (int32_t *)ctx->s_nwords.p;
+    uint8_t *d_flags = (uint8_t *)ctx->s_flags.p;
+    // two copy streams: a download waits for its range's kernels and must not hold back the next upload
+    if (!ctx->copy_stream) PG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->down_stream) PG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = ctx->copy_stream, ds = ctx->down_stream;
+
+    ClassifyJob job;
+    PG_TRY(job.begin(ctx, md, d_off, n, d_words, d_nwords, d_flags, opts, d_res, d_bw));
+    // everything queued so far on the compute stream (scratch growth, counters) precedes the first upload
+    {
+        cudaEvent_t e = take_event(ctx);
+        PG_CUDA(ctx, cudaEventRecord(e, ctx->stream));
+        PG_CUDA(ctx, cudaStreamWaitEvent(cs, e, 0));
+        ctx->ev_free.push_back(e);
+    }
+    auto prepare = [&](int64_t r0, int64_t r1, cudaEvent_t *ev) -> int {
+        // upload on the copy stream, then pack + extract + word counts on the compute stream
+        const int64_t b0 = reads->off[r0], b1 = reads->off[r1];
+        PG_CUDA(ctx, cudaMemcpyAsync(d_bytes + b0, reads->bytes + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
+        PG_CUDA(ctx, cudaMemcpyAsync(d_off + r0, reads->off + r0, (size_t)(r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, cs));
+        cudaEvent_t up = take_event(ctx);
+        PG_CUDA(ctx, cudaEventRecord(up, cs));
+        PG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
+        ctx->ev_free.push_back(up);
+        PG_TRY(pg_pack_launch(ctx, d_bytes, d_off + r0, r1 - r0, d_planes + 3 * r0));
+        PG_TRY(pg_extract_launch(ctx, md, d_planes + 3 * r0, d_off + r0, r1 - r0, d_words, d_nwords + r0, d_flags + 2 * r0));
+        return job.fetch_counts(r0, r1, ev);
+    };
+    auto download = [&](int64_t r0, int64_t r1) -> int {
+        cudaEvent_t done = take_event(ctx);
+        PG_CUDA(ctx, cudaEventRecord(done, ctx->stream));
+        PG_CUDA(ctx, cudaStreamWaitEvent(ds, done, 0));
+        ctx->ev_free.push_back(done);
+        PG_CUDA(ctx, cudaMemcpyAsync(results_host + r0, d_res + r0, (size_t)(r1 - r0) * sizeof(pg_result), cudaMemcpyDeviceToHost, ds));
+        if (d_bw)
+            PG_CUDA(ctx, cudaMemcpyAsync(boot_winners_host + r0 * PG_NUM_BOOT, d_bw + r0 * PG_NUM_BOOT, (size_t)(r1 - r0) * 400,
+                                         cudaMemcpyDeviceToHost, ds));
+        return PG_OK;
+    };
+    cudaEvent_t ev_cur = NULL, ev_next = NULL;
+    int64_t r0 = 0, r1 = job.next_range(0);
+    PG_TRY(prepare(r0, r1, &ev_cur));
+    while (r0 < n) {
+        const int64_t r2 = job.next_range(r1);
+        if (r1 < n) PG_TRY(prepare(r1, r2, &ev_next));
+        PG_TRY(job.range(r0, r1, ev_cur));
+        PG_TRY(download(r0, r1));
+        r0 = r1; r1 = r2; ev_cur = ev_next; ev_next = NULL;
+    }
+    PG_TRY(job.finish());
+    PG_CUDA(ctx, cudaStreamSynchronize(ds));
+    if (!job.redone.empty()) {
+        // records rewritten by the fallback passes: gather them, one small copy, scatter on the host
+        const int cnt = (int)job.redone.size();
+        const int wpr = (int)(sizeof(pg_result) / 4);
+        PG_TRY(pg_scratch(ctx, &ctx->s_boot, (size_t)cnt * (4 + sizeof(pg_result) + (d_bw ? 400 : 0))));
+        int32_t *d_list = (int32_t *)ctx->s_boot.p;
+        uint32_t *d_rec = (uint32_t *)(d_list + cnt);
+        uint32_t *d_bwc = d_rec + (size_t)cnt * wpr;
+        std::vector<uint32_t> rec((size_t)cnt * wpr), bwc(d_bw ? (size_t)cnt * PG_NUM_BOOT : 0);
+        PG_CUDA(ctx, cudaMemcpyAsync(d_list, job.redone.data(), (size_t)cnt * 4, cudaMemcpyHostToDevice, ctx->stream));
+        k_gather_words<<<cnt, 32, 0, ctx->stream>>>((const uint32_t *)d_res, wpr, d_list, cnt, d_rec);
+        PG_LAUNCHED(ctx);
+        PG_CUDA(ctx, cudaMemcpyAsync(rec.data(), d_rec, rec.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (d_bw) {
+            k_gather_words<<<cnt, 128, 0, ctx->stream>>>((const uint32_t *)d_bw, PG_NUM_BOOT, d_list, cnt, d_bwc);
+            PG_LAUNCHED(ctx);
+            PG_CUDA(ctx, cudaMemcpyAsync(bwc.data(), d_bwc, bwc.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < cnt; i++) {
+            memcpy(results_host + job.redone[(size_t)i], rec.data() + (size_t)i * wpr, sizeof(pg_result));
+            if (d_bw) memcpy(boot_winners_host + (size_t)job.redone[(size_t)i] * PG_NUM_BOOT, bwc.data() + (size_t)i * PG_NUM_BOOT, 400);
+        }
+    }
     return PG_OK;
 }
 

@@ -63,6 +63,7 @@ extern "C" pg_ctx *pg_init(int device)
         return NULL;
     }
     ctx->stream = ctx->own_stream;
+    ctx->copy_stream = ctx->down_stream = NULL;
     return ctx;
 }
 
@@ -79,6 +80,8 @@ extern "C" void pg_shutdown(pg_ctx *ctx)
     for (auto &p : ctx->ev_pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto &ev : ctx->ev_free) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->down_stream) cudaStreamDestroy(ctx->down_stream);
     delete ctx;
 }
 

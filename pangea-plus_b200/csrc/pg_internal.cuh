@@ -18,6 +18,7 @@ struct pg_ctx {
     int          sm_count;
     cudaStream_t stream;
     cudaStream_t own_stream;
+    cudaStream_t copy_stream, down_stream;    // uploads / downloads of pg_classify(), created on first use
     mutable char err[512];
     int64_t      launches;
 
