@@ -678,7 +678,7 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
             // The four units of a warp walk in lockstep (a settled unit just stops loading): partial sums only
             // grow, so once every block of a unit is above the threshold its task is settled.
             for (; b + 4 <= nb; b += 4) {           // 16 rows x 4095 < 2^16: one spill per four batches
-                if (open) {
+                if (open) {                         // (a check every 8 draws was measured: no gain)
                     const uint4 q0 = __ldg(lp + (b + 0) * 4), q1 = __ldg(lp + (b + 1) * 4);
                     const uint4 q2 = __ldg(lp + (b + 2) * 4), q3 = __ldg(lp + (b + 3) * 4);
                     PG_BADD(q0.x >> 1) PG_BADD(q0.y >> 1) PG_BADD(q0.z >> 1) PG_BADD(q0.w >> 1)

@@ -116,21 +116,26 @@ k_extract(const uint32_t *__restrict__ planes, const int64_t *__restrict__ off, 
     // ---- A3: fwd = sum logPrior[w_j], rev = sum logPrior[rc(w_j)], fp32, word order.
     // Every lane carries the same two running sums; values are fetched 32 at a
     // time and fed through shuffles so the adds stay in sequence order.
-    float fwd = 0.0f, rev = 0.0f;
-    for (int j0 = 0; j0 < n; j0 += 32) {
-        int j = j0 + lane;
-        float pf = 0.0f, pr = 0.0f;
+    // Lanes 0-15 carry the forward chain, lanes 16-31 the reverse-complement chain: 16 words per round,
+    // one shuffle + one add per word for both sums.
+    float acc = 0.0f;
+    const int half = lane & 16, hl = lane & 15;
+    for (int j0 = 0; j0 < n; j0 += 16) {
+        const int j = j0 + hl;
+        float p = 0.0f;
         if (j < n) {
-            uint32_t wj = w[j];
-            pf = __ldg(logPrior + wj);
-            pr = __ldg(logPrior + pg_revcomp_word(wj));
+            const uint32_t wj = w[j];
+            p = __ldg(logPrior + (half ? pg_revcomp_word(wj) : wj));
         }
-        int cnt = n - j0 < 32 ? n - j0 : 32;
-        for (int t = 0; t < cnt; t++) {
-            fwd = __fadd_rn(fwd, __shfl_sync(0xffffffffu, pf, t));
-            rev = __fadd_rn(rev, __shfl_sync(0xffffffffu, pr, t));
+        const int cnt = n - j0 < 16 ? n - j0 : 16;
+        if (cnt == 16) {
+#pragma unroll
+            for (int t = 0; t < 16; t++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, p, half + t));
+        } else {
+            for (int t = 0; t < cnt; t++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, p, half + t));
         }
     }
+    const float fwd = __shfl_sync(0xffffffffu, acc, 0), rev = __shfl_sync(0xffffffffu, acc, 16);
     const bool reversed = rev > fwd;
     if (reversed) {
         // word list of the reverse-complemented read = reversed list of rc words
