@@ -398,9 +398,12 @@ class Context:
     # ---- Stage C
     def consensus(self, hit_off, lineages, pidents, rdps, first_is_fresh=True):
         """lineages/pidents: list[bytes] per hit; rdps: list[bytes] per read (text after the 5 TABs)."""
-        lb, lo = pack_sequences(lineages)
-        pb, po = pack_sequences(pidents)
-        rb, ro = pack_sequences(rdps)
+        return self.consensus_packed(hit_off, pack_sequences(lineages), pack_sequences(pidents), pack_sequences(rdps),
+                                     first_is_fresh)
+
+    def consensus_packed(self, hit_off, lineages, pidents, rdps, first_is_fresh=True):
+        """the C ABI call itself: every argument already a (bytes uint8, offsets int64) pair of host arrays."""
+        (lb, lo), (pb, po), (rb, ro) = lineages, pidents, rdps
         hit_off = np.ascontiguousarray(hit_off, np.int64)
         n = len(hit_off) - 1
         inp = _ConsensusIn(n, hit_off.ctypes.data, lb.ctypes.data, lo.ctypes.data, pb.ctypes.data, po.ctypes.data,
@@ -429,21 +432,27 @@ class Tax:
         self.ctx._chk(self.ctx.lib.pg_tax_leaf(self.ctx.h, self.h, gi.ctypes.data, len(gi), out.ctypes.data))
         return out
 
-    def lineage(self, gi) -> list[bytes]:
+    def lineage_raw(self, gi, buf=None, off=None):
+        """the C ABI call itself: lineage strings of all hits back to back in `buf`, hit i at off[i]..off[i+1]."""
         gi = np.ascontiguousarray(gi, np.int32)
         n = len(gi)
-        off = np.zeros(n + 1, np.int64)
-        cap = max(4096, 160 * n)
+        if off is None:
+            off = np.zeros(n + 1, np.int64)
+        if buf is None:
+            buf = np.zeros(max(4096, 160 * n), np.uint8)
         while True:
-            buf = np.zeros(cap, np.uint8)
-            rc = self.ctx.lib.pg_tax_lineage(self.ctx.h, self.h, gi.ctypes.data, n, buf.ctypes.data, cap, off.ctypes.data)
-            if rc == -6 and off[n] > cap:
-                cap = int(off[n]) + 64
+            rc = self.ctx.lib.pg_tax_lineage(self.ctx.h, self.h, gi.ctypes.data, n, buf.ctypes.data, buf.size, off.ctypes.data)
+            if rc == -6 and off[n] > buf.size:
+                buf = np.zeros(int(off[n]) + 64, np.uint8)
                 continue
             self.ctx._chk(rc)
             break
+        return buf, off
+
+    def lineage(self, gi) -> list[bytes]:
+        buf, off = self.lineage_raw(gi)
         raw = buf.tobytes()
-        return [raw[off[i]:off[i + 1]] for i in range(n)]
+        return [raw[off[i]:off[i + 1]] for i in range(len(off) - 1)]
 
     def free(self) -> None:
         if self.h:
