@@ -675,12 +675,20 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
             uint32_t s[4] = {0u, 0u, 0u, 0u}, cx = 0u, cy = 0u;
             int b = 0;
             bool open = true;                       // some block of this unit may still be within the threshold
-            // The four units of a warp walk in lockstep (a settled unit just stops loading): partial sums only
-            // grow, so once every block of a unit is above the threshold its task is settled.
-            for (; b + 4 <= nb; b += 4) {           // 16 rows x 4095 < 2^16: one spill per four batches
-                if (open) {                         // (a check every 8 draws was measured: no gain)
-                    const uint4 q0 = __ldg(lp + (b + 0) * 4), q1 = __ldg(lp + (b + 1) * 4);
-                    const uint4 q2 = __ldg(lp + (b + 2) * 4), q3 = __ldg(lp + (b + 3) * 4);
+            bool lane_open = true;                  // ... some block of this lane
+            // The four units of a warp walk in lockstep.  Partial sums only grow, so a lane whose four blocks are
+            // all above the threshold stops loading (its frozen sums stay above it: fewer bytes per row fetch,
+            // fewer shared-memory wavefronts), and once every lane of a unit has stopped its task is settled.
+            // The list entries run one trip (four batches) ahead of the loads that need them; batches past
+            // the task's end point at the zero row.
+            const uint32_t zoff = (uint32_t)n * PG_ROW_PITCH;
+            const uint4 zq = make_uint4(zoff, zoff, zoff, zoff);
+#define PG_LQ(bb) ((bb) < nb ? __ldg(lp + (bb) * 4) : zq)
+            uint4 n0 = PG_LQ(0), n1 = PG_LQ(1), n2 = PG_LQ(2), n3 = PG_LQ(3);
+            for (; b < nb; b += 4) {                // 16 rows x 4095 < 2^16: one spill per four batches
+                const uint4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
+                if (lane_open && b + 4 < nb) { n0 = PG_LQ(b + 4); n1 = PG_LQ(b + 5); n2 = PG_LQ(b + 6); n3 = PG_LQ(b + 7); }
+                if (lane_open) {                    // (a check every 8 draws was measured: no gain)
                     PG_BADD(q0.x >> 1) PG_BADD(q0.y >> 1) PG_BADD(q0.z >> 1) PG_BADD(q0.w >> 1)
                     PG_BADD(q1.x >> 1) PG_BADD(q1.y >> 1) PG_BADD(q1.z >> 1) PG_BADD(q1.w >> 1)
                     PG_BADD(q2.x >> 1) PG_BADD(q2.y >> 1) PG_BADD(q2.z >> 1) PG_BADD(q2.w >> 1)
@@ -690,20 +698,16 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
                 bool mine = false;
 #pragma unroll
                 for (int i = 0; i < 4; i++) mine |= ok[i] && (unsigned long long)s[i] <= thr;
-                const unsigned vote = __ballot_sync(0xffffffffu, mine && open);
+                lane_open = mine && lane_open;
+                const unsigned vote = __ballot_sync(0xffffffffu, lane_open);
                 open = (vote & qmask) != 0u;
                 if (vote == 0u) break;
             }
-            if (open) {
-                for (; b < nb; b++) {
-                    const uint4 q0 = __ldg(lp + b * 4);
-                    PG_BADD(q0.x >> 1) PG_BADD(q0.y >> 1) PG_BADD(q0.z >> 1) PG_BADD(q0.w >> 1)
-                }
-            }
+#undef PG_LQ
             PG_BSPILL()
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                if (open && ok[i] && (unsigned long long)s[i] <= thr) PG_SURVIVE(1 + t, b0 + i)
+                if (lane_open && ok[i] && (unsigned long long)s[i] <= thr) PG_SURVIVE(1 + t, b0 + i)
         }
     }
     __syncthreads();
