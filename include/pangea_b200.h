@@ -271,6 +271,29 @@ typedef struct {
 int pg_trim_join(pg_ctx *ctx, const char *a_host, int64_t a_len, const char *b_host, int64_t b_len, int paired,
                  const pg_trim_opts *opts, char *out_host, int64_t out_cap, int64_t *out_len, pg_reads **reads_out);
 
+/* ------------------------------------------------------------------ Megaclust (widening: SURVEY.md 8(f) next-2)
+ * Replaces: `perl megaclust2.pl -i <consensus or BLAST tabular> -o <out> [-s sim] [-e evalue] [-b bitscore] [-c x]`
+ * (README.md:176; Megaclust/megaclust2.pl:80-153): lines not starting with '#' are split on the script's
+ * delimiter pattern, kept when pident >= sim, evalue <= eval and bitscore >= bits (Perl's numeric reading of
+ * the text), and counted per subject (field 2): once per distinct (subject, query) pair, or every line when
+ * count_every_hit is set.
+ */
+typedef struct {
+    double  sim_threshold;      /* -s, the script's default is 95   */
+    double  eval_threshold;     /* -e, default 1e-20                */
+    double  bitscore_threshold; /* -b, default 200                  */
+    int32_t count_every_hit;    /* -c <true value>                  */
+    int32_t reserved[5];
+} pg_megaclust_opts;
+
+/* text_host: the whole input file.  OTUs come back in order of first appearance (the script prints them in
+ * Perl's hash order, i.e. unspecified): subject i is text_host[otu_off[i] .. otu_off[i]+otu_len[i]) and was hit
+ * otu_count[i] times.  PG_ERANGE (count in *n_otus) when cap is too small.  lines_examined / lines_beyond are
+ * the two numbers of the script's run summary. */
+int pg_megaclust(pg_ctx *ctx, const char *text_host, int64_t len, const pg_megaclust_opts *opts, int64_t cap,
+                 int64_t *n_otus, int64_t *otu_off, int32_t *otu_len, int64_t *otu_count, int64_t *lines_examined,
+                 int64_t *lines_beyond);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,7 +219,7 @@ __global__ void k_trim_fastq(TextLines A, int64_t nrec, int paired, int gap, int
 
 // ------------------------------------------------------------------ host
 
-static int index_lines(pg_ctx *ctx, const char *d_text, int64_t n, int64_t **d_start_out, int64_t *nlines_out)
+int pg_index_lines(pg_ctx *ctx, const char *d_text, int64_t n, int64_t **d_start_out, int64_t *nlines_out)
 {
     const int64_t nseg = (n + PG_SEG - 1) / PG_SEG;
     int64_t *d_cnt = NULL, *d_off = NULL, *d_start = NULL;
@@ -270,11 +270,11 @@ extern "C" int pg_trim_join(pg_ctx *ctx, const char *a_host, int64_t a_len, cons
     int64_t *d_sa = NULL, *d_sb = NULL, na = 0, nb = 0;
     PG_CUDA(ctx, cudaMalloc(&d_a, (size_t)a_len + 16));
     PG_CUDA(ctx, cudaMemcpyAsync(d_a, a_host, (size_t)a_len, cudaMemcpyHostToDevice, ctx->stream));
-    PG_TRY(index_lines(ctx, d_a, a_len, &d_sa, &na));
+    PG_TRY(pg_index_lines(ctx, d_a, a_len, &d_sa, &na));
     if (!fastq) {
         PG_CUDA(ctx, cudaMalloc(&d_b, (size_t)b_len + 16));
         PG_CUDA(ctx, cudaMemcpyAsync(d_b, b_host, (size_t)b_len, cudaMemcpyHostToDevice, ctx->stream));
-        PG_TRY(index_lines(ctx, d_b, b_len, &d_sb, &nb));
+        PG_TRY(pg_index_lines(ctx, d_b, b_len, &d_sb, &nb));
     }
     TextLines A = {d_a, d_sa, na, a_len}, B = {d_b, d_sb, nb, b_len};
     const int64_t per = fastq ? (paired ? 8 : 4) : 1;

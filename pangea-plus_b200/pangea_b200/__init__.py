@@ -59,6 +59,11 @@ class _TrimOpts(C.Structure):
     _fields_ = [("gap", C.c_int32), ("truncate", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
+class _MegaclustOpts(C.Structure):
+    _fields_ = [("sim_threshold", C.c_double), ("eval_threshold", C.c_double), ("bitscore_threshold", C.c_double),
+                ("count_every_hit", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
 class _ConsensusIn(C.Structure):
     _fields_ = [
         ("nreads", C.c_int64),
@@ -151,6 +156,8 @@ def load_library() -> C.CDLL:
     lib.pg_tax_leaf.argtypes = [vp, vp, vp, i64, vp]
     lib.pg_tax_lineage.argtypes = [vp, vp, vp, i64, vp, i64, vp]
     lib.pg_consensus.argtypes = [vp, C.POINTER(_ConsensusIn), vp, vp]
+    lib.pg_megaclust.argtypes = [vp, C.c_char_p, i64, C.POINTER(_MegaclustOpts), i64, C.POINTER(i64), vp, vp, vp,
+                                 C.POINTER(i64), C.POINTER(i64)]
     lib.pg_trim_join.argtypes = [vp, C.c_char_p, i64, C.c_char_p, i64, C.c_int, C.POINTER(_TrimOpts), vp, i64, C.POINTER(i64), C.POINTER(vp)]
     lib.pg_tax_chain.argtypes = [vp, vp, vp, i64, i32, vp, vp]
     lib.pg_tax_node_record.argtypes = [vp, i32, vp]
@@ -369,6 +376,19 @@ class Context:
         self._chk(self.lib.pg_boot_indices(self.h, n, min_boot_words, out.ctypes.data))
         return out
 
+
+    # ---- Megaclust
+    def megaclust(self, text: bytes, sim: float = 95.0, ev: float = 1e-20, bits: float = 200.0, every: bool = False):
+        """-> (list[(subject bytes, count)] in order of first appearance, lines examined, lines beyond)"""
+        opts = _MegaclustOpts(sim, ev, bits, 1 if every else 0)
+        cap = max(16, text.count(b"\n") + 2)
+        off = np.zeros(cap, np.int64)
+        ln = np.zeros(cap, np.int32)
+        cnt = np.zeros(cap, np.int64)
+        n, ex, by = C.c_int64(), C.c_int64(), C.c_int64()
+        self._chk(self.lib.pg_megaclust(self.h, text, len(text), C.byref(opts), cap, C.byref(n), off.ctypes.data,
+                                        ln.ctypes.data, cnt.ctypes.data, C.byref(ex), C.byref(by)))
+        return [(text[off[i]:off[i] + ln[i]], int(cnt[i])) for i in range(n.value)], ex.value, by.value
 
     # ---- Trim join
     def trim_join(self, a: bytes, b: bytes | None = None, paired: bool = False, gap: int = 189, truncate: int = 11,

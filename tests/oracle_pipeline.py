@@ -18,13 +18,19 @@ def lib():
     global _lib
     if _lib is None:
         so = ORACLE_DIR / "libpipeline_ref.so"
-        srcs = [ORACLE_DIR / "taxcollector_ref.c", ORACLE_DIR / "consensus_ref.c", ORACLE_DIR / "trim_ref.c"]
+        srcs = [ORACLE_DIR / "taxcollector_ref.c", ORACLE_DIR / "consensus_ref.c", ORACLE_DIR / "trim_ref.c",
+                ORACLE_DIR / "megaclust_ref.c"]
         if not so.exists() or any(so.stat().st_mtime < s.stat().st_mtime for s in srcs):
             subprocess.run(["make", "-C", str(ORACLE_DIR), str(so)], check=True, capture_output=True)
         L = C.CDLL(str(so))
         L.txc_file.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
         L.cns_run.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64]
         L.trim_run.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p]
+        L.mc_ref_megaclust.restype = C.c_longlong
+        L.mc_ref_megaclust.argtypes = [C.c_char_p, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_int, C.c_longlong,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mc_ref_number.restype = C.c_double
+        L.mc_ref_number.argtypes = [C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -105,3 +111,52 @@ def real_trim(a, b, gap, out, truncate=None):
         if sd.exists():
             shutil.rmtree(sd, ignore_errors=True)
         return r.stdout
+
+
+# ------------------------------------------------------------------ Megaclust
+
+def oracle_megaclust(text: bytes, sim=95.0, ev=1e-20, bits=200.0, every=False):
+    """-> (list[(subject bytes, count)] in order of first appearance, lines examined, lines beyond)"""
+    import numpy as np
+
+    cap = text.count(b"\n") + 2
+    off = np.zeros(cap, np.int64)
+    ln = np.zeros(cap, np.int32)
+    cnt = np.zeros(cap, np.int64)
+    ex, by = C.c_longlong(), C.c_longlong()
+    n = lib().mc_ref_megaclust(text, len(text), sim, ev, bits, 1 if every else 0, cap, off.ctypes.data, ln.ctypes.data,
+                               cnt.ctypes.data, C.byref(ex), C.byref(by))
+    assert n >= 0
+    return [(text[off[i]:off[i] + ln[i]], int(cnt[i])) for i in range(n)], ex.value, by.value
+
+
+def oracle_number(s: bytes) -> float:
+    return lib().mc_ref_number(s, len(s))
+
+
+def have_megaclust_reference() -> bool:
+    return (REF / "Megaclust" / "megaclust2.pl").exists() and shutil.which("perl") is not None
+
+
+def real_megaclust(text: bytes, args=()):
+    """the live script -> (set of output lines after the header, header, stdout)"""
+    with tempfile.TemporaryDirectory() as wd:
+        wd = Path(wd)
+        (wd / "in.txt").write_bytes(text)
+        r = subprocess.run(["perl", str(REF / "Megaclust" / "megaclust2.pl"), "-i", "in.txt", "-o", "out.txt", *args],
+                           cwd=wd, capture_output=True)
+        out = (wd / "out.txt").read_bytes() if (wd / "out.txt").exists() else b""
+    lines = out.split(b"\n")
+    return sorted(l for l in lines[1:] if l), lines[0], r.stdout
+
+
+def real_megaclustable(files: dict, level: str, order=None):
+    """files: name -> bytes; the live megaclustable.pl -> output bytes"""
+    with tempfile.TemporaryDirectory() as wd:
+        wd = Path(wd)
+        for k, v in files.items():
+            (wd / k).write_bytes(v)
+        names = order or list(files)
+        subprocess.run(["perl", str(REF / "Megaclustable" / "megaclustable.pl"), "-m", *names, "-t", level, "-o", "table.txt"],
+                       cwd=wd, capture_output=True)
+        return (wd / "table.txt").read_bytes() if (wd / "table.txt").exists() else None
