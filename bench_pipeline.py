@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--species", type=int, default=20000)
     ap.add_argument("--max-gi", type=int, default=5_000_000)
     ap.add_argument("--repeat", type=int, default=5)
+    ap.add_argument("--mega-reads", type=int, default=400000, help="reads of the Megaclust input (about 3 lines each)")
     args = ap.parse_args()
 
     import oracle_pipeline as op
@@ -109,6 +110,30 @@ def main():
         "gpu_launches": ctx.launch_count(),
         "parity": "lineage strings, winners and match counts identical to the oracle on the whole input",
     }
+    # ---- Megaclust: thresholds + OTU counting over consensus-like text
+    from pangea_b200 import synth_mega
+
+    mtext = synth_mega.make_consensus_text(0x7A73, args.mega_reads, otus=5000)
+    mlines = mtext.count(b"\n")
+    ctx.megaclust(mtext[: 1 << 16])
+    mbufs = (np.zeros(mlines + 2, np.int64), np.zeros(mlines + 2, np.int32), np.zeros(mlines + 2, np.int64))
+    best_m = 1e9
+    for _ in range(args.repeat):
+        t0 = time.perf_counter()
+        ctx.megaclust_raw(mtext, sim=80.0, bits=100.0, bufs=mbufs)           # the C ABI call: host text in, OTU arrays out
+        best_m = min(best_m, time.perf_counter() - t0)
+    mres = ctx.megaclust(mtext, sim=80.0, bits=100.0)
+    t0 = time.perf_counter()
+    mref = op.oracle_megaclust(mtext, sim=80.0, bits=100.0)
+    cpu_m = time.perf_counter() - t0
+    assert mres == mref, "GPU OTU counts differ from the oracle"
+    line["megaclust"] = {"value": mlines / best_m, "unit": "lines/s", "lines": mlines, "otus": len(mres[0]),
+                         "cpu_port": {"value": mlines / cpu_m, "unit": "lines/s", "cores": 1, "what": "oracle/megaclust_ref.c"}}
+    if op.have_megaclust_reference():
+        t0 = time.perf_counter()
+        op.real_megaclust(mtext[: mtext.find(b"\n", len(mtext) // 8) + 1], ["-s", "80", "-b", "100"])
+        line["megaclust"]["reference_perl"] = {"value": (mlines / 8) / (time.perf_counter() - t0), "unit": "lines/s",
+                                               "sample": "first eighth of the input, megaclust2.pl"}
     if op.have_reference():
         n_ref = min(300, nh)
         h2 = tmp / "hits_small.txt"

@@ -8,7 +8,7 @@
 //   k_mc_parse     thread per line: fields, thresholds, 64-bit hashes of subject and (subject, query)
 //   k_mc_pairs     thread per passing line: insert-if-absent into an open-addressing table keyed by the
 //                  (subject, query) strings (atomicCAS on the slot, byte compare on a hash match)
-//   k_mc_subjects  thread per counted line: subject table, atomicAdd on the count, atomicMin on the
+//   k_mc_subjects  thread per passing line: subject table, atomicAdd on the count (counted lines), atomicMin on the
 //                  first line (the output lists OTUs in order of first appearance; the script's own
 //                  order is Perl's hash order, i.e. unspecified)
 //   k_mc_collect   occupied subject slots -> compact (first line, count) records
@@ -140,7 +140,9 @@ __global__ void k_mc_subjects(const char *__restrict__ t, const McLine *__restri
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nlines) return;
     const McLine &L = lines[i];
-    if (!L.counted) return;
+    if (L.state != 2) return;
+    // every passing line votes for the subject's first line (which of two lines of the same (subject, query)
+    // pair won the race in k_mc_pairs must not show in the output order); only counted lines add to the count
     uint64_t slot = L.h_subj & mask;
     for (;;) {
         unsigned long long cur = table[slot].owner;
@@ -150,7 +152,7 @@ __global__ void k_mc_subjects(const char *__restrict__ t, const McLine *__restri
         }
         const McLine &O = lines[cur - 1];
         if (O.h_subj == L.h_subj && mc_same(t, O.subj_off, O.subj_len, L.subj_off, L.subj_len)) {
-            atomicAdd(&table[slot].count, 1ULL);
+            if (L.counted) atomicAdd(&table[slot].count, 1ULL);
             atomicMin(&table[slot].first, (unsigned long long)i);
             return;
         }
@@ -216,16 +218,23 @@ extern "C" int pg_megaclust(pg_ctx *ctx, const char *text_host, int64_t len, con
     unsigned long long st[3] = {0, 0, 0};
     uint64_t size = 1;
 #define MC_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { rc = pg_fail(ctx, PG_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); goto done; } } while (0)
-    MC_CUDA(cudaMalloc(&d_text, (size_t)len + 16));
+    // grow-only context scratch (shared with the other stages; one call at a time per context)
+    if ((rc = pg_scratch(ctx, &ctx->s_bytes, (size_t)len + 16)) != PG_OK) goto done;
+    d_text = (char *)ctx->s_bytes.p;
     MC_CUDA(cudaMemcpyAsync(d_text, text_host, (size_t)len, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = pg_index_lines(ctx, d_text, len, &d_start, &nlines)) != PG_OK) goto done;
     if (nlines == 0) goto done;
     while (size < (uint64_t)nlines * 2) size <<= 1;                    // load factor <= 0.5
-    MC_CUDA(cudaMalloc(&d_lines, (size_t)nlines * sizeof(McLine)));
-    MC_CUDA(cudaMalloc(&d_pairs, (size_t)size * 8));
-    MC_CUDA(cudaMalloc(&d_subj, (size_t)size * sizeof(McSlot)));
-    MC_CUDA(cudaMalloc(&d_stats, 32));
-    MC_CUDA(cudaMalloc(&d_recs, (size_t)nlines * 16 + 16));
+    if ((rc = pg_scratch(ctx, &ctx->s_cand, (size_t)nlines * sizeof(McLine))) != PG_OK ||
+        (rc = pg_scratch(ctx, &ctx->s_candl, (size_t)size * 8)) != PG_OK ||
+        (rc = pg_scratch(ctx, &ctx->s_champ, (size_t)size * sizeof(McSlot))) != PG_OK ||
+        (rc = pg_scratch(ctx, &ctx->s_results, (size_t)nlines * 16 + 96)) != PG_OK)
+        goto done;
+    d_lines = (McLine *)ctx->s_cand.p;
+    d_pairs = (unsigned long long *)ctx->s_candl.p;
+    d_subj = (McSlot *)ctx->s_champ.p;
+    d_recs = (unsigned long long *)ctx->s_results.p + 4;
+    d_stats = (unsigned long long *)ctx->s_results.p;
     MC_CUDA(cudaMemsetAsync(d_pairs, 0, (size_t)size * 8, ctx->stream));
     MC_CUDA(cudaMemsetAsync(d_stats, 0, 32, ctx->stream));
     {
@@ -268,7 +277,6 @@ extern "C" int pg_megaclust(pg_ctx *ctx, const char *text_host, int64_t len, con
     }
 done:
 #undef MC_CUDA
-    cudaFree(d_text); cudaFree(d_start); cudaFree(d_lines); cudaFree(d_pairs); cudaFree(d_subj);
-    cudaFree(d_stats); cudaFree(d_recs); cudaFree(d_off); cudaFree(d_len);
+    cudaFree(d_start); cudaFree(d_off); cudaFree(d_len);
     return rc;
 }

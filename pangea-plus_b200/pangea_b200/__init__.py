@@ -378,17 +378,23 @@ class Context:
 
 
     # ---- Megaclust
+    def megaclust_raw(self, text: bytes, sim: float = 95.0, ev: float = 1e-20, bits: float = 200.0, every: bool = False,
+                      bufs=None):
+        """the C ABI call itself -> (n, off, len, count, examined, beyond); bufs = (off, len, count) arrays to reuse"""
+        opts = _MegaclustOpts(sim, ev, bits, 1 if every else 0)
+        if bufs is None:
+            cap = max(16, text.count(b"\n") + 2)
+            bufs = (np.zeros(cap, np.int64), np.zeros(cap, np.int32), np.zeros(cap, np.int64))
+        off, ln, cnt = bufs
+        n, ex, by = C.c_int64(), C.c_int64(), C.c_int64()
+        self._chk(self.lib.pg_megaclust(self.h, text, len(text), C.byref(opts), len(off), C.byref(n), off.ctypes.data,
+                                        ln.ctypes.data, cnt.ctypes.data, C.byref(ex), C.byref(by)))
+        return n.value, off, ln, cnt, ex.value, by.value
+
     def megaclust(self, text: bytes, sim: float = 95.0, ev: float = 1e-20, bits: float = 200.0, every: bool = False):
         """-> (list[(subject bytes, count)] in order of first appearance, lines examined, lines beyond)"""
-        opts = _MegaclustOpts(sim, ev, bits, 1 if every else 0)
-        cap = max(16, text.count(b"\n") + 2)
-        off = np.zeros(cap, np.int64)
-        ln = np.zeros(cap, np.int32)
-        cnt = np.zeros(cap, np.int64)
-        n, ex, by = C.c_int64(), C.c_int64(), C.c_int64()
-        self._chk(self.lib.pg_megaclust(self.h, text, len(text), C.byref(opts), cap, C.byref(n), off.ctypes.data,
-                                        ln.ctypes.data, cnt.ctypes.data, C.byref(ex), C.byref(by)))
-        return [(text[off[i]:off[i] + ln[i]], int(cnt[i])) for i in range(n.value)], ex.value, by.value
+        n, off, ln, cnt, ex, by = self.megaclust_raw(text, sim, ev, bits, every)
+        return [(text[off[i]:off[i] + ln[i]], int(cnt[i])) for i in range(n)], ex, by
 
     # ---- Trim join
     def trim_join(self, a: bytes, b: bytes | None = None, paired: bool = False, gap: int = 189, truncate: int = 11,
