@@ -180,6 +180,10 @@ int pg_classify(pg_ctx *ctx, const pg_model *m, const pg_seqbatch *reads_host,
                 const pg_classify_opts *opts, pg_result *results_host, int32_t *boot_winners_host);
 int pg_classify_packed(pg_ctx *ctx, const pg_model *m, const pg_reads *reads,
                        const pg_classify_opts *opts, pg_result *results_dev, int32_t *boot_winners_dev);
+/* the same with the records (and optional replicate winners) delivered to host memory: what a C host program
+ * calls after pg_fasta_ingest() / pg_trim_join(..., reads_out) */
+int pg_classify_packed_host(pg_ctx *ctx, const pg_model *m, const pg_reads *reads,
+                            const pg_classify_opts *opts, pg_result *results_host, int32_t *boot_winners_host);
 
 /* Parity hook for A1/A3: the word list the classifier uses for each read
  * (after orientation).  words_host[off[i] + j], n_words_host[i], reversed_host[i]. */
@@ -270,6 +274,18 @@ typedef struct {
  * for pg_classify_packed -- records the trim dropped are simply absent from both outputs. */
 int pg_trim_join(pg_ctx *ctx, const char *a_host, int64_t a_len, const char *b_host, int64_t b_len, int paired,
                  const pg_trim_opts *opts, char *out_host, int64_t out_cap, int64_t *out_len, pg_reads **reads_out);
+
+/* ------------------------------------------------------------------ FASTA ingest (widening: SURVEY.md 8(f) next-1)
+ * Replaces the file reading of `java -jar rdp_classifier-2.5.jar -q <in.fa>` (README.md:119): the whole query
+ * file goes to the device as text; out come the packed read store for pg_classify_packed (records in file
+ * order) and, per record, where its header sits in text_host: the header is
+ * text_host[hdr_off[i] .. hdr_off[i]+hdr_len[i]) (without '>'), the id its first id_len[i] bytes.
+ * Lines starting with '>' open a record; other lines are sequence ('\r' and blanks dropped; lines before the
+ * first header ignored).  PG_ERANGE (count in *nrec) when cap is too small.  reads_out may be NULL. */
+int pg_fasta_ingest(pg_ctx *ctx, const char *text_host, int64_t len, int64_t cap, int64_t *nrec, int64_t *hdr_off,
+                    int32_t *id_len, int32_t *hdr_len, pg_reads **reads_out);
+/* Parity hook: sequence bytes (concatenated) and offsets [nrec+1] produced by the last pg_fasta_ingest(). */
+int pg_fasta_last_bytes(pg_ctx *ctx, int64_t nrec, char *bytes_host, int64_t cap, int64_t *off_host);
 
 /* ------------------------------------------------------------------ Megaclust (widening: SURVEY.md 8(f) next-2)
  * Replaces: `perl megaclust2.pl -i <consensus or BLAST tabular> -o <out> [-s sim] [-e evalue] [-b bitscore] [-c x]`

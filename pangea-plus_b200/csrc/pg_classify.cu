@@ -619,6 +619,24 @@ extern "C" int pg_classify_packed(pg_ctx *ctx, const pg_model *md, const pg_read
                            results_dev, boot_winners_dev);
 }
 
+extern "C" int pg_classify_packed_host(pg_ctx *ctx, const pg_model *md, const pg_reads *reads, const pg_classify_opts *opts,
+                                       pg_result *results_host, int32_t *boot_winners_host)
+{
+    if (!ctx || !md || !reads || !results_host) return pg_fail(ctx, PG_EINVAL, "pg_classify_packed_host: bad arguments");
+    if (!md->committed) return pg_fail(ctx, PG_EINVAL, "pg_classify_packed_host: model has no tables (commit it first)");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = reads->count;
+    if (n == 0) return PG_OK;
+    PG_TRY(pg_scratch(ctx, &ctx->s_results, (size_t)n * sizeof(pg_result) + (boot_winners_host ? (size_t)n * 400 : 0)));
+    pg_result *d_res = (pg_result *)ctx->s_results.p;
+    int32_t *d_bw = boot_winners_host ? (int32_t *)(d_res + n) : NULL;
+    PG_TRY(classify_planes(ctx, md, reads->d_planes, reads->d_off, n, reads->total_bytes, opts, d_res, d_bw));
+    PG_CUDA(ctx, cudaMemcpyAsync(results_host, d_res, (size_t)n * sizeof(pg_result), cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_bw) PG_CUDA(ctx, cudaMemcpyAsync(boot_winners_host, d_bw, (size_t)n * 400, cudaMemcpyDeviceToHost, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PG_OK;
+}
+
 // records of the listed reads, gathered for one small copy to the host
 static __global__ void k_gather_words(const uint32_t *__restrict__ src, int words_per_rec, const int32_t *__restrict__ list,
                                       int cnt, uint32_t *__restrict__ out)

@@ -27,6 +27,21 @@
 #include "pg_host_common.h"
 #include <time.h>
 
+static char *slurp_file(const char *path, int64_t *len)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return NULL;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    char *b = (char *)malloc((size_t)n + 1);
+    if (n && fread(b, 1, (size_t)n, f) != (size_t)n) { fclose(f); free(b); return NULL; }
+    fclose(f);
+    b[n] = 0;
+    *len = n;
+    return b;
+}
+
 static double now_s(void)
 {
     struct timespec ts;
@@ -261,19 +276,38 @@ int main(int argc, char **argv)
     taxonomy t;
     if (!blob || tax_from_blob((const char *)blob, blen, &t)) { fprintf(stderr, "rdp_classifier: %s has no taxonomy section\n", model); return 1; }
     LAP("model load");
-    pg_fasta fa;
-    if (pg_fasta_read(q, &fa)) { fprintf(stderr, "rdp_classifier: cannot read %s\n", q); return 1; }
-    LAP("FASTA parse");
+    /* the query file goes to the device as text: records, ids and the packed read store come from the GPU
+     * (pg_fasta_ingest); the host keeps the text only to print the ids */
+    int64_t qlen = 0;
+    char *qtext = slurp_file(q, &qlen);
+    if (!qtext) { fprintf(stderr, "rdp_classifier: cannot read %s\n", q); return 1; }
+    LAP("file read");
+    int64_t cap = qlen / 32 + 1024, nrec = 0;
+    int64_t *hdr_off = NULL;
+    int32_t *id_len = NULL;
+    pg_reads *reads = NULL;
+    for (;;) {
+        hdr_off = (int64_t *)realloc(hdr_off, sizeof(int64_t) * (size_t)cap);
+        id_len = (int32_t *)realloc(id_len, sizeof(int32_t) * (size_t)cap);
+        int rc = pg_fasta_ingest(ctx, qtext, qlen, cap, &nrec, hdr_off, id_len, NULL, &reads);
+        if (rc == PG_ERANGE && nrec > cap) { cap = nrec; continue; }
+        if (rc != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx)); return 1; }
+        break;
+    }
+    LAP("FASTA ingest (GPU)");
     FILE *fo = fopen(o, "w");
     if (!fo) { fprintf(stderr, "rdp_classifier: cannot write %s\n", o); return 1; }
-    pg_result *res = (pg_result *)malloc(sizeof(pg_result) * (size_t)(fa.count + 1));
-    pg_seqbatch sb = {fa.bytes, fa.off, fa.count};
+    pg_result *res = (pg_result *)malloc(sizeof(pg_result) * (size_t)(nrec + 1));
     pg_classify_opts opts;
     memset(&opts, 0, sizeof opts);
     opts.min_boot_words = min_boot;
     opts.mode = strict ? 0 : 1;
-    if (pg_classify(ctx, md, &sb, &opts, res, NULL) != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx)); return 1; }
-    LAP("pg_classify");
+    if (nrec > 0 && pg_classify_packed_host(ctx, md, reads, &opts, res, NULL) != PG_OK) {
+        fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx));
+        return 1;
+    }
+    pg_reads_free(reads);
+    LAP("pg_classify_packed");
     static const char *FIX[6] = {"domain", "phylum", "class", "order", "family", "genus"};
     /* Output is assembled from pieces prepared once per taxon ("\tname\trank\t") and once per vote
      * count (the 101 possible confidences), so a line costs a few memcpy()s, not a dozen fprintf()s. */
@@ -290,17 +324,18 @@ int main(int argc, char **argv)
     char *obuf = (char *)malloc(ocap);
 #define OUT_ROOM(need) do { if (on + (need) > ocap) { fwrite(obuf, 1, on, fo); on = 0; } } while (0)
 #define OUT_STR(s, n) do { memcpy(obuf + on, (s), (n)); on += (n); } while (0)
-    for (int64_t i = 0; i < fa.count; i++) {
+    for (int64_t i = 0; i < nrec; i++) {
         const pg_result *r = &res[i];
+        const char *rid = qtext + hdr_off[i];
+        const size_t idlen = (size_t)id_len[i];
         if (r->status) {
-            printf("ShortSequenceException: The length of sequence with recordID=%s is less than %d\n", fa.id[i], PG_MIN_SEQ_LEN);
+            printf("ShortSequenceException: The length of sequence with recordID=%.*s is less than %d\n", (int)idlen, rid, PG_MIN_SEQ_LEN);
             continue;
         }
         int path[PG_MAX_DEPTH], np = 0;                   /* the genus' lineage, leaf first */
         for (int n = t.genus_node[r->genus]; n >= 0 && np < PG_MAX_DEPTH; n = t.parent[n]) path[np++] = n;
-        size_t idlen = strlen(fa.id[i]);
         OUT_ROOM(idlen + 16 + (size_t)np * 256);
-        OUT_STR(fa.id[i], idlen);
+        OUT_STR(rid, idlen);
         if (ifmt == 2) OUT_STR("\t\t\t\t", 4);           /* with the piece's own leading TAB: five */
         else { OUT_STR("\t", 1); if (r->reversed) OUT_STR("-", 1); }
         if (ifmt == 1) {
@@ -331,7 +366,9 @@ int main(int argc, char **argv)
     fclose(fo);
     free(res);
     pg_free(blob);
-    pg_fasta_free(&fa);
+    free(qtext);
+    free(hdr_off);
+    free(id_len);
     pg_model_free(md);
     pg_shutdown(ctx);
     return 0;

@@ -156,6 +156,9 @@ def load_library() -> C.CDLL:
     lib.pg_tax_leaf.argtypes = [vp, vp, vp, i64, vp]
     lib.pg_tax_lineage.argtypes = [vp, vp, vp, i64, vp, i64, vp]
     lib.pg_consensus.argtypes = [vp, C.POINTER(_ConsensusIn), vp, vp]
+    lib.pg_fasta_ingest.argtypes = [vp, C.c_char_p, i64, i64, C.POINTER(i64), vp, vp, vp, C.POINTER(vp)]
+    lib.pg_fasta_last_bytes.argtypes = [vp, i64, vp, i64, vp]
+    lib.pg_classify_packed_host.argtypes = [vp, vp, vp, C.POINTER(_Opts), vp, vp]
     lib.pg_megaclust.argtypes = [vp, C.c_char_p, i64, C.POINTER(_MegaclustOpts), i64, C.POINTER(i64), vp, vp, vp,
                                  C.POINTER(i64), C.POINTER(i64)]
     lib.pg_trim_join.argtypes = [vp, C.c_char_p, i64, C.c_char_p, i64, C.c_int, C.POINTER(_TrimOpts), vp, i64, C.POINTER(i64), C.POINTER(vp)]
@@ -376,6 +379,31 @@ class Context:
         self._chk(self.lib.pg_boot_indices(self.h, n, min_boot_words, out.ctypes.data))
         return out
 
+
+    # ---- FASTA ingest
+    def fasta_ingest(self, text: bytes, want_reads: bool = True):
+        """-> (ids list[bytes], headers list[bytes], sequence bytes uint8, offsets int64, Reads or None)"""
+        cap = max(16, text.count(b">") + 1)
+        hoff, idl, hl = np.zeros(cap, np.int64), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+        n, h = C.c_int64(), C.c_void_p()
+        self._chk(self.lib.pg_fasta_ingest(self.h, text, len(text), cap, C.byref(n), hoff.ctypes.data, idl.ctypes.data,
+                                           hl.ctypes.data, C.byref(h) if want_reads else None))
+        n = n.value
+        off = np.zeros(n + 1, np.int64)
+        buf = np.zeros(max(int(len(text)), 1), np.uint8)
+        self._chk(self.lib.pg_fasta_last_bytes(self.h, n, buf.ctypes.data, buf.size, off.ctypes.data))
+        ids = [text[hoff[i]:hoff[i] + idl[i]] for i in range(n)]
+        hdr = [text[hoff[i]:hoff[i] + hl[i]] for i in range(n)]
+        reads = Reads(self, h.value) if (want_reads and h.value) else None
+        return ids, hdr, buf[: int(off[n])], off, reads
+
+    def classify_packed_host(self, model: Model, reads: Reads, mode: int = 0, min_boot_words: int = 0, want_boot: bool = False):
+        n = len(reads)
+        opts = _Opts(min_boot_words, mode, 0, 0)
+        res = np.zeros(n, RESULT_DTYPE)
+        boot = np.zeros((n, PG_NUM_BOOT), np.int32) if want_boot else None
+        self._chk(self.lib.pg_classify_packed_host(self.h, model.h, reads.h, C.byref(opts), _ptr(res), _ptr(boot)))
+        return (res, boot) if want_boot else res
 
     # ---- Megaclust
     def megaclust_raw(self, text: bytes, sim: float = 95.0, ev: float = 1e-20, bits: float = 200.0, every: bool = False,
