@@ -492,3 +492,39 @@ def test_certified_without_lineage(ctx):
     assert np.array_equal(bits(c["score"]), bits(b["score"]))
     om.free()
     gm.free()
+
+
+@pytest.mark.parametrize("seed,genera,seqs,length", [(11, 70, 150, 500), (12, 130, 500, 1200), (13, 700, 1400, 800),
+                                                     (14, 2150, 4300, 420)])
+def test_certified_equals_strict_on_random_models(ctx, seed, genera, seqs, length):
+    """random taxonomies of 2 .. 40 table blocks (2 150 genera = two block groups in k_bound), reads of every
+    length bucket (single mates, joined pairs, long fragments, fragments with runs of N): the certified plans and
+    the strict kernels must agree byte for byte, and a sample must agree with the oracle."""
+    tr = synth.synth16s(seed=seed, seqs=seqs, genera=genera, length=length)
+    gm = ctx.train(tr["data"], tr["off"], tr["genus"], tr["G"])
+    gm.set_lineage(tr["anc"])
+    assert gm.certifiable
+    rng = np.random.default_rng(seed)
+    reads = []
+    for i in range(1200):
+        s = tr["data"][tr["off"][i % seqs]:tr["off"][i % seqs + 1]]
+        ln = int(rng.choice([60, 120, 250, min(700, len(s)), len(s)]))
+        a = int(rng.integers(0, len(s) - ln + 1))
+        r = s[a:a + ln].copy()
+        hit = rng.random(ln) < 0.01
+        r[hit] = synth.BASES[rng.integers(0, 4, int(hit.sum()))]
+        if i % 9 == 0 and ln > 80:
+            r[30:30 + int(rng.integers(1, 40))] = ord("N")
+        if i % 2:
+            r = synth.revcomp(r)
+        reads.append(r.tobytes())
+    data, off = pack_sequences(reads)
+    want, wb = ctx.classify(gm, data, off, mode=0, want_boot=True)
+    for kw in (dict(), dict(cert_plan=1), dict(light_max=5)):
+        got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True, **kw)
+        assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb), kw
+    om = ora.Model(tr["data"], tr["off"], tr["genus"], tr["G"])
+    ref = om.classify(data[: off[150]], off[:151])
+    assert np.array_equal(want["genus"][:150], ref["genus"]) and np.array_equal(wb[:150], ref["boot"])
+    om.free()
+    gm.free()
