@@ -154,8 +154,9 @@ typedef struct {
     int32_t mode;             /* 0 = strict (reference order);
                                  1 = certified (quantised pre-filter, strict re-check)  */
     int32_t cert_plan;        /* certified mode only, results never depend on it:
-                                 0 = default (best block + block lower bounds + items),
-                                 1 = every genus block with partial-sum pruning          */
+                                 0 = default (better half of the best block + lower bounds + items),
+                                 1 = every genus block with partial-sum pruning,
+                                 2 = the whole best block + lower bounds + items         */
     int32_t light_max;        /* cert_plan 0: open (task, block) pairs per read above which the
                                  read is redone under cert_plan 1; 0 = default, -1 = none */
     int32_t reserved[4];

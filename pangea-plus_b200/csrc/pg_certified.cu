@@ -83,17 +83,21 @@ __global__ void k_quantise(const float *__restrict__ table, const float *__restr
     q[idx] = (uint16_t)v;
 }
 
-// one thread per (block, word): minimum deficit over the block's 64 positions (padding holds
-// PG_Q_MAX and never wins).  bm[(blk/32)][w][blk%32]: the 32 blocks of a group are one 64-byte row.
-__global__ void k_blockmin(const uint16_t *__restrict__ q, int ntile64, uint16_t *__restrict__ bm)
+// Lower-bound tables.  bm: per (word, block) the minimum deficit over the block's 64 positions (padding holds
+// PG_Q_MAX and never wins).  A group is PG_GB = 31 blocks: bm[group][w][slot], slot 31 of every 64-byte row is
+// spare -- k_bound puts the minima of the best block's other half there (plan 3).
+#define PG_GB 31
+__global__ void k_blockmin(const uint16_t *__restrict__ q, int ntile64, int ngroup, uint16_t *__restrict__ bm)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int w = (int)(idx & (PG_NWORDS - 1));
-    const int blk = (int)(idx >> 16);
-    const int ngroup = (ntile64 + 31) / 32;
-    if (blk >= ngroup * 32) return;
-    uint32_t m = 0xFFFFu;
-    if (blk < ntile64) {
+    const int gs = (int)(idx >> 16);
+    if (gs >= ngroup * 32) return;
+    const int grp = gs >> 5, slot = gs & 31;
+    const int blk = grp * PG_GB + slot;
+    uint32_t m = PG_Q_MAX;
+    if (slot < PG_GB && blk < ntile64) {
+        m = 0xFFFFu;
         const uint4 *row = reinterpret_cast<const uint4 *>(q + ((size_t)blk * PG_NWORDS + w) * 64);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -102,7 +106,29 @@ __global__ void k_blockmin(const uint16_t *__restrict__ q, int ntile64, uint16_t
             m = min(m, min(a & 0xFFFFu, a >> 16));
         }
     }
-    bm[((size_t)(blk >> 5) * PG_NWORDS + w) * 32 + (blk & 31)] = (uint16_t)m;
+    bm[((size_t)grp * PG_NWORDS + w) * 32 + slot] = (uint16_t)m;
+}
+
+// hm: per (word, half block) the minimum over the half's 32 positions; hm[hb / 32][w][hb % 32], hb = 2*block + half
+__global__ void k_halfmin(const uint16_t *__restrict__ q, int ntile64, uint16_t *__restrict__ hm)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int w = (int)(idx & (PG_NWORDS - 1));
+    const int blk = (int)(idx >> 16);
+    if (blk >= ntile64) return;
+    const uint4 *row = reinterpret_cast<const uint4 *>(q + ((size_t)blk * PG_NWORDS + w) * 64);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        uint32_t m = 0xFFFFu;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint4 v = row[h * 4 + i];
+            const uint32_t a = __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w));
+            m = min(m, min(a & 0xFFFFu, a >> 16));
+        }
+        const int hb = 2 * blk + h;
+        hm[((size_t)(hb >> 5) * PG_NWORDS + w) * 32 + (hb & 31)] = (uint16_t)m;
+    }
 }
 
 // Table layout of certified mode.  pos_host[p] = genus stored at table position p, or -1 for padding;
@@ -122,11 +148,12 @@ int pg_model_set_layout(pg_model *md, const int32_t *pos_host, int npos)
     }
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (nblk != md->ntile64) {                           // a different block count: the tables are re-allocated
-        cudaFree(md->d_perm); cudaFree(md->d_blockmask); cudaFree(md->d_qtable); cudaFree(md->d_bmtable);
-        md->d_perm = NULL; md->d_blockmask = NULL; md->d_qtable = NULL; md->d_bmtable = NULL;
+        cudaFree(md->d_perm); cudaFree(md->d_blockmask); cudaFree(md->d_qtable); cudaFree(md->d_bmtable); cudaFree(md->d_hmtable);
+        md->d_perm = NULL; md->d_blockmask = NULL; md->d_qtable = NULL; md->d_bmtable = NULL; md->d_hmtable = NULL;
     }
     md->ntile64 = nblk;
-    md->ngroup = (nblk + 31) / 32;
+    md->ngroup = (nblk + PG_GB - 1) / PG_GB;
+    md->ngroup_h = (2 * nblk + 31) / 32;
     if (!md->d_perm) {
         PG_CUDA(ctx, cudaMalloc(&md->d_perm, full.size() * 4));
         PG_CUDA(ctx, cudaMalloc(&md->d_blockmask, mask.size() * 8));
@@ -203,7 +230,8 @@ int pg_model_derive_quantised(pg_model *md)
     if (!md->d_qtable) {
         cudaError_t e;
         if ((e = cudaMalloc(&md->d_qtable, cells * 2)) != cudaSuccess ||
-            (e = cudaMalloc(&md->d_bmtable, bmcells * 2)) != cudaSuccess) {
+            (e = cudaMalloc(&md->d_bmtable, bmcells * 2)) != cudaSuccess ||
+            (e = cudaMalloc(&md->d_hmtable, (size_t)md->ngroup_h * PG_NWORDS * 32 * 2)) != cudaSuccess) {
             (void)cudaGetLastError();
             return pg_fail(ctx, PG_ENOMEM, "quantised table allocation failed: %s", cudaGetErrorString(e));
         }
@@ -216,7 +244,11 @@ int pg_model_derive_quantised(pg_model *md)
     k_quantise<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(md->d_table, md->d_rowmax, md->d_perm, md->G,
                                                                          cells, md->d_qtable, d_stat + 1);
     PG_LAUNCHED(ctx);
-    k_blockmin<<<(unsigned)((bmcells + 255) / 256), 256, 0, ctx->stream>>>(md->d_qtable, md->ntile64, md->d_bmtable);
+    k_blockmin<<<(unsigned)((bmcells + 255) / 256), 256, 0, ctx->stream>>>(md->d_qtable, md->ntile64, md->ngroup, md->d_bmtable);
+    PG_LAUNCHED(ctx);
+    PG_CUDA(ctx, cudaMemsetAsync(md->d_hmtable, 0xFF, (size_t)md->ngroup_h * PG_NWORDS * 32 * 2, ctx->stream));
+    k_halfmin<<<(unsigned)(((size_t)md->ntile64 * PG_NWORDS + 255) / 256), 256, 0, ctx->stream>>>(md->d_qtable, md->ntile64,
+                                                                                                  md->d_hmtable);
     PG_LAUNCHED(ctx);
     unsigned int stat[2];
     PG_CUDA(ctx, cudaMemcpyAsync(stat, d_stat, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -512,6 +544,164 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
 #undef PG_QROW
 }
 
+// ------------------------------------------------------------------ plan 3: half blocks, two reads per CTA
+//
+// k_classify_q spends one 128-byte shared-memory wavefront per (task, draw): a row of 64 positions.  Most of
+// those 64 are irrelevant even inside the best block, so plan 3 evaluates only the better HALF of it (32
+// positions, a 64-byte row) and leaves the other half to the lower bounds like any other block (k_bound gets
+// the sibling half's minima in the spare 32nd slot of its rows).  Two reads share a CTA and interleave their
+// rows -- row r = [read A: 64 bytes | read B: 64 bytes] -- so that the two 4-lane groups of a quarter-warp
+// (one task of A, the same task of B) always hit different banks: one wavefront now serves two (task, draw)
+// pairs, and reads of equal length (adjacent in the order array) share their sample-list loads.
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB)
+k_classify_h(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
+             const int64_t *__restrict__ off, const int32_t *__restrict__ nwords,
+             const uint8_t *__restrict__ flags, const int32_t *__restrict__ order, int nreads_b, int64_t slot0,
+             const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot,
+             const unsigned long long *__restrict__ blockmask, double vmax,
+             unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand,
+             unsigned long long *__restrict__ cand, const int32_t *__restrict__ guess /* half-block ids */)
+{
+    constexpr int NGR = (BLOCK - 32) / 8;           // task slots per read: a quarter-warp = one slot of A + one of B
+    extern __shared__ uint4 sQ[];                   // (nmax+1) rows x 8 uint4: [A 4 | B 4]; row n of a read is zero
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    // ---- the two reads of this CTA (B may be missing, either may be short or wordless)
+    int n2[2], hb2[2];
+    size_t rc2[2];
+    const uint16_t *w2[2];
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int slot = 2 * (int)blockIdx.x + s;
+        n2[s] = 0; hb2[s] = 0; rc2[s] = 0; w2[s] = words;
+        if (slot < nreads_b) {
+            const int64_t read = order[slot];
+            if (!flags[2 * read + 1]) {
+                n2[s] = nwords[read];
+                w2[s] = words + off[read];
+                rc2[s] = (size_t)slot0 + slot;
+                hb2[s] = guess[rc2[s]];
+            }
+        }
+    }
+    if (n2[0] == 0 && n2[1] == 0) return;
+
+    // ---- stage the two reads' half rows
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        const int n = n2[s];
+        const uint16_t *tb = qtable + (size_t)(hb2[s] >> 1) * PG_NWORDS * 64 + (hb2[s] & 1) * 32;
+        for (int c = tid; c < n * 4; c += BLOCK) {
+            const int r = c >> 2, l = c & 3;
+            pg_cp_async16(&sQ[r * 8 + s * 4 + l], tb + (size_t)w2[s][r] * 64 + l * 8);
+        }
+        if (tid < 4) sQ[n * 8 + s * 4 + tid] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    pg_cp_async_wait_all();
+    __syncthreads();
+
+    if (tid < 32) {
+        // ---- full sums (task 0): lanes 0-15 read A, 16-31 read B; lane = one packed pair of positions
+        const int s = lane >> 4, hl = lane & 15;
+        const int n = s ? n2[1] : n2[0];
+        const int hb = s ? hb2[1] : hb2[0];
+        const size_t rc = s ? rc2[1] : rc2[0];
+        const unsigned hmask = 0xFFFFu << (s * 16);
+        if (n == 0) return;
+        const uint32_t *col = reinterpret_cast<const uint32_t *>(sQ) + s * 16 + hl;
+        uint32_t lo = 0u, hi = 0u;
+        int j = 0;
+        for (; j + 16 <= n; j += 16) {
+            uint32_t c = 0u;
+#pragma unroll
+            for (int u = 0; u < 16; u++) c += col[(j + u) * 32];
+            lo += c & 0xFFFFu;
+            hi += c >> 16;
+        }
+        uint32_t c = 0u;
+        for (; j < n; j++) c += col[j * 32];
+        lo += c & 0xFFFFu;
+        hi += c >> 16;
+        const uint32_t sums[2] = {lo, hi};
+        const uint32_t gbase = (uint32_t)(hb >> 1) * 64u, g0 = gbase + (uint32_t)(hb & 1) * 32u + 2u * hl;
+        const uint32_t vb2 = (uint32_t)(blockmask[hb >> 1] >> (g0 - gbase)) & 3u;
+        unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
+        PgPending pp;
+        pg_epilogue_begin<2>(hmask, hl == 0, sums, g0, gbase, vb2, mychamp, pp);
+        pg_epilogue_finish<2>(hmask, hl == 0, s * 16, sums, g0, gbase, vb2, 0, pg_margin(n, vmax), pp, ncand + rc,
+                              cand + rc * PG_CANDCAP);
+        return;
+    }
+
+    // ---- replicates (tasks 1..100): 4 lanes per (read, task); groups g8 = 2*slot + read
+    const int g8 = lane >> 2, l4 = lane & 3, s = g8 & 1;
+    const int group = ((tid - 32) >> 5) * 4 + (g8 >> 1);
+    const int n = s ? n2[1] : n2[0], no = s ? n2[0] : n2[1];
+    const int hb = s ? hb2[1] : hb2[0];
+    const size_t rc = s ? rc2[1] : rc2[0];
+    int k = n >> 3;
+    if (k < min_boot) k = min_boot;
+    const int nb = n > 0 ? (k + 3) >> 2 : 0;
+    // both reads of the quarter-warp walk the same number of batches (a finished one just stops loading)
+    int ko = no >> 3;
+    if (ko < min_boot) ko = min_boot;
+    const int nbo = no > 0 ? (ko + 3) >> 2 : 0;
+    const int nbmax = nb > nbo ? nb : nbo;
+    if (nbmax == 0) return;
+    const unsigned gmask = 0xFu << (lane & ~3);
+    const uint4 *lists = reinterpret_cast<const uint4 *>(boot_pool + boot_off[n]);
+    const char *lane_base = reinterpret_cast<const char *>(sQ) + s * 64 + l4 * 16;
+    const uint32_t margin = pg_margin(k, vmax);
+    const uint32_t gbase = (uint32_t)(hb >> 1) * 64u, genus0 = gbase + (uint32_t)(hb & 1) * 32u + 8u * l4;
+    const uint32_t vb8 = (uint32_t)(blockmask[hb >> 1] >> (genus0 - gbase)) & 0xFFu;
+    unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
+    unsigned int *mync = ncand + rc;
+    unsigned long long *mycand = cand + rc * PG_CANDCAP;
+    const uint32_t zoff = (uint32_t)n * PG_ROW_PITCH;
+    const uint4 zq = make_uint4(zoff, zoff, zoff, zoff);
+#define PG_HROW(o) (*reinterpret_cast<const uint4 *>(lane_base + (o)))
+#define PG_HLQ(bb) ((bb) < nb ? __ldg(lp + (bb) * 4) : zq)
+    PgPending pend;
+    uint32_t psum[8];
+    int ptask = -1;
+    for (int task = group; task < PG_NUM_BOOT; task += NGR) {
+        uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
+        uint32_t s0 = 0u, s1 = 0u, s2 = 0u, s3 = 0u, s4 = 0u, s5 = 0u, s6 = 0u, s7 = 0u;
+        const uint4 *lp = lists + (size_t)(task >> 2) * nb * 4 + (task & 3);
+        // list entries one trip (four batches) ahead of the row loads; batches past this read's end are the zero row
+        uint4 n0 = PG_HLQ(0), n1 = PG_HLQ(1), n2q = PG_HLQ(2), n3 = PG_HLQ(3);
+        for (int b = 0; b < nbmax; b += 4) {
+            const uint4 q0 = n0, q1 = n1, q2 = n2q, q3 = n3;
+            if (b + 4 < nbmax) { n0 = PG_HLQ(b + 4); n1 = PG_HLQ(b + 5); n2q = PG_HLQ(b + 6); n3 = PG_HLQ(b + 7); }
+            if (b < nb) {
+                uint4 x0, x1, x2, x3;
+                x0 = PG_HROW(q0.x); x1 = PG_HROW(q0.y); x2 = PG_HROW(q0.z); x3 = PG_HROW(q0.w);
+                PG_QADD4(x0) PG_QADD4(x1) PG_QADD4(x2) PG_QADD4(x3)
+                x0 = PG_HROW(q1.x); x1 = PG_HROW(q1.y); x2 = PG_HROW(q1.z); x3 = PG_HROW(q1.w);
+                PG_QADD4(x0) PG_QADD4(x1) PG_QADD4(x2) PG_QADD4(x3)
+                x0 = PG_HROW(q2.x); x1 = PG_HROW(q2.y); x2 = PG_HROW(q2.z); x3 = PG_HROW(q2.w);
+                PG_QADD4(x0) PG_QADD4(x1) PG_QADD4(x2) PG_QADD4(x3)
+                x0 = PG_HROW(q3.x); x1 = PG_HROW(q3.y); x2 = PG_HROW(q3.z); x3 = PG_HROW(q3.w);
+                PG_QADD4(x0) PG_QADD4(x1) PG_QADD4(x2) PG_QADD4(x3)
+                PG_QSPILL()                          // 16 rows x 4095 < 2^16
+            }
+        }
+        if (nb == 0) continue;                          // k == 0: every sum is 0, genus 0 wins (phase 2)
+        // the previous replicate's atomic has had a whole main loop to come back
+        if (ptask >= 0)
+            pg_epilogue_finish<8>(gmask, l4 == 0, lane & ~3, psum, genus0, gbase, vb8, 1 + ptask, margin, pend, mync, mycand);
+        psum[0] = s0; psum[1] = s1; psum[2] = s2; psum[3] = s3;
+        psum[4] = s4; psum[5] = s5; psum[6] = s6; psum[7] = s7;
+        ptask = task;
+        pg_epilogue_begin<8>(gmask, l4 == 0, psum, genus0, gbase, vb8, mychamp + 1 + task, pend);
+    }
+    if (ptask >= 0)
+        pg_epilogue_finish<8>(gmask, l4 == 0, lane & ~3, psum, genus0, gbase, vb8, 1 + ptask, margin, pend, mync, mycand);
+#undef PG_HROW
+#undef PG_HLQ
+}
+
 // ------------------------------------------------------------------ phase 0: most promising block
 
 // One warp per read: deficit sums over 16 evenly spaced words for every genus block; the block
@@ -571,7 +761,7 @@ k_guess_block(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ 
 __global__ void __launch_bounds__(256)
 k_guess_bm(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
            const int32_t *__restrict__ nwords, const int32_t *__restrict__ order, int nreads_b, int64_t slot0,
-           int ntile64, int ngroup, int32_t *__restrict__ guess)
+           int count, int per_group, int ngroup, int32_t *__restrict__ guess)
 {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -590,8 +780,9 @@ k_guess_bm(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, 
                 const uint32_t wj = __shfl_sync(0xffffffffu, wv, j);
                 acc += __ldg(bm + ((size_t)grp * PG_NWORDS + wj) * 32 + lane);
             }
-            const uint32_t blk = (uint32_t)grp * 32u + lane;
-            const uint32_t key = (int)blk < ntile64 ? ((acc << 12) | blk) : 0xFFFFFFFFu;   // acc < 2^17, blk < 2^12
+            // the table holds `count` units (blocks: 31 per group; half blocks: 32 per group)
+            const uint32_t blk = (uint32_t)grp * (uint32_t)per_group + lane;
+            const uint32_t key = ((int)lane < per_group && (int)blk < count) ? ((acc << 12) | blk) : 0xFFFFFFFFu;   // acc < 2^17, blk < 2^12
             bestkey = min(bestkey, __reduce_min_sync(0xffffffffu, key));
         }
         best = bestkey & 0xFFFu;
@@ -606,7 +797,7 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         int64_t slot0, const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot,
         int ntile64, double vmax, const unsigned long long *__restrict__ champ, const int32_t *__restrict__ guess,
         unsigned long long *__restrict__ items, unsigned int *__restrict__ item_count, unsigned int item_cap,
-        uint8_t *__restrict__ heavy, unsigned int light_max)
+        uint8_t *__restrict__ heavy, unsigned int light_max, const uint16_t *__restrict__ hm /* plan 3: guess[] holds half-block ids */)
 {
     constexpr int NUNIT = BLOCK / 8;                // quarter-warps: one task each, lane = four blocks (one LDS.64 per draw)
     extern __shared__ uint4 sB[];                   // (n+1) rows x 4 uint4 (32 blocks x 16 bit); row n is zero
@@ -632,11 +823,28 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
 
     const int unit = tid >> 3, hl = tid & 7;
     const unsigned qmask = 0xFFu << (tid & 24);
-    const int b0 = grp * 32 + 4 * hl;
-    const int best = guess[rc];
+    const int b0 = grp * PG_GB + 4 * hl;
+    // plan 3: the best block was evaluated on one half only; the other half competes here like a block of its
+    // own, its minima written into the spare slot 31 of the rows of the best block's group
+    const int gs = guess[rc];
+    const int best = hm ? gs >> 1 : gs;
+    const bool sib_here = hm && best / PG_GB == grp;
+    if (sib_here) {
+        const int sib = gs ^ 1;
+        const uint16_t *hcol = hm + (size_t)(sib >> 5) * PG_NWORDS * 32 + (sib & 31);
+        uint16_t *rows16 = reinterpret_cast<uint16_t *>(sB);
+        for (int j = tid; j < n; j += BLOCK) rows16[j * 32 + 31] = __ldg(hcol + (size_t)w[j] * 32);
+        __syncthreads();
+    }
     bool ok[4];
+    int okblk[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) ok[i] = b0 + i < ntile64 && b0 + i != best;
+    for (int i = 0; i < 4; i++) {
+        const int slot = 4 * hl + i;
+        okblk[i] = b0 + i;
+        ok[i] = slot < PG_GB && b0 + i < ntile64 && b0 + i != best;
+        if (slot == PG_GB) { ok[i] = sib_here; okblk[i] = best; }      // an open sibling half re-opens the whole block
+    }
     const char *base = reinterpret_cast<const char *>(sB) + hl * 8;
     const unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
 #define PG_BROW(o) (*reinterpret_cast<const uint2 *>(base + (o)))
@@ -707,15 +915,16 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
             PG_BSPILL()
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                if (lane_open && ok[i] && (unsigned long long)s[i] <= thr) PG_SURVIVE(1 + t, b0 + i)
+                if (lane_open && ok[i] && (unsigned long long)s[i] <= thr) PG_SURVIVE(1 + t, okblk[i])
         }
     }
     __syncthreads();
     if (tid < 32) {
-        const int blk = grp * 32 + tid;
+        const int blk = grp * PG_GB + tid;
         const unsigned long long cv = __ldg(mychamp);
         const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + pg_margin(n, vmax);
-        if (blk < ntile64 && blk != best && (unsigned long long)s_full[tid] <= thr) PG_SURVIVE(0, blk)
+        const bool real = tid < PG_GB && blk < ntile64 && blk != best;
+        if ((real || (tid == PG_GB && sib_here)) && (unsigned long long)s_full[tid] <= thr) PG_SURVIVE(0, real ? blk : best)
     }
     __syncthreads();
     const unsigned int cnt = s_cnt;
@@ -1088,10 +1297,16 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     if (noprune < 0) { const char *e = getenv("PG_NO_PRUNE"); noprune = (e && atoi(e)) ? 1 : 0; }
     int32_t *d_guess = cb.guess;
     if (noprune || md->ntile64 < 2) { d_guess = NULL; version = 1; }
+    // version 3 = plan 3 (half blocks, two reads per CTA, the default); 2 = plan 2 (whole best block);
+    // 1 = plan 1 (every block, partial-sum pruning)
     unsigned nblk_y = (unsigned)md->ntile64;
-    if (d_guess && version == 2) {
-        k_guess_bm<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_bmtable, d_words, d_off, d_nwords, d_order,
-                                                               (int)nreads_b, slot0, md->ntile64, md->ngroup, d_guess);
+    if (d_guess && version == 3) {
+        k_guess_bm<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_hmtable, d_words, d_off, d_nwords, d_order, (int)nreads_b,
+                                                               slot0, 2 * md->ntile64, 32, md->ngroup_h, d_guess);
+        PG_LAUNCHED(ctx);
+    } else if (d_guess && version == 2) {
+        k_guess_bm<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_bmtable, d_words, d_off, d_nwords, d_order, (int)nreads_b,
+                                                               slot0, md->ntile64, PG_GB, md->ngroup, d_guess);
         PG_LAUNCHED(ctx);
         nblk_y = 1;                                     // grid row 0 = the guessed block, in full
     } else if (d_guess) {
@@ -1101,15 +1316,30 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     }
     static int qblock = -1;                             // PG_Q_BLOCK=448: experiment switch for the first bucket
     if (qblock < 0) { const char *e = getenv("PG_Q_BLOCK"); qblock = e ? atoi(e) : 0; }
-    int rc;
-    if (bk.block == 192 && qblock != 448)
+    int rc = PG_OK;
+    if (d_guess && version == 3) {
+        const unsigned npair = (nreads_b + 1) / 2;
+#define PG_LAUNCH_H(B, M)                                                                                               \
+    {                                                                                                                   \
+        PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_h<B, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_classify_h<B, M><<<npair, B, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,   \
+                                                            (int)nreads_b, slot0, ctx->d_boot_pool, ctx->d_boot_off,    \
+                                                            min_boot, md->d_blockmask, md->vmax, cb.champ, cb.ncand,    \
+                                                            cb.cand, d_guess);                                          \
+        PG_LAUNCHED(ctx);                                                                                               \
+    }
+        if (bk.block == 192) PG_LAUNCH_H(192, 3)
+        else if (bk.block == 448) PG_LAUNCH_H(352, 2)
+        else PG_LAUNCH_H(832, 1)
+#undef PG_LAUNCH_H
+    } else if (bk.block == 192 && qblock != 448)
         rc = launch_q<192, 3>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
     else if (bk.block == 448 || bk.block == 192)
         rc = launch_q<448, 2>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
     else
         rc = launch_q<832, 1>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
     PG_TRY(rc);
-    if (!(d_guess && version == 2)) return PG_OK;
+    if (!(d_guess && version >= 2)) return PG_OK;
 
     int light_max = cb.light_max == 0 ? PG_LIGHT_MAX : (cb.light_max < 0 ? 0 : cb.light_max);
     if (light_max > PG_LIGHT_MAX) light_max = PG_LIGHT_MAX;
@@ -1119,7 +1349,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     k_bound<160><<<dim3(nreads_b, (unsigned)md->ngroup), 160, bsmem, ctx->stream>>>(
         md->d_bmtable, d_words, d_off, d_nwords, d_flags, d_order, slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot,
         md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.counters + 2, cb.item_cap, cb.heavy,
-        (unsigned int)light_max);
+        (unsigned int)light_max, version == 3 ? md->d_hmtable : NULL);
     PG_LAUNCHED(ctx);
     k_light<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_order - slot0, ctx->d_boot_pool,
                                                         ctx->d_boot_off, min_boot, md->d_blockmask, md->vmax, cb.items,

@@ -340,12 +340,12 @@ struct ClassifyJob {
         nkeys = PG_NUM_BOOT + 1;
         if (min_boot < 0 || min_boot > 64) return pg_fail(ctx, PG_EINVAL, "min_boot_words out of range");
         if (mode != 0 && mode != 1) return pg_fail(ctx, PG_EINVAL, "unknown classify mode %d", mode);
-        if (opts && (opts->cert_plan < 0 || opts->cert_plan > 1)) return pg_fail(ctx, PG_EINVAL, "unknown cert_plan %d", opts->cert_plan);
+        if (opts && (opts->cert_plan < 0 || opts->cert_plan > 2)) return pg_fail(ctx, PG_EINVAL, "unknown cert_plan %d", opts->cert_plan);
         if (count > 0x7fffffffLL) return pg_fail(ctx, PG_ERANGE, "more than 2^31-1 reads in one batch");
         certified = (mode == 1) && md->q_ok;
         static int env_v1 = -1;                         // PG_CERT_V1=1: the all-block kernel for every read (A/B switch)
         if (env_v1 < 0) { const char *e = getenv("PG_CERT_V1"); env_v1 = (e && atoi(e)) ? 1 : 0; }
-        cert_version = (env_v1 || (opts && opts->cert_plan == 1)) ? 1 : 2;
+        cert_version = (env_v1 || (opts && opts->cert_plan == 1)) ? 1 : ((opts && opts->cert_plan == 2) ? 2 : 3);
         ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
         ctx->st_heavy = ctx->st_items = 0;
         // Chunk of reads per pass.  Plan 1 walks every genus block of a chunk (tile-major grid) and wants the
@@ -399,25 +399,34 @@ struct ClassifyJob {
         return PG_OK;
     }
 
-    // stable counting sort of a list of reads by bucket -> h_dst, bucket extents in bcount/bstart/bmaxn
+    // stable counting sort of a list of reads by word count -> h_dst; buckets are ranges of n, so they come out
+    // contiguous (extents in bcount/bstart/bmaxn), and reads of equal length end up adjacent -- plan 3 pairs
+    // neighbours in one CTA and equal lengths share their sample lists
+    std::vector<int64_t> ncount;
     void bucket_sort(const int32_t *src, int64_t base, int64_t cn, int32_t *h_dst)
     {
-        int64_t fill[16];
-        for (int b = 0; b < 16; b++) bcount[b] = bmaxn[b] = 0;
-        for (int64_t i = 0; i < cn; i++) {
-            const int32_t r = src ? src[i] : (int32_t)(base + i);
-            int n = h_n[r], b = 0;
-            while (kBuckets[b].nmax < n) b++;
-            bcount[b]++;
-            if (n > bmaxn[b]) bmaxn[b] = n;
+        ncount.assign(PG_MAX_WORDS + 2, 0);
+        for (int64_t i = 0; i < cn; i++) ncount[(size_t)h_n[src ? src[i] : (int32_t)(base + i)] + 1]++;
+        for (int b = 0; b < 16; b++) bcount[b] = bstart[b] = bmaxn[b] = 0;
+        {
+            int b = 0;
+            int64_t acc = 0;
+            for (int n = 0; n <= PG_MAX_WORDS; n++) {
+                const int64_t c = ncount[(size_t)n + 1];
+                ncount[(size_t)n + 1] = 0;
+                if (c) {
+                    while (kBuckets[b].nmax < n) b++;
+                    if (!bcount[b]) bstart[b] = acc;
+                    bcount[b] += c;
+                    bmaxn[b] = n;
+                }
+                ncount[(size_t)n] = acc;                // start of the reads with n words
+                acc += c;
+            }
         }
-        int64_t acc = 0;
-        for (int b = 0; b < kNumBuckets; b++) { bstart[b] = fill[b] = acc; acc += bcount[b]; }
         for (int64_t i = 0; i < cn; i++) {
             const int32_t r = src ? src[i] : (int32_t)(base + i);
-            int n = h_n[r], b = 0;
-            while (kBuckets[b].nmax < n) b++;
-            h_dst[fill[b]++] = r;
+            h_dst[ncount[(size_t)h_n[r]]++] = r;
         }
     }
 
@@ -489,7 +498,7 @@ struct ClassifyJob {
                     ctx->ev_pending.push_back(std::make_pair(e0, e1));
                 }
                 PG_TRY(pg_certified_phase2(ctx, md, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords, d_flags, ord,
-                                           bstart[b], min_boot, cb, plan == 2, d_results, d_boot_winners));
+                                           bstart[b], min_boot, cb, plan >= 2, d_results, d_boot_winners));
             } else {
                 if (timed) ctx->st_strict += bcount[b];
                 PG_TRY(run_strict(bk, ord, bstart[b], (unsigned)bcount[b], nmax, timed));

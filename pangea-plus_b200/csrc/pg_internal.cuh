@@ -73,7 +73,9 @@ struct pg_model {
     int32_t  *d_perm;           // [ntile64*64] table position -> genus index (>= G: padding)
     unsigned long long *d_blockmask;   // [ntile64] bit i: position blk*64+i holds a genus
     uint16_t *d_bmtable;        // [ngroup][65536][32]   min over the 64 genera of block (group*32 + i)
-    int      ngroup;            // ceil(ntile64 / 32)
+    uint16_t *d_hmtable;        // [ngroup_h][65536][32]  min over each 32-position half block (2*block + half)
+    int      ngroup;            // ceil(ntile64 / 31): slot 31 of a bm row is spare (k_bound, plan 3)
+    int      ngroup_h;          // ceil(2*ntile64 / 32)
     double   vmax;              // max |table entry| over real genera (fp32 error bound)
     bool     q_ok;              // every deficit fits the 12-bit field: certificates are valid
     bool     committed;

@@ -173,7 +173,7 @@ extern "C" void pg_model_free(pg_model *md)
     cudaFree(md->d_m); cudaFree(md->d_table); cudaFree(md->d_nw); cudaFree(md->d_M);
     cudaFree(md->d_N); cudaFree(md->d_logPrior); cudaFree(md->d_Pw); cudaFree(md->d_logLeave);
     cudaFree(md->d_anc); cudaFree(md->d_qtable); cudaFree(md->d_rowmax);
-    cudaFree(md->d_perm); cudaFree(md->d_bmtable); cudaFree(md->d_blockmask);
+    cudaFree(md->d_perm); cudaFree(md->d_bmtable); cudaFree(md->d_blockmask); cudaFree(md->d_hmtable);
     delete md;
 }
 

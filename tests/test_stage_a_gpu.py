@@ -472,6 +472,10 @@ def test_certified_plans_agree(ctx, baseline_model):
     st = ctx.classify_stats()
     assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb)
     assert st["heavy"] == 0 and st["items"] == 0, st
+    got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True, cert_plan=2)     # whole best block, one read per CTA
+    st = ctx.classify_stats()
+    assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb)
+    assert st["items"] > 0, st
 
 
 def test_certified_without_lineage(ctx):
@@ -520,7 +524,7 @@ def test_certified_equals_strict_on_random_models(ctx, seed, genera, seqs, lengt
         reads.append(r.tobytes())
     data, off = pack_sequences(reads)
     want, wb = ctx.classify(gm, data, off, mode=0, want_boot=True)
-    for kw in (dict(), dict(cert_plan=1), dict(light_max=5)):
+    for kw in (dict(), dict(cert_plan=1), dict(cert_plan=2), dict(light_max=5)):
         got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True, **kw)
         assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb), kw
     om = ora.Model(tr["data"], tr["off"], tr["genus"], tr["G"])
