@@ -338,6 +338,13 @@ __device__ __forceinline__ void pg_epilogue_finish(unsigned mask, bool leader, i
         for (int i = 0; i < NV; i++) hit |= (sums[i] <= thr ? 1u : 0u) << i;
         hit &= vbits;
         if (took && bg - genus0 < (uint32_t)NV) hit &= ~(1u << (bg - genus0));
+        // a block evaluated a second time (plan 3: an open sibling half re-opens the best block) meets the
+        // standing champion again: it is not its own near-tie
+        if (!took && opos - genus0 < (uint32_t)NV) {
+#pragma unroll
+            for (int i = 0; i < NV; i++)
+                if (opos == genus0 + i && sums[i] == osum) hit &= ~(1u << i);
+        }
         if (hit) {
 #pragma unroll
             for (int i = 0; i < NV; i++)
@@ -815,27 +822,40 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     const uint16_t *w = words + off[read];
     const uint16_t *tb = bm + (size_t)grp * PG_NWORDS * 32;
     for (int c = tid; c < n * 4; c += BLOCK) pg_cp_async16(&sB[c], tb + (size_t)w[c >> 2] * 32 + (c & 3) * 8);
+    // plan 3: the best block was evaluated on one half only; the other half competes here like a block of its
+    // own, its minima written into the spare slot 31 of the rows of the best block's group (gathered while the
+    // cp.async copies are in flight, stored once they have landed)
+    const int gs = guess[rc];
+    const int best = hm ? gs >> 1 : gs;
+    const bool sib_here = hm && best / PG_GB == grp;
+    const uint16_t *hcol = hm ? hm + (size_t)((gs ^ 1) >> 5) * PG_NWORDS * 32 + ((gs ^ 1) & 31) : NULL;
+    uint16_t hv[4] = {0, 0, 0, 0};
+    if (sib_here) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = tid + u * BLOCK;
+            if (j < n) hv[u] = __ldg(hcol + (size_t)w[j] * 32);
+        }
+    }
     if (tid < 4) sB[n * 4 + tid] = make_uint4(0u, 0u, 0u, 0u);
     if (tid < 32) s_full[tid] = 0u;
     if (tid == 0) s_cnt = 0u;
     pg_cp_async_wait_all();
     __syncthreads();
+    if (sib_here) {
+        uint16_t *rows16 = reinterpret_cast<uint16_t *>(sB);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int j = tid + u * BLOCK;
+            if (j < n) rows16[j * 32 + 31] = hv[u];
+        }
+        for (int j = tid + 4 * BLOCK; j < n; j += BLOCK) rows16[j * 32 + 31] = __ldg(hcol + (size_t)w[j] * 32);
+        __syncthreads();
+    }
 
     const int unit = tid >> 3, hl = tid & 7;
     const unsigned qmask = 0xFFu << (tid & 24);
     const int b0 = grp * PG_GB + 4 * hl;
-    // plan 3: the best block was evaluated on one half only; the other half competes here like a block of its
-    // own, its minima written into the spare slot 31 of the rows of the best block's group
-    const int gs = guess[rc];
-    const int best = hm ? gs >> 1 : gs;
-    const bool sib_here = hm && best / PG_GB == grp;
-    if (sib_here) {
-        const int sib = gs ^ 1;
-        const uint16_t *hcol = hm + (size_t)(sib >> 5) * PG_NWORDS * 32 + (sib & 31);
-        uint16_t *rows16 = reinterpret_cast<uint16_t *>(sB);
-        for (int j = tid; j < n; j += BLOCK) rows16[j * 32 + 31] = __ldg(hcol + (size_t)w[j] * 32);
-        __syncthreads();
-    }
     bool ok[4];
     int okblk[4];
 #pragma unroll
@@ -843,7 +863,7 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         const int slot = 4 * hl + i;
         okblk[i] = b0 + i;
         ok[i] = slot < PG_GB && b0 + i < ntile64 && b0 + i != best;
-        if (slot == PG_GB) { ok[i] = sib_here; okblk[i] = best; }      // an open sibling half re-opens the whole block
+        if (slot == PG_GB) { ok[i] = sib_here; okblk[i] = 0x8000 | (((gs ^ 1) & 1) << 14) | best; }   // half item: the sibling half only
     }
     const char *base = reinterpret_cast<const char *>(sB) + hl * 8;
     const unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
@@ -924,7 +944,8 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         const unsigned long long cv = __ldg(mychamp);
         const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + pg_margin(n, vmax);
         const bool real = tid < PG_GB && blk < ntile64 && blk != best;
-        if ((real || (tid == PG_GB && sib_here)) && (unsigned long long)s_full[tid] <= thr) PG_SURVIVE(0, real ? blk : best)
+        if ((real || (tid == PG_GB && sib_here)) && (unsigned long long)s_full[tid] <= thr)
+            PG_SURVIVE(0, real ? blk : (0x8000 | (((gs ^ 1) & 1) << 14) | best))
     }
     __syncthreads();
     const unsigned int cnt = s_cnt;
@@ -975,7 +996,11 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
         const unsigned long long e = items[it];
         const int task = (int)((e >> 16) & 0xFFFFu);
         if (task == (int)PG_ITEM_NULL) continue;
-        const int blk = (int)(e & 0xFFFFu);
+        // block field: bit 15 = half item (plan 3: only one 32-position half is open), bit 14 = which half
+        const bool half_item = ((e >> 15) & 1ULL) != 0ULL;
+        const int which = (int)((e >> 14) & 1ULL);
+        const int blk = (int)(e & 0x3FFFu);
+        const bool lane_on = !half_item || (l >> 2) == which;
         const size_t rc = (size_t)(e >> 32);
         const int64_t read = order_base[rc];
         const int n = nwords[read];
@@ -1014,12 +1039,12 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
             uint4 v[8];
 #pragma unroll
             for (int u = 0; u < 8; u++)
-                v[u] = wi[u] != 0xFFFFFFFFu ? __ldg(tb + (size_t)wi[u] * 8) : make_uint4(0u, 0u, 0u, 0u);
+                v[u] = (wi[u] != 0xFFFFFFFFu && lane_on) ? __ldg(tb + (size_t)wi[u] * 8) : make_uint4(0u, 0u, 0u, 0u);
             uint32_t c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u;
 #pragma unroll
             for (int u = 0; u < 8; u++) { PG_QADD4(v[u]) }
             PG_QSPILL()
-            const uint32_t smin = min(min(min(s0, s1), min(s2, s3)), min(min(s4, s5), min(s6, s7)));
+            const uint32_t smin = lane_on ? min(min(min(s0, s1), min(s2, s3)), min(min(s4, s5), min(s6, s7))) : 0xFFFFFFFFu;
             const unsigned over = __ballot_sync(gmask, (unsigned long long)smin > thr);
             if (((over >> gshift) & 0xFFu) == 0xFFu) { pruned = true; break; }
         }
@@ -1027,7 +1052,7 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
         const uint32_t sums[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
         const uint32_t gbase = (uint32_t)blk * 64u;
         PgPending pend;
-        const uint32_t vb8 = (uint32_t)(__ldg(blockmask + blk) >> (8 * l)) & 0xFFu;
+        const uint32_t vb8 = lane_on ? (uint32_t)(__ldg(blockmask + blk) >> (8 * l)) & 0xFFu : 0u;
         pg_epilogue_begin<8>(gmask, l == 0, sums, gbase + (uint32_t)l * 8u, gbase, vb8, slot, pend);
         pg_epilogue_finish<8>(gmask, l == 0, gshift, sums, gbase + (uint32_t)l * 8u, gbase, vb8, task, margin, pend,
                               ncand + rc, cand + rc * PG_CANDCAP);
