@@ -84,9 +84,11 @@ __global__ void k_quantise(const float *__restrict__ table, const float *__restr
 }
 
 // Lower-bound tables.  bm: per (word, block) the minimum deficit over the block's 64 positions (padding holds
-// PG_Q_MAX and never wins).  A group is PG_GB = 31 blocks: bm[group][w][slot], slot 31 of every 64-byte row is
-// spare -- k_bound puts the minima of the best block's other half there (plan 3).
-#define PG_GB 31
+// PG_Q_MAX and never wins).  A group is PG_GB = 29 blocks: bm[group][w][slot], the last PG_PARTS - 1 slots of
+// every 64-byte row are spare -- k_bound puts the minima of the best block's other parts there (plan 3).
+#define PG_PARTS 4                       // plan 3 evaluates one part (64 / PG_PARTS positions) of the best block
+#define PG_PART_POS (64 / PG_PARTS)
+#define PG_GB (32 - (PG_PARTS - 1))
 __global__ void k_blockmin(const uint16_t *__restrict__ q, int ntile64, int ngroup, uint16_t *__restrict__ bm)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,8 +111,9 @@ __global__ void k_blockmin(const uint16_t *__restrict__ q, int ntile64, int ngro
     bm[((size_t)grp * PG_NWORDS + w) * 32 + slot] = (uint16_t)m;
 }
 
-// hm: per (word, half block) the minimum over the half's 32 positions; hm[hb / 32][w][hb % 32], hb = 2*block + half
-__global__ void k_halfmin(const uint16_t *__restrict__ q, int ntile64, uint16_t *__restrict__ hm)
+// hm: per (word, part) the minimum over the part's positions; hm[pb / 32][w][pb % 32], pb = PG_PARTS*block + part
+// (the parts of one block are adjacent slots of one row)
+__global__ void k_partmin(const uint16_t *__restrict__ q, int ntile64, uint16_t *__restrict__ hm)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int w = (int)(idx & (PG_NWORDS - 1));
@@ -118,16 +121,16 @@ __global__ void k_halfmin(const uint16_t *__restrict__ q, int ntile64, uint16_t 
     if (blk >= ntile64) return;
     const uint4 *row = reinterpret_cast<const uint4 *>(q + ((size_t)blk * PG_NWORDS + w) * 64);
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
+    for (int h = 0; h < PG_PARTS; h++) {
         uint32_t m = 0xFFFFu;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint4 v = row[h * 4 + i];
+        for (int i = 0; i < 8 / PG_PARTS; i++) {
+            const uint4 v = row[h * (8 / PG_PARTS) + i];
             const uint32_t a = __vminu2(__vminu2(v.x, v.y), __vminu2(v.z, v.w));
             m = min(m, min(a & 0xFFFFu, a >> 16));
         }
-        const int hb = 2 * blk + h;
-        hm[((size_t)(hb >> 5) * PG_NWORDS + w) * 32 + (hb & 31)] = (uint16_t)m;
+        const int pb = PG_PARTS * blk + h;
+        hm[((size_t)(pb >> 5) * PG_NWORDS + w) * 32 + (pb & 31)] = (uint16_t)m;
     }
 }
 
@@ -153,7 +156,7 @@ int pg_model_set_layout(pg_model *md, const int32_t *pos_host, int npos)
     }
     md->ntile64 = nblk;
     md->ngroup = (nblk + PG_GB - 1) / PG_GB;
-    md->ngroup_h = (2 * nblk + 31) / 32;
+    md->ngroup_h = (PG_PARTS * nblk + 31) / 32;
     if (!md->d_perm) {
         PG_CUDA(ctx, cudaMalloc(&md->d_perm, full.size() * 4));
         PG_CUDA(ctx, cudaMalloc(&md->d_blockmask, mask.size() * 8));
@@ -247,7 +250,7 @@ int pg_model_derive_quantised(pg_model *md)
     k_blockmin<<<(unsigned)((bmcells + 255) / 256), 256, 0, ctx->stream>>>(md->d_qtable, md->ntile64, md->ngroup, md->d_bmtable);
     PG_LAUNCHED(ctx);
     PG_CUDA(ctx, cudaMemsetAsync(md->d_hmtable, 0xFF, (size_t)md->ngroup_h * PG_NWORDS * 32 * 2, ctx->stream));
-    k_halfmin<<<(unsigned)(((size_t)md->ntile64 * PG_NWORDS + 255) / 256), 256, 0, ctx->stream>>>(md->d_qtable, md->ntile64,
+    k_partmin<<<(unsigned)(((size_t)md->ntile64 * PG_NWORDS + 255) / 256), 256, 0, ctx->stream>>>(md->d_qtable, md->ntile64,
                                                                                                   md->d_hmtable);
     PG_LAUNCHED(ctx);
     unsigned int stat[2];
@@ -551,15 +554,15 @@ k_classify_q(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
 #undef PG_QROW
 }
 
-// ------------------------------------------------------------------ plan 3: half blocks, two reads per CTA
+// ------------------------------------------------------------------ plan 3: one part of the best block, PG_PARTS reads per CTA
 //
 // k_classify_q spends one 128-byte shared-memory wavefront per (task, draw): a row of 64 positions.  Most of
-// those 64 are irrelevant even inside the best block, so plan 3 evaluates only the better HALF of it (32
-// positions, a 64-byte row) and leaves the other half to the lower bounds like any other block (k_bound gets
-// the sibling half's minima in the spare 32nd slot of its rows).  Two reads share a CTA and interleave their
-// rows -- row r = [read A: 64 bytes | read B: 64 bytes] -- so that the two 4-lane groups of a quarter-warp
-// (one task of A, the same task of B) always hit different banks: one wavefront now serves two (task, draw)
-// pairs, and reads of equal length (adjacent in the order array) share their sample-list loads.
+// those 64 are irrelevant even inside the best block, so plan 3 evaluates only the best PART of it
+// (PG_PART_POS = 16 positions, a 32-byte row) and leaves the other parts to the lower bounds like any other
+// block (k_bound gets their minima in the spare slots of its rows).  PG_PARTS reads share a CTA and interleave
+// their rows -- row r = [read 0: 32 bytes | read 1 | read 2 | read 3] -- so that the groups of a quarter-warp
+// (the same task of the four reads) always hit different banks: one wavefront serves four (task, draw) pairs,
+// and reads of equal length (adjacent in the order array) load the same sample-list entries.
 template <int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_classify_h(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
@@ -568,55 +571,59 @@ k_classify_h(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
              const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot,
              const unsigned long long *__restrict__ blockmask, double vmax,
              unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand,
-             unsigned long long *__restrict__ cand, const int32_t *__restrict__ guess /* half-block ids */)
+             unsigned long long *__restrict__ cand, const int32_t *__restrict__ guess /* part ids */)
 {
-    constexpr int NGR = (BLOCK - 32) / 8;           // task slots per read: a quarter-warp = one slot of A + one of B
-    extern __shared__ uint4 sQ[];                   // (nmax+1) rows x 8 uint4: [A 4 | B 4]; row n of a read is zero
+    constexpr int R = PG_PARTS;                     // reads per CTA
+    constexpr int GL = 8 / R;                       // lanes per (read, task) group: GL x 8 positions
+    constexpr int NGR = (BLOCK - 32) / 8;           // task slots per read: a quarter-warp = one slot of every read
+    constexpr int FL = 32 / R;                      // full-sum lanes per read
+    extern __shared__ uint4 sQ[];                   // (nmax+1) rows x 8 uint4: GL per read; row n of a read is zero
     const int tid = threadIdx.x, lane = tid & 31;
 
-    // ---- the two reads of this CTA (B may be missing, either may be short or wordless)
-    int n2[2], hb2[2];
-    size_t rc2[2];
-    const uint16_t *w2[2];
+    // ---- the reads of this CTA (some may be missing, short or wordless: n = 0); this thread's read = sel
+    const int sel = tid < 32 ? lane / FL : (lane / GL) % R;
+    int n = 0, pb = 0, nmaxr = 0;
+    size_t rc = 0;
 #pragma unroll
-    for (int s = 0; s < 2; s++) {
-        const int slot = 2 * (int)blockIdx.x + s;
-        n2[s] = 0; hb2[s] = 0; rc2[s] = 0; w2[s] = words;
+    for (int s = 0; s < R; s++) {
+        const int slot = R * (int)blockIdx.x + s;
+        int ns = 0, ps = 0;
+        const uint16_t *ws = words;
+        size_t rcs = 0;
         if (slot < nreads_b) {
             const int64_t read = order[slot];
             if (!flags[2 * read + 1]) {
-                n2[s] = nwords[read];
-                w2[s] = words + off[read];
-                rc2[s] = (size_t)slot0 + slot;
-                hb2[s] = guess[rc2[s]];
+                ns = nwords[read];
+                ws = words + off[read];
+                rcs = (size_t)slot0 + slot;
+                ps = guess[rcs];
             }
         }
-    }
-    if (n2[0] == 0 && n2[1] == 0) return;
-
-    // ---- stage the two reads' half rows
-#pragma unroll
-    for (int s = 0; s < 2; s++) {
-        const int n = n2[s];
-        const uint16_t *tb = qtable + (size_t)(hb2[s] >> 1) * PG_NWORDS * 64 + (hb2[s] & 1) * 32;
-        for (int c = tid; c < n * 4; c += BLOCK) {
-            const int r = c >> 2, l = c & 3;
-            pg_cp_async16(&sQ[r * 8 + s * 4 + l], tb + (size_t)w2[s][r] * 64 + l * 8);
+        // stage read s: its part of the best block, GL 16-byte chunks per row
+        const uint16_t *tb = qtable + (size_t)(ps / R) * PG_NWORDS * 64 + (ps % R) * PG_PART_POS;
+        for (int c = tid; c < ns * GL; c += BLOCK) {
+            const int r = c / GL, l = c % GL;
+            pg_cp_async16(&sQ[r * 8 + s * GL + l], tb + (size_t)ws[r] * 64 + l * 8);
         }
-        if (tid < 4) sQ[n * 8 + s * 4 + tid] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < GL) sQ[ns * 8 + s * GL + tid] = make_uint4(0u, 0u, 0u, 0u);
+        if (s == sel) { n = ns; pb = ps; rc = rcs; }
+        nmaxr = ns > nmaxr ? ns : nmaxr;
     }
+    if (nmaxr == 0) return;
     pg_cp_async_wait_all();
     __syncthreads();
+    const uint32_t gbase = (uint32_t)(pb / R) * 64u, pbase = gbase + (uint32_t)(pb % R) * PG_PART_POS;
+    const unsigned long long bmask = blockmask[pb / R];
+    unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
+    unsigned int *mync = ncand + rc;
+    unsigned long long *mycand = cand + rc * PG_CANDCAP;
 
     if (tid < 32) {
-        // ---- full sums (task 0): lanes 0-15 read A, 16-31 read B; lane = one packed pair of positions
-        const int s = lane >> 4, hl = lane & 15;
-        const int n = s ? n2[1] : n2[0];
-        const int hb = s ? hb2[1] : hb2[0];
-        const size_t rc = s ? rc2[1] : rc2[0];
-        const unsigned hmask = 0xFFFFu << (s * 16);
+        // ---- full sums (task 0): FL lanes per read, lane = one packed pair of positions = word `lane` of the row
         if (n == 0) return;
-        const uint32_t *col = reinterpret_cast<const uint32_t *>(sQ) + s * 16 + hl;
+        const int hl = lane % FL;
+        const unsigned hmask = (FL == 32 ? 0xFFFFFFFFu : ((1u << FL) - 1u)) << (sel * FL);
+        const uint32_t *col = reinterpret_cast<const uint32_t *>(sQ) + lane;
         uint32_t lo = 0u, hi = 0u;
         int j = 0;
         for (; j + 16 <= n; j += 16) {
@@ -631,40 +638,31 @@ k_classify_h(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
         lo += c & 0xFFFFu;
         hi += c >> 16;
         const uint32_t sums[2] = {lo, hi};
-        const uint32_t gbase = (uint32_t)(hb >> 1) * 64u, g0 = gbase + (uint32_t)(hb & 1) * 32u + 2u * hl;
-        const uint32_t vb2 = (uint32_t)(blockmask[hb >> 1] >> (g0 - gbase)) & 3u;
-        unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
+        const uint32_t g0 = pbase + 2u * hl;
+        const uint32_t vb2 = (uint32_t)(bmask >> (g0 - gbase)) & 3u;
         PgPending pp;
         pg_epilogue_begin<2>(hmask, hl == 0, sums, g0, gbase, vb2, mychamp, pp);
-        pg_epilogue_finish<2>(hmask, hl == 0, s * 16, sums, g0, gbase, vb2, 0, pg_margin(n, vmax), pp, ncand + rc,
-                              cand + rc * PG_CANDCAP);
+        pg_epilogue_finish<2>(hmask, hl == 0, sel * FL, sums, g0, gbase, vb2, 0, pg_margin(n, vmax), pp, mync, mycand);
         return;
     }
 
-    // ---- replicates (tasks 1..100): 4 lanes per (read, task); groups g8 = 2*slot + read
-    const int g8 = lane >> 2, l4 = lane & 3, s = g8 & 1;
-    const int group = ((tid - 32) >> 5) * 4 + (g8 >> 1);
-    const int n = s ? n2[1] : n2[0], no = s ? n2[0] : n2[1];
-    const int hb = s ? hb2[1] : hb2[0];
-    const size_t rc = s ? rc2[1] : rc2[0];
+    // ---- replicates (tasks 1..100): GL lanes per (read, task); quarter-warp = the task slot, groups = the reads
+    const int lg = lane % GL;
+    const int group = ((tid - 32) >> 5) * 4 + (lane >> 3);
     int k = n >> 3;
     if (k < min_boot) k = min_boot;
     const int nb = n > 0 ? (k + 3) >> 2 : 0;
-    // both reads of the quarter-warp walk the same number of batches (a finished one just stops loading)
-    int ko = no >> 3;
-    if (ko < min_boot) ko = min_boot;
-    const int nbo = no > 0 ? (ko + 3) >> 2 : 0;
-    const int nbmax = nb > nbo ? nb : nbo;
+    // the reads of a CTA walk the same number of batches (a finished one just stops loading)
+    int kmax = nmaxr >> 3;
+    if (kmax < min_boot) kmax = min_boot;
+    const int nbmax = (kmax + 3) >> 2;
     if (nbmax == 0) return;
-    const unsigned gmask = 0xFu << (lane & ~3);
+    const unsigned gmask = ((1u << GL) - 1u) << (lane - lg);
     const uint4 *lists = reinterpret_cast<const uint4 *>(boot_pool + boot_off[n]);
-    const char *lane_base = reinterpret_cast<const char *>(sQ) + s * 64 + l4 * 16;
+    const char *lane_base = reinterpret_cast<const char *>(sQ) + sel * (GL * 16) + lg * 16;
     const uint32_t margin = pg_margin(k, vmax);
-    const uint32_t gbase = (uint32_t)(hb >> 1) * 64u, genus0 = gbase + (uint32_t)(hb & 1) * 32u + 8u * l4;
-    const uint32_t vb8 = (uint32_t)(blockmask[hb >> 1] >> (genus0 - gbase)) & 0xFFu;
-    unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
-    unsigned int *mync = ncand + rc;
-    unsigned long long *mycand = cand + rc * PG_CANDCAP;
+    const uint32_t genus0 = pbase + 8u * lg;
+    const uint32_t vb8 = (uint32_t)(bmask >> (genus0 - gbase)) & 0xFFu;
     const uint32_t zoff = (uint32_t)n * PG_ROW_PITCH;
     const uint4 zq = make_uint4(zoff, zoff, zoff, zoff);
 #define PG_HROW(o) (*reinterpret_cast<const uint4 *>(lane_base + (o)))
@@ -697,14 +695,14 @@ k_classify_h(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ w
         if (nb == 0) continue;                          // k == 0: every sum is 0, genus 0 wins (phase 2)
         // the previous replicate's atomic has had a whole main loop to come back
         if (ptask >= 0)
-            pg_epilogue_finish<8>(gmask, l4 == 0, lane & ~3, psum, genus0, gbase, vb8, 1 + ptask, margin, pend, mync, mycand);
+            pg_epilogue_finish<8>(gmask, lg == 0, lane - lg, psum, genus0, gbase, vb8, 1 + ptask, margin, pend, mync, mycand);
         psum[0] = s0; psum[1] = s1; psum[2] = s2; psum[3] = s3;
         psum[4] = s4; psum[5] = s5; psum[6] = s6; psum[7] = s7;
         ptask = task;
-        pg_epilogue_begin<8>(gmask, l4 == 0, psum, genus0, gbase, vb8, mychamp + 1 + task, pend);
+        pg_epilogue_begin<8>(gmask, lg == 0, psum, genus0, gbase, vb8, mychamp + 1 + task, pend);
     }
     if (ptask >= 0)
-        pg_epilogue_finish<8>(gmask, l4 == 0, lane & ~3, psum, genus0, gbase, vb8, 1 + ptask, margin, pend, mync, mycand);
+        pg_epilogue_finish<8>(gmask, lg == 0, lane - lg, psum, genus0, gbase, vb8, 1 + ptask, margin, pend, mync, mycand);
 #undef PG_HROW
 #undef PG_HLQ
 }
@@ -822,19 +820,19 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     const uint16_t *w = words + off[read];
     const uint16_t *tb = bm + (size_t)grp * PG_NWORDS * 32;
     for (int c = tid; c < n * 4; c += BLOCK) pg_cp_async16(&sB[c], tb + (size_t)w[c >> 2] * 32 + (c & 3) * 8);
-    // plan 3: the best block was evaluated on one half only; the other half competes here like a block of its
-    // own, its minima written into the spare slot 31 of the rows of the best block's group (gathered while the
-    // cp.async copies are in flight, stored once they have landed)
+    // plan 3: the best block was evaluated on one part only; its other parts compete here like blocks of their
+    // own, their minima written into the spare slots PG_GB..31 of the rows of the best block's group (gathered
+    // while the cp.async copies are in flight, stored once they have landed)
     const int gs = guess[rc];
-    const int best = hm ? gs >> 1 : gs;
+    const int best = hm ? gs / PG_PARTS : gs, own = hm ? gs % PG_PARTS : 0;
     const bool sib_here = hm && best / PG_GB == grp;
-    const uint16_t *hcol = hm ? hm + (size_t)((gs ^ 1) >> 5) * PG_NWORDS * 32 + ((gs ^ 1) & 31) : NULL;
-    uint16_t hv[4] = {0, 0, 0, 0};
+    const uint16_t *hrow = hm ? hm + (size_t)((best * PG_PARTS) >> 5) * PG_NWORDS * 32 + ((best * PG_PARTS) & 31) : NULL;
+    uint2 hv[4];
     if (sib_here) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int j = tid + u * BLOCK;
-            if (j < n) hv[u] = __ldg(hcol + (size_t)w[j] * 32);
+            hv[u] = j < n ? __ldg(reinterpret_cast<const uint2 *>(hrow + (size_t)w[j] * 32)) : make_uint2(0u, 0u);
         }
     }
     if (tid < 4) sB[n * 4 + tid] = make_uint4(0u, 0u, 0u, 0u);
@@ -844,12 +842,16 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     __syncthreads();
     if (sib_here) {
         uint16_t *rows16 = reinterpret_cast<uint16_t *>(sB);
+        auto put = [&](int j, uint2 v) {
+            const unsigned long long all = ((unsigned long long)v.y << 32) | v.x;     // the block's four part minima
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int j = tid + u * BLOCK;
-            if (j < n) rows16[j * 32 + 31] = hv[u];
-        }
-        for (int j = tid + 4 * BLOCK; j < n; j += BLOCK) rows16[j * 32 + 31] = __ldg(hcol + (size_t)w[j] * 32);
+            for (int jj = 0; jj < PG_PARTS - 1; jj++)
+                rows16[j * 32 + PG_GB + jj] = (uint16_t)(all >> (16 * (jj < own ? jj : jj + 1)));
+        };
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (tid + u * BLOCK < n) put(tid + u * BLOCK, hv[u]);
+        for (int j = tid + 4 * BLOCK; j < n; j += BLOCK) put(j, __ldg(reinterpret_cast<const uint2 *>(hrow + (size_t)w[j] * 32)));
         __syncthreads();
     }
 
@@ -863,7 +865,11 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         const int slot = 4 * hl + i;
         okblk[i] = b0 + i;
         ok[i] = slot < PG_GB && b0 + i < ntile64 && b0 + i != best;
-        if (slot == PG_GB) { ok[i] = sib_here; okblk[i] = 0x8000 | (((gs ^ 1) & 1) << 14) | best; }   // half item: the sibling half only
+        if (slot >= PG_GB) {                        // part item: that sibling part of the best block only
+            const int jj = slot - PG_GB;
+            ok[i] = sib_here;
+            okblk[i] = 0x8000 | ((jj < own ? jj : jj + 1) << 13) | best;
+        }
     }
     const char *base = reinterpret_cast<const char *>(sB) + hl * 8;
     const unsigned long long *mychamp = champ + rc * (PG_NUM_BOOT + 1);
@@ -944,8 +950,9 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         const unsigned long long cv = __ldg(mychamp);
         const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + pg_margin(n, vmax);
         const bool real = tid < PG_GB && blk < ntile64 && blk != best;
-        if ((real || (tid == PG_GB && sib_here)) && (unsigned long long)s_full[tid] <= thr)
-            PG_SURVIVE(0, real ? blk : (0x8000 | (((gs ^ 1) & 1) << 14) | best))
+        const int jj = tid - PG_GB;
+        if ((real || (tid >= PG_GB && sib_here)) && (unsigned long long)s_full[tid] <= thr)
+            PG_SURVIVE(0, real ? blk : (0x8000 | ((jj < own ? jj : jj + 1) << 13) | best))
     }
     __syncthreads();
     const unsigned int cnt = s_cnt;
@@ -996,11 +1003,11 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
         const unsigned long long e = items[it];
         const int task = (int)((e >> 16) & 0xFFFFu);
         if (task == (int)PG_ITEM_NULL) continue;
-        // block field: bit 15 = half item (plan 3: only one 32-position half is open), bit 14 = which half
-        const bool half_item = ((e >> 15) & 1ULL) != 0ULL;
-        const int which = (int)((e >> 14) & 1ULL);
-        const int blk = (int)(e & 0x3FFFu);
-        const bool lane_on = !half_item || (l >> 2) == which;
+        // block field: bit 15 = part item (plan 3: only one part of the block is open), bits 13-14 = which part
+        const bool part_item = ((e >> 15) & 1ULL) != 0ULL;
+        const int which = (int)((e >> 13) & 3ULL);
+        const int blk = (int)(e & 0x1FFFu);
+        const bool lane_on = !part_item || l / (8 / PG_PARTS) == which;
         const size_t rc = (size_t)(e >> 32);
         const int64_t read = order_base[rc];
         const int n = nwords[read];
@@ -1327,7 +1334,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     unsigned nblk_y = (unsigned)md->ntile64;
     if (d_guess && version == 3) {
         k_guess_bm<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_hmtable, d_words, d_off, d_nwords, d_order, (int)nreads_b,
-                                                               slot0, 2 * md->ntile64, 32, md->ngroup_h, d_guess);
+                                                               slot0, PG_PARTS * md->ntile64, 32, md->ngroup_h, d_guess);
         PG_LAUNCHED(ctx);
     } else if (d_guess && version == 2) {
         k_guess_bm<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_bmtable, d_words, d_off, d_nwords, d_order, (int)nreads_b,
@@ -1343,7 +1350,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     if (qblock < 0) { const char *e = getenv("PG_Q_BLOCK"); qblock = e ? atoi(e) : 0; }
     int rc = PG_OK;
     if (d_guess && version == 3) {
-        const unsigned npair = (nreads_b + 1) / 2;
+        const unsigned npair = (nreads_b + PG_PARTS - 1) / PG_PARTS;
 #define PG_LAUNCH_H(B, M)                                                                                               \
     {                                                                                                                   \
         PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_h<B, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
@@ -1369,6 +1376,8 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     int light_max = cb.light_max == 0 ? PG_LIGHT_MAX : (cb.light_max < 0 ? 0 : cb.light_max);
     if (light_max > PG_LIGHT_MAX) light_max = PG_LIGHT_MAX;
     PG_CUDA(ctx, cudaMemsetAsync(cb.counters + 2, 0, 4, ctx->stream));
+    // (a two-reads-per-CTA k_bound with interleaved rows, like k_classify_h, was measured: same wavefronts,
+    // 46 % more instructions, 28 % slower -- LDS.64 rows of 64 bytes gain nothing from the interleave)
     const size_t bsmem = (size_t)(nmax + 1) * 64;
     PG_CUDA(ctx, cudaFuncSetAttribute(k_bound<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
     k_bound<160><<<dim3(nreads_b, (unsigned)md->ngroup), 160, bsmem, ctx->stream>>>(
