@@ -326,6 +326,7 @@ struct ClassifyJob {
     int32_t *d_order;
     PgCertBufs cb;
     int32_t *h_n, *h_order;
+    int64_t *h_off;
     std::vector<char> seen;
     std::vector<int32_t> redone;                 // reads whose records were rewritten by finish()
     int64_t bcount[16], bstart[16], bmaxn[16];
@@ -356,9 +357,10 @@ struct ClassifyJob {
         CHUNK = !certified ? ((int64_t)1 << 20) : ((int64_t)1 << (chunk_override ? chunk_override : (cert_version == 1 ? 14 : 16)));
         cmax = count < CHUNK ? count : CHUNK;
         if (cmax < 1) cmax = 1;
-        PG_TRY(pg_pinned(ctx, (size_t)count * 8 + 64));
+        PG_TRY(pg_pinned(ctx, (size_t)count * 16 + 128));
         h_n = (int32_t *)ctx->h_pin;
         h_order = h_n + count;
+        h_off = (int64_t *)(h_order + count + 2);        // rebased read offsets of pg_classify()'s uploads
         seen.assign(PG_MAX_WORDS + 1, 0);
         redone.clear();
         PG_TRY(pg_scratch(ctx, &ctx->s_best, (size_t)cmax * nkeys * 8));
@@ -658,16 +660,14 @@ static __global__ void k_gather_words(const uint32_t *__restrict__ src, int word
 
 // Host ASCII in, host records out.  Three things overlap: the upload of range i+1 (copy stream), the
 // kernels of range i (compute stream) and the download of the records of range i-1 (copy stream).
-extern "C" int pg_classify(pg_ctx *ctx, const pg_model *md, const pg_seqbatch *reads, const pg_classify_opts *opts,
-                           pg_result *results_host, int32_t *boot_winners_host)
+static int classify_host_batch(pg_ctx *ctx, const pg_model *md, const pg_seqbatch *reads, const pg_classify_opts *opts,
+                               pg_result *results_host, int32_t *boot_winners_host)
 {
-    if (!ctx || !md || !reads || !results_host || reads->count < 0)
-        return pg_fail(ctx, PG_EINVAL, "pg_classify: bad arguments");
-    if (!md->committed) return pg_fail(ctx, PG_EINVAL, "pg_classify: model has no tables (commit it first)");
-    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    // reads->off need not start at 0 (a slice of a larger batch): device offsets are rebased to off[0]
     const int64_t n = reads->count;
     if (n == 0) return PG_OK;
-    const int64_t total = reads->off[n];
+    const int64_t base0 = reads->off[0];
+    const int64_t total = reads->off[n] - base0;
     PG_TRY(pg_scratch(ctx, &ctx->s_bytes, (size_t)total + 64));
     PG_TRY(pg_scratch(ctx, &ctx->s_off, (size_t)(n + 1) * 8));
     const size_t nch = (size_t)(total >> 5) + n + 2;
@@ -701,8 +701,9 @@ extern "C" int pg_classify(pg_ctx *ctx, const pg_model *md, const pg_seqbatch *r
     auto prepare = [&](int64_t r0, int64_t r1, cudaEvent_t *ev) -> int {
         // upload on the copy stream, then pack + extract + word counts on the compute stream
         const int64_t b0 = reads->off[r0], b1 = reads->off[r1];
-        PG_CUDA(ctx, cudaMemcpyAsync(d_bytes + b0, reads->bytes + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
-        PG_CUDA(ctx, cudaMemcpyAsync(d_off + r0, reads->off + r0, (size_t)(r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, cs));
+        for (int64_t r = r0; r <= r1; r++) job.h_off[r] = reads->off[r] - base0;
+        PG_CUDA(ctx, cudaMemcpyAsync(d_bytes + (b0 - base0), reads->bytes + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, cs));
+        PG_CUDA(ctx, cudaMemcpyAsync(d_off + r0, job.h_off + r0, (size_t)(r1 - r0 + 1) * 8, cudaMemcpyHostToDevice, cs));
         cudaEvent_t up = take_event(ctx);
         PG_CUDA(ctx, cudaEventRecord(up, cs));
         PG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
@@ -758,6 +759,43 @@ extern "C" int pg_classify(pg_ctx *ctx, const pg_model *md, const pg_seqbatch *r
             if (d_bw) memcpy(boot_winners_host + (size_t)job.redone[(size_t)i] * PG_NUM_BOOT, bwc.data() + (size_t)i * PG_NUM_BOOT, 400);
         }
     }
+    return PG_OK;
+}
+
+// Host ASCII in, host records out.  Large batches are cut into slices of at most PG_SLICE_READS reads /
+// PG_SLICE_BYTES bases so that the device scratch (text, planes, 2 bytes of word id per base, records) stays
+// bounded whatever the caller passes -- 100 M reads in one call included.
+#define PG_SLICE_READS ((int64_t)1 << 22)
+#define PG_SLICE_BYTES ((int64_t)3 << 30)
+extern "C" int pg_classify(pg_ctx *ctx, const pg_model *md, const pg_seqbatch *reads, const pg_classify_opts *opts,
+                           pg_result *results_host, int32_t *boot_winners_host)
+{
+    if (!ctx || !md || !reads || !results_host || reads->count < 0)
+        return pg_fail(ctx, PG_EINVAL, "pg_classify: bad arguments");
+    if (!md->committed) return pg_fail(ctx, PG_EINVAL, "pg_classify: model has no tables (commit it first)");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = reads->count;
+    int64_t st[5] = {0, 0, 0, 0, 0};
+    int64_t slice_reads = PG_SLICE_READS;
+    if (const char *e = getenv("PG_SLICE_READS")) {         // tests: exercise the slicing on small batches
+        const long long v = atoll(e);
+        if (v > 0) slice_reads = v;
+    }
+    for (int64_t r0 = 0; r0 < n;) {
+        int64_t r1 = r0 + slice_reads < n ? r0 + slice_reads : n;
+        while (r1 > r0 + 1 && reads->off[r1] - reads->off[r0] > PG_SLICE_BYTES) r1 = r0 + (r1 - r0) / 2;
+        pg_seqbatch slice;
+        slice.bytes = reads->bytes;
+        slice.off = reads->off + r0;
+        slice.count = r1 - r0;
+        PG_TRY(classify_host_batch(ctx, md, &slice, opts, results_host + r0,
+                                   boot_winners_host ? boot_winners_host + r0 * PG_NUM_BOOT : NULL));
+        st[0] += ctx->st_certified; st[1] += ctx->st_strict; st[2] += ctx->st_handed_back;
+        st[3] += ctx->st_heavy; st[4] += ctx->st_items;
+        r0 = r1;
+    }
+    ctx->st_certified = st[0]; ctx->st_strict = st[1]; ctx->st_handed_back = st[2];
+    ctx->st_heavy = st[3]; ctx->st_items = st[4];
     return PG_OK;
 }
 

@@ -282,32 +282,21 @@ int main(int argc, char **argv)
     char *qtext = slurp_file(q, &qlen);
     if (!qtext) { fprintf(stderr, "rdp_classifier: cannot read %s\n", q); return 1; }
     LAP("file read");
-    int64_t cap = qlen / 32 + 1024, nrec = 0;
-    int64_t *hdr_off = NULL;
-    int32_t *id_len = NULL;
-    pg_reads *reads = NULL;
-    for (;;) {
-        hdr_off = (int64_t *)realloc(hdr_off, sizeof(int64_t) * (size_t)cap);
-        id_len = (int32_t *)realloc(id_len, sizeof(int32_t) * (size_t)cap);
-        int rc = pg_fasta_ingest(ctx, qtext, qlen, cap, &nrec, hdr_off, id_len, NULL, &reads);
-        if (rc == PG_ERANGE && nrec > cap) { cap = nrec; continue; }
-        if (rc != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx)); return 1; }
-        break;
-    }
-    LAP("FASTA ingest (GPU)");
     FILE *fo = fopen(o, "w");
     if (!fo) { fprintf(stderr, "rdp_classifier: cannot write %s\n", o); return 1; }
-    pg_result *res = (pg_result *)malloc(sizeof(pg_result) * (size_t)(nrec + 1));
     pg_classify_opts opts;
     memset(&opts, 0, sizeof opts);
     opts.min_boot_words = min_boot;
     opts.mode = strict ? 0 : 1;
-    if (nrec > 0 && pg_classify_packed_host(ctx, md, reads, &opts, res, NULL) != PG_OK) {
-        fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx));
-        return 1;
-    }
-    pg_reads_free(reads);
-    LAP("pg_classify_packed");
+    /* Files of any size: the text is handed over in pieces of about 1 GiB cut at record boundaries (a line
+     * starting with '>'), so the device never holds more than one piece with its word ids and records.
+     * PG_CLI_PIECE_BYTES overrides the size (tests). */
+    int64_t piece_bytes = (int64_t)1 << 30;
+    if (getenv("PG_CLI_PIECE_BYTES") && atoll(getenv("PG_CLI_PIECE_BYTES")) > 0) piece_bytes = atoll(getenv("PG_CLI_PIECE_BYTES"));
+    int64_t *hdr_off = NULL;
+    int32_t *id_len = NULL;
+    pg_result *res = NULL;
+    int64_t cap = 0, rescap = 0;
     static const char *FIX[6] = {"domain", "phylum", "class", "order", "family", "genus"};
     /* Output is assembled from pieces prepared once per taxon ("\tname\trank\t") and once per vote
      * count (the 101 possible confidences), so a line costs a few memcpy()s, not a dozen fprintf()s. */
@@ -322,11 +311,44 @@ int main(int argc, char **argv)
     }
     size_t ocap = (size_t)8 << 20, on = 0;
     char *obuf = (char *)malloc(ocap);
+    for (int64_t p0 = 0; p0 < qlen;) {
+        int64_t p1 = p0 + piece_bytes < qlen ? p0 + piece_bytes : qlen;
+        if (p1 < qlen) {                                   /* back up to the start of a record */
+            int64_t c = p1;
+            while (c > p0 + 1 && !(qtext[c] == '>' && qtext[c - 1] == '\n')) c--;
+            if (c > p0 + 1) p1 = c;
+            else {                                         /* one record longer than a piece: take it whole */
+                c = p1;
+                while (c < qlen && !(qtext[c] == '>' && qtext[c - 1] == '\n')) c++;
+                p1 = c;
+            }
+        }
+        const char *ptext = qtext + p0;
+        const int64_t plen = p1 - p0;
+        int64_t nrec = 0;
+        pg_reads *reads = NULL;
+        if (cap == 0) cap = plen / 32 + 1024;
+        for (;;) {
+            hdr_off = (int64_t *)realloc(hdr_off, sizeof(int64_t) * (size_t)cap);
+            id_len = (int32_t *)realloc(id_len, sizeof(int32_t) * (size_t)cap);
+            int rc = pg_fasta_ingest(ctx, ptext, plen, cap, &nrec, hdr_off, id_len, NULL, &reads);
+            if (rc == PG_ERANGE && nrec > cap) { cap = nrec; continue; }
+            if (rc != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx)); return 1; }
+            break;
+        }
+        LAP("FASTA ingest (GPU)");
+        if (nrec + 1 > rescap) { rescap = nrec + 1; res = (pg_result *)realloc(res, sizeof(pg_result) * (size_t)rescap); }
+        if (nrec > 0 && pg_classify_packed_host(ctx, md, reads, &opts, res, NULL) != PG_OK) {
+            fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx));
+            return 1;
+        }
+        pg_reads_free(reads);
+        LAP("pg_classify_packed");
 #define OUT_ROOM(need) do { if (on + (need) > ocap) { fwrite(obuf, 1, on, fo); on = 0; } } while (0)
 #define OUT_STR(s, n) do { memcpy(obuf + on, (s), (n)); on += (n); } while (0)
     for (int64_t i = 0; i < nrec; i++) {
         const pg_result *r = &res[i];
-        const char *rid = qtext + hdr_off[i];
+        const char *rid = ptext + hdr_off[i];
         const size_t idlen = (size_t)id_len[i];
         if (r->status) {
             printf("ShortSequenceException: The length of sequence with recordID=%.*s is less than %d\n", (int)idlen, rid, PG_MIN_SEQ_LEN);
@@ -360,9 +382,11 @@ int main(int argc, char **argv)
         }
         OUT_STR("\n", 1);
     }
+        LAP("format + write");
+        p0 = p1;
+    }
     fwrite(obuf, 1, on, fo);
     free(obuf);
-    LAP("format + write");
     fclose(fo);
     free(res);
     pg_free(blob);

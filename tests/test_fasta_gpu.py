@@ -112,3 +112,34 @@ def test_ingested_reads_classify_like_host_parsed_reads(ctx):
     assert got["status"][-1] != 0                       # the short record is reported, not classified
     reads.free()
     gm.free()
+
+
+def test_cli_pieces_give_the_same_file(tmp_path):
+    """rdp_classifier hands its query file to the GPU in record-aligned pieces; tiny pieces (PG_CLI_PIECE_BYTES)
+    must give the file a single piece gives, multi-line records and CRLF included."""
+    import os
+
+    tr = synth.synth16s(seed=8, seqs=120, genera=30, length=700)
+    names, anc = tr["node_names"], tr["anc"]
+    with open(tmp_path / "train.fa", "w") as f:
+        for i, g in enumerate(tr["genus"]):
+            s = tr["data"][tr["off"][i]:tr["off"][i + 1]].tobytes().decode()
+            f.write(f">T{i:04d}\t" + ";".join(names[n] for n in anc[g]) + "\n" + s + "\n")
+    data, off, _ = synth.synth_reads(4, tr, 800, paired=False, read_len=230)
+    arr = data.reshape(-1, int(off[1]))
+    with open(tmp_path / "q.fa", "wb") as f:
+        for i in range(arr.shape[0]):
+            b = arr[i].tobytes()
+            f.write(b">q%04d some description\r\n" % i + b[:100] + b"\r\n" + b[100:] + b"\n")
+        f.write(b">tiny\nACGTACGT\n")
+    exe = str(BIN / "rdp_classifier")
+    subprocess.run([exe, "--train", "train.fa", "-t", "m.pgm"], cwd=tmp_path, check=True, capture_output=True)
+    r1 = subprocess.run([exe, "-q", "q.fa", "-o", "one.txt", "-t", "m.pgm"], cwd=tmp_path, capture_output=True, text=True)
+    r2 = subprocess.run([exe, "-q", "q.fa", "-o", "many.txt", "-t", "m.pgm"], cwd=tmp_path, capture_output=True, text=True,
+                        env=dict(os.environ, PG_CLI_PIECE_BYTES="5000"))
+    assert r1.returncode == 0 and r2.returncode == 0, (r1.stderr, r2.stderr)
+    one = (tmp_path / "one.txt").read_text()
+    assert one == (tmp_path / "many.txt").read_text() and r1.stdout == r2.stdout
+    lines = one.split("\n")
+    assert len([l for l in lines if l]) == 800 and lines[0].startswith("q0000\t")
+    assert "recordID=tiny" in r1.stdout                      # the short record is reported on stdout, not classified

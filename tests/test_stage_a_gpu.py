@@ -532,3 +532,17 @@ def test_certified_equals_strict_on_random_models(ctx, seed, genera, seqs, lengt
     assert np.array_equal(want["genus"][:150], ref["genus"]) and np.array_equal(wb[:150], ref["boot"])
     om.free()
     gm.free()
+
+
+def test_large_batches_are_sliced(ctx, small, monkeypatch):
+    """pg_classify cuts a batch into slices so that device scratch stays bounded; slices of 700 reads
+    (PG_SLICE_READS) of a 3 000-read batch must give the records of one pass, statistics summed."""
+    tr, om, gm = small
+    data, off, _ = synth.synth_reads(21, tr, 3000, paired=False, read_len=200)
+    want, wb = ctx.classify(gm, data, off, mode=1, want_boot=True)
+    st0 = ctx.classify_stats()
+    monkeypatch.setenv("PG_SLICE_READS", "700")
+    got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True)
+    st1 = ctx.classify_stats()
+    assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb)
+    assert st1["certified"] + st1["strict"] == 3000 == st0["certified"] + st0["strict"]
