@@ -84,11 +84,12 @@ __global__ void k_quantise(const float *__restrict__ table, const float *__restr
 }
 
 // Lower-bound tables.  bm: per (word, block) the minimum deficit over the block's 64 positions (padding holds
-// PG_Q_MAX and never wins).  A group is PG_GB = 29 blocks: bm[group][w][slot], the last PG_PARTS - 1 slots of
-// every 64-byte row are spare -- k_bound puts the minima of the best block's other parts there (plan 3).
+// PG_Q_MAX and never wins).  A group is PG_GB = 28 blocks: bm[group][w][slot], the last PG_PARTS slots of
+// every 64-byte row are spare -- k_bound puts the part minima of the best block there with one 8-byte store
+// per row (plan 3).
 #define PG_PARTS 4                       // plan 3 evaluates one part (64 / PG_PARTS positions) of the best block
 #define PG_PART_POS (64 / PG_PARTS)
-#define PG_GB (32 - (PG_PARTS - 1))
+#define PG_GB (32 - PG_PARTS)
 __global__ void k_blockmin(const uint16_t *__restrict__ q, int ntile64, int ngroup, uint16_t *__restrict__ bm)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -842,12 +843,9 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     __syncthreads();
     if (sib_here) {
         uint16_t *rows16 = reinterpret_cast<uint16_t *>(sB);
-        auto put = [&](int j, uint2 v) {
-            const unsigned long long all = ((unsigned long long)v.y << 32) | v.x;     // the block's four part minima
-#pragma unroll
-            for (int jj = 0; jj < PG_PARTS - 1; jj++)
-                rows16[j * 32 + PG_GB + jj] = (uint16_t)(all >> (16 * (jj < own ? jj : jj + 1)));
-        };
+        // slots PG_GB .. 31 of row j <- the block's four part minima (the read's own part is never tested); one
+        // 8-byte store per row: a column of a row-major array is a 16-way bank conflict whatever the width
+        auto put = [&](int j, uint2 v) { *reinterpret_cast<uint2 *>(rows16 + j * 32 + PG_GB) = v; };
 #pragma unroll
         for (int u = 0; u < 4; u++)
             if (tid + u * BLOCK < n) put(tid + u * BLOCK, hv[u]);
@@ -866,9 +864,9 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         okblk[i] = b0 + i;
         ok[i] = slot < PG_GB && b0 + i < ntile64 && b0 + i != best;
         if (slot >= PG_GB) {                        // part item: that sibling part of the best block only
-            const int jj = slot - PG_GB;
-            ok[i] = sib_here;
-            okblk[i] = 0x8000 | ((jj < own ? jj : jj + 1) << 13) | best;
+            const int part = slot - PG_GB;
+            ok[i] = sib_here && part != own;
+            okblk[i] = 0x8000 | (part << 13) | best;
         }
     }
     const char *base = reinterpret_cast<const char *>(sB) + hl * 8;
@@ -950,9 +948,9 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         const unsigned long long cv = __ldg(mychamp);
         const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + pg_margin(n, vmax);
         const bool real = tid < PG_GB && blk < ntile64 && blk != best;
-        const int jj = tid - PG_GB;
-        if ((real || (tid >= PG_GB && sib_here)) && (unsigned long long)s_full[tid] <= thr)
-            PG_SURVIVE(0, real ? blk : (0x8000 | ((jj < own ? jj : jj + 1) << 13) | best))
+        const int part = tid - PG_GB;
+        if ((real || (tid >= PG_GB && sib_here && part != own)) && (unsigned long long)s_full[tid] <= thr)
+            PG_SURVIVE(0, real ? blk : (0x8000 | (part << 13) | best))
     }
     __syncthreads();
     const unsigned int cnt = s_cnt;
@@ -1026,6 +1024,8 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
         const uint4 *lp = reinterpret_cast<const uint4 *>(boot_pool + boot_off[n]) +
                           (task > 0 ? (size_t)((task - 1) >> 2) * nb * 4 + ((task - 1) & 3) : 0);
         const int nstep = task == 0 ? (n + 7) >> 3 : (nb + 1) >> 1;
+        // (prefetching the next step's list entries and word ids while this step's rows are in flight was
+        // measured: 80 registers, a quarter fewer resident warps, 12 % slower)
         for (int st = 0; st < nstep; st++) {
             // row indices of this step's 8 draws (index n = padding = no row)
             uint32_t r[8];
@@ -1095,8 +1095,11 @@ __device__ float pg_strict_sum(const float *__restrict__ table, const uint16_t *
     return a;
 }
 
-// the same sum by the whole warp: the gathers are spread over the lanes (8 in flight per lane), the adds
-// stay one chain in the reference's order (shuffle + FADD per term); every lane ends with the result
+// the same sum by the whole warp.  Lane l gathers the 16 consecutive terms 16l .. 16l+15 of a 512-term pass (all
+// loads in flight at once); the running sum then hops from lane to lane: every lane adds its own 16 terms in
+// order to the value it receives from its predecessor, so the adds stay one chain in the reference's order at
+// the price of ONE shuffle per 16 terms (a shuffle per term kept the LSU pipe 80 % busy).  Every lane returns
+// the result.
 __device__ float pg_strict_sum_warp(const float *__restrict__ table, const uint16_t *sw, int n, int k, int nb,
                                     const uint32_t *__restrict__ list, int task, uint32_t g, int lane)
 {
@@ -1105,27 +1108,33 @@ __device__ float pg_strict_sum_warp(const float *__restrict__ table, const uint1
     const int t1 = task > 0 ? task - 1 : 0;
     const uint32_t *lp = list + ((size_t)(t1 / 4) * nb * 4 + (t1 % 4)) * 4;
     float a = 0.f;
-    for (int base = 0; base < terms; base += 256) {
-        float v[8];
+    for (int base = 0; base < terms; base += 512) {
+        float v[16];
+        const int j0 = base + lane * 16;
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int j = base + u * 32 + lane;
+        for (int u = 0; u < 16; u++) {
+            const int j = j0 + u;
             v[u] = 0.f;
             if (j < terms) {
                 const uint32_t r = task == 0 ? (uint32_t)j : __ldg(lp + (size_t)(j >> 2) * 16 + (j & 3)) / PG_ROW_PITCH;
                 v[u] = __ldg(tb + (size_t)sw[r] * PG_GENUS_TILE);
             }
         }
+        const int cnt = terms - j0;                 // terms this lane owns in this pass (may be <= 0 or > 16)
+        const int hops = (terms - base + 15) / 16 < 32 ? (terms - base + 15) / 16 : 32;
+        for (int h = 0; h < hops; h++) {
+            // lane h continues the chain from lane h-1 (lane 0 from the previous pass); the other lanes idle along
+            const float in = __shfl_sync(0xffffffffu, a, h == 0 ? (base == 0 ? 0 : 31) : h - 1);
+            if (lane == h) {
+                float x = (h == 0 && base == 0) ? 0.f : in;
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int j0 = base + u * 32;
-            if (j0 + 32 <= terms) {
-#pragma unroll
-                for (int l = 0; l < 32; l++) a = __fadd_rn(a, __shfl_sync(0xffffffffu, v[u], l));
-            } else if (j0 < terms) {
-                for (int l = 0; j0 + l < terms; l++) a = __fadd_rn(a, __shfl_sync(0xffffffffu, v[u], l));
+                for (int u = 0; u < 16; u++)
+                    if (u < cnt) x = __fadd_rn(x, v[u]);
+                a = x;
             }
         }
+        // the pass ends in lane hops-1: park its value in lane 31 for the next pass / the result
+        a = __shfl_sync(0xffffffffu, a, hops - 1);
     }
     return a;
 }
@@ -1385,7 +1394,11 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
         md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.counters + 2, cb.item_cap, cb.heavy,
         (unsigned int)light_max, version == 3 ? md->d_hmtable : NULL);
     PG_LAUNCHED(ctx);
-    k_light<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_order - slot0, ctx->d_boot_pool,
+    static int light_ctas = 0;                          // resident CTAs per SM of the persistent item kernel
+    if (!light_ctas) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&light_ctas, k_light, 256, 0) != cudaSuccess || light_ctas < 1) light_ctas = 2;
+    }
+    k_light<<<ctx->sm_count * light_ctas, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_order - slot0, ctx->d_boot_pool,
                                                         ctx->d_boot_off, min_boot, md->d_blockmask, md->vmax, cb.items,
                                                         cb.counters + 2, cb.item_cap, cb.champ, cb.ncand, cb.cand, cb.counters + 3);
     PG_LAUNCHED(ctx);

@@ -116,24 +116,36 @@ k_extract(const uint32_t *__restrict__ planes, const int64_t *__restrict__ off, 
     // ---- A3: fwd = sum logPrior[w_j], rev = sum logPrior[rc(w_j)], fp32, word order.
     // Every lane carries the same two running sums; values are fetched 32 at a
     // time and fed through shuffles so the adds stay in sequence order.
-    // Lanes 0-15 carry the forward chain, lanes 16-31 the reverse-complement chain: 16 words per round,
-    // one shuffle + one add per word for both sums.
+    // Lanes 0-15 carry the forward chain, lanes 16-31 the reverse-complement chain.  Lane hl of a half gathers
+    // the 16 consecutive terms 16*hl .. 16*hl+15 of a 256-word pass; the running sum hops from lane to lane, each
+    // adding its own 16 terms in order: the adds stay one chain in word order for one shuffle per 16 words.
     float acc = 0.0f;
     const int half = lane & 16, hl = lane & 15;
-    for (int j0 = 0; j0 < n; j0 += 16) {
-        const int j = j0 + hl;
-        float p = 0.0f;
-        if (j < n) {
-            const uint32_t wj = w[j];
-            p = __ldg(logPrior + (half ? pg_revcomp_word(wj) : wj));
-        }
-        const int cnt = n - j0 < 16 ? n - j0 : 16;
-        if (cnt == 16) {
+    for (int base = 0; base < n; base += 256) {
+        float v[16];
+        const int j0 = base + hl * 16;
 #pragma unroll
-            for (int t = 0; t < 16; t++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, p, half + t));
-        } else {
-            for (int t = 0; t < cnt; t++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, p, half + t));
+        for (int u = 0; u < 16; u++) {
+            const int j = j0 + u;
+            v[u] = 0.0f;
+            if (j < n) {
+                const uint32_t wj = w[j];
+                v[u] = __ldg(logPrior + (half ? pg_revcomp_word(wj) : wj));
+            }
         }
+        const int cnt = n - j0;
+        const int hops = (n - base + 15) / 16 < 16 ? (n - base + 15) / 16 : 16;
+        for (int h = 0; h < hops; h++) {
+            const float in = __shfl_sync(0xffffffffu, acc, half + (h == 0 ? 15 : h - 1));
+            if (hl == h) {
+                float x = (h == 0 && base == 0) ? 0.0f : in;
+#pragma unroll
+                for (int u = 0; u < 16; u++)
+                    if (u < cnt) x = __fadd_rn(x, v[u]);
+                acc = x;
+            }
+        }
+        acc = __shfl_sync(0xffffffffu, acc, half + hops - 1);       // every lane of the half holds the pass result
     }
     const float fwd = __shfl_sync(0xffffffffu, acc, 0), rev = __shfl_sync(0xffffffffu, acc, 16);
     const bool reversed = rev > fwd;
