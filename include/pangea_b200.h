@@ -311,6 +311,15 @@ int pg_megaclust(pg_ctx *ctx, const char *text_host, int64_t len, const pg_megac
                  int64_t *n_otus, int64_t *otu_off, int32_t *otu_len, int64_t *otu_count, int64_t *lines_examined,
                  int64_t *lines_beyond);
 
+/* ------------------------------------------------------------------ first hit per read (widening: SURVEY.md 8(f) next-4)
+ * Replaces: `perl get_uniq.pl -f <tabular hits>` (Scripts/get_uniq.pl:34-40), which writes <file>.unique: every
+ * line whose first TAB-separated column has not occurred on an earlier line, in input order (a line without a TAB
+ * keys on its whole text, newline included, as the script's misplaced chomp makes it).
+ * out_host receives the kept lines; kept_lines_host (optional) their 0-based line numbers.  PG_ERANGE (needed
+ * sizes in *out_len / *n_kept) when a buffer is too small. */
+int pg_first_hits(pg_ctx *ctx, const char *text_host, int64_t len, char *out_host, int64_t out_cap, int64_t *out_len,
+                  int64_t *kept_lines_host, int64_t lines_cap, int64_t *n_kept);
+
 #ifdef __cplusplus
 }
 #endif

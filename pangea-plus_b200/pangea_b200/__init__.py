@@ -159,6 +159,7 @@ def load_library() -> C.CDLL:
     lib.pg_fasta_ingest.argtypes = [vp, C.c_char_p, i64, i64, C.POINTER(i64), vp, vp, vp, C.POINTER(vp)]
     lib.pg_fasta_last_bytes.argtypes = [vp, i64, vp, i64, vp]
     lib.pg_classify_packed_host.argtypes = [vp, vp, vp, C.POINTER(_Opts), vp, vp]
+    lib.pg_first_hits.argtypes = [vp, C.c_char_p, i64, vp, i64, C.POINTER(i64), vp, i64, C.POINTER(i64)]
     lib.pg_megaclust.argtypes = [vp, C.c_char_p, i64, C.POINTER(_MegaclustOpts), i64, C.POINTER(i64), vp, vp, vp,
                                  C.POINTER(i64), C.POINTER(i64)]
     lib.pg_trim_join.argtypes = [vp, C.c_char_p, i64, C.c_char_p, i64, C.c_int, C.POINTER(_TrimOpts), vp, i64, C.POINTER(i64), C.POINTER(vp)]
@@ -404,6 +405,16 @@ class Context:
         boot = np.zeros((n, PG_NUM_BOOT), np.int32) if want_boot else None
         self._chk(self.lib.pg_classify_packed_host(self.h, model.h, reads.h, C.byref(opts), _ptr(res), _ptr(boot)))
         return (res, boot) if want_boot else res
+
+    # ---- first hit per read
+    def first_hits(self, text: bytes):
+        """-> (kept text bytes, kept 0-based line numbers)"""
+        out = np.zeros(max(len(text), 1), np.uint8)
+        lines = np.zeros(text.count(b"\n") + 2, np.int64)
+        n, k = C.c_int64(), C.c_int64()
+        self._chk(self.lib.pg_first_hits(self.h, text, len(text), out.ctypes.data, out.size, C.byref(n), lines.ctypes.data,
+                                         lines.size, C.byref(k)))
+        return out[: n.value].tobytes(), lines[: k.value].tolist()
 
     # ---- Megaclust
     def megaclust_raw(self, text: bytes, sim: float = 95.0, ev: float = 1e-20, bits: float = 200.0, every: bool = False,

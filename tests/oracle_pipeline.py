@@ -19,7 +19,7 @@ def lib():
     if _lib is None:
         so = ORACLE_DIR / "libpipeline_ref.so"
         srcs = [ORACLE_DIR / "taxcollector_ref.c", ORACLE_DIR / "consensus_ref.c", ORACLE_DIR / "trim_ref.c",
-                ORACLE_DIR / "megaclust_ref.c"]
+                ORACLE_DIR / "megaclust_ref.c", ORACLE_DIR / "uniq_ref.c"]
         if not so.exists() or any(so.stat().st_mtime < s.stat().st_mtime for s in srcs):
             subprocess.run(["make", "-C", str(ORACLE_DIR), str(so)], check=True, capture_output=True)
         L = C.CDLL(str(so))
@@ -29,6 +29,8 @@ def lib():
         L.mc_ref_megaclust.restype = C.c_longlong
         L.mc_ref_megaclust.argtypes = [C.c_char_p, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_int, C.c_longlong,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.uq_ref_first_hits.restype = C.c_longlong
+        L.uq_ref_first_hits.argtypes = [C.c_char_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mc_ref_number.restype = C.c_double
         L.mc_ref_number.argtypes = [C.c_char_p, C.c_int]
         _lib = L
@@ -160,3 +162,26 @@ def real_megaclustable(files: dict, level: str, order=None):
         subprocess.run(["perl", str(REF / "Megaclustable" / "megaclustable.pl"), "-m", *names, "-t", level, "-o", "table.txt"],
                        cwd=wd, capture_output=True)
         return (wd / "table.txt").read_bytes() if (wd / "table.txt").exists() else None
+
+
+# ------------------------------------------------------------------ first hit per read
+
+def oracle_first_hits(text: bytes):
+    """-> (kept text bytes, kept 0-based line numbers)"""
+    import numpy as np
+
+    out = C.create_string_buffer(max(len(text), 1))
+    lines = np.zeros(text.count(b"\n") + 2, np.int64)
+    nk = C.c_longlong()
+    n = lib().uq_ref_first_hits(text, len(text), out, lines.ctypes.data, C.byref(nk))
+    assert n >= 0
+    return out.raw[:n], lines[: nk.value].tolist()
+
+
+def real_get_uniq(text: bytes):
+    """the live Scripts/get_uniq.pl -> bytes of <file>.unique"""
+    with tempfile.TemporaryDirectory() as wd:
+        wd = Path(wd)
+        (wd / "hits.txt").write_bytes(text)
+        subprocess.run(["perl", str(REF / "Scripts" / "get_uniq.pl"), "-f", "hits.txt"], cwd=wd, capture_output=True)
+        return (wd / "hits.txt.unique").read_bytes()
