@@ -854,7 +854,6 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     }
 
     const int unit = tid >> 3, hl = tid & 7;
-    const unsigned qmask = 0xFFu << (tid & 24);
     const int b0 = grp * PG_GB + 4 * hl;
     bool ok[4];
     int okblk[4];
@@ -903,43 +902,52 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         for (int t = unit; t < PG_NUM_BOOT; t += NUNIT) {
             const unsigned long long cv = __ldg(mychamp + 1 + t);
             const uint4 *lp = lists + (size_t)(t >> 2) * nb * 4 + (t & 3);
-            const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + margin;
+            // sums stay below 2^26: the threshold is kept in 32 bits (an empty slot = no threshold)
+            const uint32_t thr = (cv == PG_CHAMP_INIT) ? 0xFFFFFFFFu : (uint32_t)(cv >> 32) + margin;
             uint32_t s[4] = {0u, 0u, 0u, 0u}, cx = 0u, cy = 0u;
-            int b = 0;
-            bool open = true;                       // some block of this unit may still be within the threshold
-            bool lane_open = true;                  // ... some block of this lane
+            bool lane_open = true;                  // some block of this lane may still be within the threshold
             // The four units of a warp walk in lockstep.  Partial sums only grow, so a lane whose four blocks are
-            // all above the threshold stops loading (its frozen sums stay above it: fewer bytes per row fetch,
-            // fewer shared-memory wavefronts), and once every lane of a unit has stopped its task is settled.
-            // The list entries run one trip (four batches) ahead of the loads that need them; batches past
-            // the task's end point at the zero row.
+            // all above the threshold stops loading (its frozen sums stay above it), and once every lane of the
+            // warp has stopped the four tasks are settled.  The list entries run one trip (four batches = 16
+            // draws) ahead of the loads that need them, in two register sets used alternately; batches past the
+            // task's end point at the zero row.  (A check every 8 draws was measured: no gain.)
             const uint32_t zoff = (uint32_t)n * PG_ROW_PITCH;
             const uint4 zq = make_uint4(zoff, zoff, zoff, zoff);
 #define PG_LQ(bb) ((bb) < nb ? __ldg(lp + (bb) * 4) : zq)
-            uint4 n0 = PG_LQ(0), n1 = PG_LQ(1), n2 = PG_LQ(2), n3 = PG_LQ(3);
-            for (; b < nb; b += 4) {                // 16 rows x 4095 < 2^16: one spill per four batches
-                const uint4 q0 = n0, q1 = n1, q2 = n2, q3 = n3;
-                if (lane_open && b + 4 < nb) { n0 = PG_LQ(b + 4); n1 = PG_LQ(b + 5); n2 = PG_LQ(b + 6); n3 = PG_LQ(b + 7); }
-                if (lane_open) {                    // (a check every 8 draws was measured: no gain)
-                    PG_BADD(q0.x >> 1) PG_BADD(q0.y >> 1) PG_BADD(q0.z >> 1) PG_BADD(q0.w >> 1)
-                    PG_BADD(q1.x >> 1) PG_BADD(q1.y >> 1) PG_BADD(q1.z >> 1) PG_BADD(q1.w >> 1)
-                    PG_BADD(q2.x >> 1) PG_BADD(q2.y >> 1) PG_BADD(q2.z >> 1) PG_BADD(q2.w >> 1)
-                    PG_BADD(q3.x >> 1) PG_BADD(q3.y >> 1) PG_BADD(q3.z >> 1) PG_BADD(q3.w >> 1)
-                    PG_BSPILL()
-                }
-                bool mine = false;
-#pragma unroll
-                for (int i = 0; i < 4; i++) mine |= ok[i] && (unsigned long long)s[i] <= thr;
-                lane_open = mine && lane_open;
-                const unsigned vote = __ballot_sync(0xffffffffu, lane_open);
-                open = (vote & qmask) != 0u;
-                if (vote == 0u) break;
+#define PG_LQ4(d, bb)                                                                                      \
+    if ((bb) + 4 <= nb) { d##0 = __ldg(lp + ((bb) + 0) * 4); d##1 = __ldg(lp + ((bb) + 1) * 4);            \
+                          d##2 = __ldg(lp + ((bb) + 2) * 4); d##3 = __ldg(lp + ((bb) + 3) * 4); }          \
+    else { d##0 = PG_LQ((bb) + 0); d##1 = PG_LQ((bb) + 1); d##2 = PG_LQ((bb) + 2); d##3 = PG_LQ((bb) + 3); }
+#define PG_TRIP(d)                                                                                         \
+    if (lane_open) {                                                                                       \
+        PG_BADD((d##0).x >> 1) PG_BADD((d##0).y >> 1) PG_BADD((d##0).z >> 1) PG_BADD((d##0).w >> 1)                \
+        PG_BADD((d##1).x >> 1) PG_BADD((d##1).y >> 1) PG_BADD((d##1).z >> 1) PG_BADD((d##1).w >> 1)                \
+        PG_BADD((d##2).x >> 1) PG_BADD((d##2).y >> 1) PG_BADD((d##2).z >> 1) PG_BADD((d##2).w >> 1)                \
+        PG_BADD((d##3).x >> 1) PG_BADD((d##3).y >> 1) PG_BADD((d##3).z >> 1) PG_BADD((d##3).w >> 1)                \
+        PG_BSPILL()                                 /* 16 rows x 4095 < 2^16: one spill per trip */        \
+    }                                                                                                      \
+    {                                                                                                      \
+        bool mine = false;                                                                                 \
+        _Pragma("unroll") for (int i = 0; i < 4; i++) mine |= ok[i] && s[i] <= thr;                        \
+        lane_open = mine && lane_open;                                                                     \
+    }
+            uint4 A0, A1, A2, A3, B0, B1, B2, B3;
+            B0 = B1 = B2 = B3 = zq;
+            PG_LQ4(A, 0)
+            for (int b = 0; b < nb; b += 8) {
+                if (lane_open && b + 4 < nb) { PG_LQ4(B, b + 4) }
+                PG_TRIP(A)
+                if (__ballot_sync(0xffffffffu, lane_open) == 0u || b + 4 >= nb) break;
+                if (lane_open && b + 8 < nb) { PG_LQ4(A, b + 8) }
+                PG_TRIP(B)
+                if (__ballot_sync(0xffffffffu, lane_open) == 0u) break;
             }
 #undef PG_LQ
-            PG_BSPILL()
+#undef PG_LQ4
+#undef PG_TRIP
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                if (lane_open && ok[i] && (unsigned long long)s[i] <= thr) PG_SURVIVE(1 + t, okblk[i])
+                if (lane_open && ok[i] && s[i] <= thr) PG_SURVIVE(1 + t, okblk[i])
         }
     }
     __syncthreads();
