@@ -996,7 +996,8 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
         const int32_t *__restrict__ boot_off, int min_boot, const unsigned long long *__restrict__ blockmask,
         double vmax, const unsigned long long *__restrict__ items, const unsigned int *__restrict__ item_count,
         unsigned int item_cap, unsigned long long *__restrict__ champ, unsigned int *__restrict__ ncand,
-        unsigned long long *__restrict__ cand, unsigned int *__restrict__ items_total)
+        unsigned long long *__restrict__ cand, unsigned int *__restrict__ items_total,
+        const uint16_t *__restrict__ hm /* plan 3: part minima, or NULL */)
 {
     const int lane = threadIdx.x & 31, l = lane & 7;
     const int gshift = lane & ~7;
@@ -1013,7 +1014,7 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
         const bool part_item = ((e >> 15) & 1ULL) != 0ULL;
         const int which = (int)((e >> 13) & 3ULL);
         const int blk = (int)(e & 0x1FFFu);
-        const bool lane_on = !part_item || l / (8 / PG_PARTS) == which;
+        bool lane_on = !part_item || l / (8 / PG_PARTS) == which;
         const size_t rc = (size_t)(e >> 32);
         const int64_t read = order_base[rc];
         const int n = nwords[read];
@@ -1031,6 +1032,37 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
         bool pruned = false;
         const uint4 *lp = reinterpret_cast<const uint4 *>(boot_pool + boot_off[n]) +
                           (task > 0 ? (size_t)((task - 1) >> 2) * nb * 4 + ((task - 1) & 3) : 0);
+        if (hm && !part_item) {
+            // A whole block is open because its 64-position bound was not enough.  Bound its four parts first
+            // (8 bytes per draw instead of a 128-byte row; the 8 lanes split the draws): a part whose bound is
+            // above the threshold switches its two lanes off, a block with no part left is dropped here.
+            const uint16_t *hrow = hm + (size_t)((blk * PG_PARTS) >> 5) * PG_NWORDS * 32 + ((blk * PG_PARTS) & 31);
+            uint32_t lb0 = 0u, lb1 = 0u, lb2 = 0u, lb3 = 0u;
+#define PG_PART_ADD(r_)                                                                                     \
+    if ((int)(r_) < n) {                                                                                    \
+        const uint2 hv_ = __ldg(reinterpret_cast<const uint2 *>(hrow + (size_t)__ldg(w + (r_)) * 32));      \
+        lb0 += hv_.x & 0xFFFFu; lb1 += hv_.x >> 16; lb2 += hv_.y & 0xFFFFu; lb3 += hv_.y >> 16;             \
+    }
+            if (task == 0) {
+                for (int j = l; j < n; j += 8) PG_PART_ADD((uint32_t)j)
+            } else {
+                for (int b = l; b < nb; b += 8) {
+                    const uint4 q = __ldg(lp + (size_t)b * 4);
+                    PG_PART_ADD(q.x / PG_ROW_PITCH) PG_PART_ADD(q.y / PG_ROW_PITCH)
+                    PG_PART_ADD(q.z / PG_ROW_PITCH) PG_PART_ADD(q.w / PG_ROW_PITCH)
+                }
+            }
+#undef PG_PART_ADD
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                lb0 += __shfl_xor_sync(gmask, lb0, o); lb1 += __shfl_xor_sync(gmask, lb1, o);
+                lb2 += __shfl_xor_sync(gmask, lb2, o); lb3 += __shfl_xor_sync(gmask, lb3, o);
+            }
+            const int part = l / (8 / PG_PARTS);
+            const uint32_t mine = part == 0 ? lb0 : (part == 1 ? lb1 : (part == 2 ? lb2 : lb3));
+            lane_on = (unsigned long long)mine <= thr;
+            if ((__ballot_sync(gmask, lane_on) & gmask) == 0u) continue;
+        }
         const int nstep = task == 0 ? (n + 7) >> 3 : (nb + 1) >> 1;
         // (prefetching the next step's list entries and word ids while this step's rows are in flight was
         // measured: 80 registers, a quarter fewer resident warps, 12 % slower)
@@ -1408,7 +1440,8 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     }
     k_light<<<ctx->sm_count * light_ctas, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_order - slot0, ctx->d_boot_pool,
                                                         ctx->d_boot_off, min_boot, md->d_blockmask, md->vmax, cb.items,
-                                                        cb.counters + 2, cb.item_cap, cb.champ, cb.ncand, cb.cand, cb.counters + 3);
+                                                        cb.counters + 2, cb.item_cap, cb.champ, cb.ncand, cb.cand, cb.counters + 3,
+                                                        version == 3 ? md->d_hmtable : NULL);
     PG_LAUNCHED(ctx);
     return PG_OK;
 }
