@@ -27,21 +27,6 @@
 #include "pg_host_common.h"
 #include <time.h>
 
-static char *slurp_file(const char *path, int64_t *len)
-{
-    FILE *f = fopen(path, "rb");
-    if (!f) return NULL;
-    fseek(f, 0, SEEK_END);
-    long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    char *b = (char *)malloc((size_t)n + 1);
-    if (n && fread(b, 1, (size_t)n, f) != (size_t)n) { fclose(f); free(b); return NULL; }
-    fclose(f);
-    b[n] = 0;
-    *len = n;
-    return b;
-}
-
 static double now_s(void)
 {
     struct timespec ts;
@@ -278,10 +263,8 @@ int main(int argc, char **argv)
     LAP("model load");
     /* the query file goes to the device as text: records, ids and the packed read store come from the GPU
      * (pg_fasta_ingest); the host keeps the text only to print the ids */
-    int64_t qlen = 0;
-    char *qtext = slurp_file(q, &qlen);
-    if (!qtext) { fprintf(stderr, "rdp_classifier: cannot read %s\n", q); return 1; }
-    LAP("file read");
+    FILE *fq = fopen(q, "rb");
+    if (!fq) { fprintf(stderr, "rdp_classifier: cannot read %s\n", q); return 1; }
     FILE *fo = fopen(o, "w");
     if (!fo) { fprintf(stderr, "rdp_classifier: cannot write %s\n", o); return 1; }
     pg_classify_opts opts;
@@ -311,20 +294,30 @@ int main(int argc, char **argv)
     }
     size_t ocap = (size_t)8 << 20, on = 0;
     char *obuf = (char *)malloc(ocap);
-    for (int64_t p0 = 0; p0 < qlen;) {
-        int64_t p1 = p0 + piece_bytes < qlen ? p0 + piece_bytes : qlen;
-        if (p1 < qlen) {                                   /* back up to the start of a record */
-            int64_t c = p1;
-            while (c > p0 + 1 && !(qtext[c] == '>' && qtext[c - 1] == '\n')) c--;
-            if (c > p0 + 1) p1 = c;
-            else {                                         /* one record longer than a piece: take it whole */
-                c = p1;
-                while (c < qlen && !(qtext[c] == '>' && qtext[c - 1] == '\n')) c++;
-                p1 = c;
+    /* the file is read piece by piece: host memory holds one piece (plus the head of the next record) */
+    int64_t bufcap = piece_bytes + 4096, have = 0;
+    char *qbuf = (char *)malloc((size_t)bufcap + 1);
+    int at_eof = 0;
+    for (;;) {
+        while (!at_eof && have < bufcap) {
+            size_t got = fread(qbuf + have, 1, (size_t)(bufcap - have), fq);
+            if (got == 0) at_eof = 1;
+            have += (int64_t)got;
+        }
+        if (have == 0) break;
+        int64_t p1 = have;
+        if (!at_eof) {                                     /* cut at the start of the last record in the buffer */
+            int64_t c = have - 1;
+            while (c > 0 && !(qbuf[c] == '>' && qbuf[c - 1] == '\n')) c--;
+            if (c > 0) p1 = c;
+            else {                                         /* one record longer than the buffer: make room, read on */
+                bufcap *= 2;
+                qbuf = (char *)realloc(qbuf, (size_t)bufcap + 1);
+                continue;
             }
         }
-        const char *ptext = qtext + p0;
-        const int64_t plen = p1 - p0;
+        const char *ptext = qbuf;
+        const int64_t plen = p1;
         int64_t nrec = 0;
         pg_reads *reads = NULL;
         if (cap == 0) cap = plen / 32 + 1024;
@@ -383,14 +376,16 @@ int main(int argc, char **argv)
         OUT_STR("\n", 1);
     }
         LAP("format + write");
-        p0 = p1;
+        memmove(qbuf, qbuf + p1, (size_t)(have - p1));    /* the head of the next record moves to the front */
+        have -= p1;
     }
+    fclose(fq);
     fwrite(obuf, 1, on, fo);
     free(obuf);
     fclose(fo);
     free(res);
     pg_free(blob);
-    free(qtext);
+    free(qbuf);
     free(hdr_off);
     free(id_len);
     pg_model_free(md);
