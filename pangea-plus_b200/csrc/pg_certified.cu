@@ -1,7 +1,7 @@
 // pg_certified.cu -- certified-margin fast path for K4/K5 (classify mode 1).
 //
 // Same results as strict mode (and so as the reference order of operations,
-// SURVEY.md rows A7-A9), obtained with half the shared-memory traffic:
+// SURVEY.md rows A7-A9), obtained from a fraction of its shared-memory traffic:
 //
 //  * At training time every table entry is restated as its DEFICIT below the best
 //    genus of the same word, D[w][g] = max_g' V[w][g'] - V[w][g] >= 0, quantised
@@ -18,9 +18,17 @@
 //  * Survivors (almost always one) are re-evaluated in strict fp32 order straight
 //    from the fp32 table; ties resolve to the lowest genus index as in the reference.
 //
-// Phase 1 (k_classify_q): one CTA per (read, 64-genus block); packed 2 x 16-bit
-// adds, four per LDS.128; a per-(read, replicate) champion slot is maintained with
-// 64-bit atomicMin and near-ties are appended to a short per-read list.
+//  * Deficits are non-negative, so any UNDER-estimate of a genus's sum that already exceeds
+//    champion + margin dismisses the genus: per-block and per-part minima (k_blockmin, k_partmin)
+//    bound whole blocks of the lineage-ordered table without touching their rows (k_bound).
+//
+// Phase 1, three work plans with identical results (pg_classify_opts.cert_plan):
+//   plan 3 (default)  k_guess_bm -> k_classify_h (best 16-position part, four reads per CTA) -> k_bound -> k_light
+//   plan 2            k_guess_bm -> k_classify_q<.., false> (whole best block)               -> k_bound -> k_light
+//   plan 1            k_guess_block -> k_classify_q<.., true> (every block, partial-sum pruning); also the
+//                     fallback for "heavy" reads the bounds leave too many open pairs for
+//   packed 2 x 16-bit adds, four per LDS.128; a per-(read, task) champion slot is maintained with 64-bit
+//   atomicMin and near-ties are appended to a short per-read list.
 // Phase 2 (k_resolve): one warp per read; strict re-check of survivors, then the A9 vote.
 // Reads whose list overflows are handed back to the strict kernels.
 #include "pg_classify_common.cuh"
@@ -342,7 +350,7 @@ __device__ __forceinline__ void pg_epilogue_finish(unsigned mask, bool leader, i
         for (int i = 0; i < NV; i++) hit |= (sums[i] <= thr ? 1u : 0u) << i;
         hit &= vbits;
         if (took && bg - genus0 < (uint32_t)NV) hit &= ~(1u << (bg - genus0));
-        // a block evaluated a second time (plan 3: an open sibling half re-opens the best block) meets the
+        // a block evaluated a second time meets the
         // standing champion again: it is not its own near-tie
         if (!took && opos - genus0 < (uint32_t)NV) {
 #pragma unroll
@@ -786,7 +794,7 @@ k_guess_bm(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, 
                 const uint32_t wj = __shfl_sync(0xffffffffu, wv, j);
                 acc += __ldg(bm + ((size_t)grp * PG_NWORDS + wj) * 32 + lane);
             }
-            // the table holds `count` units (blocks: 31 per group; half blocks: 32 per group)
+            // the table holds `count` units (blocks: PG_GB per group; parts: 32 per group)
             const uint32_t blk = (uint32_t)grp * (uint32_t)per_group + lane;
             const uint32_t key = ((int)lane < per_group && (int)blk < count) ? ((acc << 12) | blk) : 0xFFFFFFFFu;   // acc < 2^17, blk < 2^12
             bestkey = min(bestkey, __reduce_min_sync(0xffffffffu, key));
@@ -803,7 +811,7 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         int64_t slot0, const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot,
         int ntile64, double vmax, const unsigned long long *__restrict__ champ, const int32_t *__restrict__ guess,
         unsigned long long *__restrict__ items, unsigned int *__restrict__ item_count, unsigned int item_cap,
-        uint8_t *__restrict__ heavy, unsigned int light_max, const uint16_t *__restrict__ hm /* plan 3: guess[] holds half-block ids */)
+        uint8_t *__restrict__ heavy, unsigned int light_max, const uint16_t *__restrict__ hm /* plan 3: guess[] holds part ids */)
 {
     constexpr int NUNIT = BLOCK / 8;                // quarter-warps: one task each, lane = four blocks (one LDS.64 per draw)
     extern __shared__ uint4 sB[];                   // (n+1) rows x 4 uint4 (32 blocks x 16 bit); row n is zero
@@ -1378,7 +1386,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     if (noprune < 0) { const char *e = getenv("PG_NO_PRUNE"); noprune = (e && atoi(e)) ? 1 : 0; }
     int32_t *d_guess = cb.guess;
     if (noprune || md->ntile64 < 2) { d_guess = NULL; version = 1; }
-    // version 3 = plan 3 (half blocks, two reads per CTA, the default); 2 = plan 2 (whole best block);
+    // version 3 = plan 3 (best part of the best block, PG_PARTS reads per CTA, the default); 2 = plan 2 (whole best block);
     // 1 = plan 1 (every block, partial-sum pruning)
     unsigned nblk_y = (unsigned)md->ntile64;
     if (d_guess && version == 3) {
