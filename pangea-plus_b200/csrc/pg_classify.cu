@@ -294,6 +294,14 @@ int pg_extract_launch(pg_ctx *ctx, const pg_model *md, const uint32_t *d_planes,
                       int64_t count, uint16_t *d_words, int32_t *d_nwords, uint8_t *d_flags);
 int pg_pack_launch(pg_ctx *ctx, const char *d_bytes, const int64_t *d_off, int64_t count, uint32_t *d_planes);
 
+#include <time.h>
+static double pg_now_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double)ts.tv_sec + 1e-6 * (double)ts.tv_nsec;
+}
+
 static cudaEvent_t take_event(pg_ctx *ctx)
 {
     cudaEvent_t ev;
@@ -580,11 +588,22 @@ struct ClassifyJob {
         return PG_OK;
     }
 
-    // ranges of the batch: a short first one (its preparation cannot overlap anything), then chunks
-    int64_t next_range(int64_t r0) const
+    // ranges of the batch: a short first one (its preparation cannot overlap anything), then chunks.  With
+    // uploads in the picture (pg_classify) the ranges double from 8 192 reads up to the chunk size: the upload of
+    // range i+1 (twice the bytes) then fits under the kernels of range i, and the first kernels wait for 17 MB
+    // of text instead of 56 MB.
+    int64_t next_range(int64_t r0, bool uploads = false) const
     {
-        const int64_t first = CHUNK < 16384 ? CHUNK : 16384;
-        const int64_t r1 = r0 == 0 ? first : r0 + CHUNK;
+        int64_t r1;
+        if (uploads) {
+            int64_t len = 8192, a = 0;                  // 8 192, 16 384, ... , CHUNK, CHUNK, ...
+            while (a + len <= r0 && len < CHUNK) { a += len; len *= 2; }
+            if (len > CHUNK) len = CHUNK;
+            r1 = r0 + len;
+        } else {
+            const int64_t first = CHUNK < 16384 ? CHUNK : 16384;
+            r1 = r0 == 0 ? first : r0 + CHUNK;
+        }
         return r1 < count ? r1 : count;
     }
 };
@@ -689,8 +708,12 @@ static int classify_host_batch(pg_ctx *ctx, const pg_model *md, const pg_seqbatc
     if (!ctx->down_stream) PG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
     cudaStream_t cs = ctx->copy_stream, ds = ctx->down_stream;
 
+    static const bool timing = getenv("PG_TIMING") != NULL;          // host-side laps of one call, on stderr
+    const double t_start = timing ? pg_now_ms() : 0.0;
+#define PG_LAPMSG(what) do { if (timing) fprintf(stderr, "[pg_classify] %-28s %8.3f ms\n", what, pg_now_ms() - t_start); } while (0)
     ClassifyJob job;
     PG_TRY(job.begin(ctx, md, d_off, n, d_words, d_nwords, d_flags, opts, d_res, d_bw));
+    PG_LAPMSG("begin");
     // everything queued so far on the compute stream (scratch growth, counters) precedes the first upload
     {
         cudaEvent_t e = take_event(ctx);
@@ -724,17 +747,21 @@ static int classify_host_batch(pg_ctx *ctx, const pg_model *md, const pg_seqbatc
         return PG_OK;
     };
     cudaEvent_t ev_cur = NULL, ev_next = NULL;
-    int64_t r0 = 0, r1 = job.next_range(0);
+    int64_t r0 = 0, r1 = job.next_range(0, true);
     PG_TRY(prepare(r0, r1, &ev_cur));
     while (r0 < n) {
-        const int64_t r2 = job.next_range(r1);
+        const int64_t r2 = job.next_range(r1, true);
         if (r1 < n) PG_TRY(prepare(r1, r2, &ev_next));
         PG_TRY(job.range(r0, r1, ev_cur));
         PG_TRY(download(r0, r1));
+        PG_LAPMSG("range enqueued");
         r0 = r1; r1 = r2; ev_cur = ev_next; ev_next = NULL;
     }
+    PG_LAPMSG("all ranges enqueued");
     PG_TRY(job.finish());
+    PG_LAPMSG("finish (fallback passes)");
     PG_CUDA(ctx, cudaStreamSynchronize(ds));
+    PG_LAPMSG("downloads done");
     if (!job.redone.empty()) {
         // records rewritten by the fallback passes: gather them, one small copy, scatter on the host
         const int cnt = (int)job.redone.size();
@@ -759,6 +786,8 @@ static int classify_host_batch(pg_ctx *ctx, const pg_model *md, const pg_seqbatc
             if (d_bw) memcpy(boot_winners_host + (size_t)job.redone[(size_t)i] * PG_NUM_BOOT, bwc.data() + (size_t)i * PG_NUM_BOOT, 400);
         }
     }
+    PG_LAPMSG("fallback records scattered");
+#undef PG_LAPMSG
     return PG_OK;
 }
 
