@@ -293,6 +293,8 @@ static int ensure_boot_lists(pg_ctx *ctx, const std::vector<int> &need_n, int mi
 int pg_extract_launch(pg_ctx *ctx, const pg_model *md, const uint32_t *d_planes, const int64_t *d_off,
                       int64_t count, uint16_t *d_words, int32_t *d_nwords, uint8_t *d_flags);
 int pg_pack_launch(pg_ctx *ctx, const char *d_bytes, const int64_t *d_off, int64_t count, uint32_t *d_planes);
+int pg_extract_ascii_launch(pg_ctx *ctx, const pg_model *md, const char *d_bytes, const int64_t *d_off,
+                            int64_t count, uint16_t *d_words, int32_t *d_nwords, uint8_t *d_flags);
 
 #include <time.h>
 static double pg_now_ms(void)
@@ -689,15 +691,12 @@ static int classify_host_batch(pg_ctx *ctx, const pg_model *md, const pg_seqbatc
     const int64_t total = reads->off[n] - base0;
     PG_TRY(pg_scratch(ctx, &ctx->s_bytes, (size_t)total + 64));
     PG_TRY(pg_scratch(ctx, &ctx->s_off, (size_t)(n + 1) * 8));
-    const size_t nch = (size_t)(total >> 5) + n + 2;
-    PG_TRY(pg_scratch(ctx, &ctx->s_cand, nch * 12));
     PG_TRY(pg_scratch(ctx, &ctx->s_results, (size_t)n * sizeof(pg_result) + (boot_winners_host ? (size_t)n * 400 : 0)));
     PG_TRY(pg_scratch(ctx, &ctx->s_words, (size_t)total * 2 + 64));
     PG_TRY(pg_scratch(ctx, &ctx->s_nwords, (size_t)n * 4 + 64));
     PG_TRY(pg_scratch(ctx, &ctx->s_flags, (size_t)n * 2 + 64));
     char *d_bytes = (char *)ctx->s_bytes.p;
     int64_t *d_off = (int64_t *)ctx->s_off.p;
-    uint32_t *d_planes = (uint32_t *)ctx->s_cand.p;
     pg_result *d_res = (pg_result *)ctx->s_results.p;
     int32_t *d_bw = boot_winners_host ? (int32_t *)(d_res + n) : NULL;
     uint16_t *d_words = (uint16_t *)ctx->s_words.p;
@@ -731,8 +730,8 @@ static int classify_host_batch(pg_ctx *ctx, const pg_model *md, const pg_seqbatc
         PG_CUDA(ctx, cudaEventRecord(up, cs));
         PG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, up, 0));
         ctx->ev_free.push_back(up);
-        PG_TRY(pg_pack_launch(ctx, d_bytes, d_off + r0, r1 - r0, d_planes + 3 * r0));
-        PG_TRY(pg_extract_launch(ctx, md, d_planes + 3 * r0, d_off + r0, r1 - r0, d_words, d_nwords + r0, d_flags + 2 * r0));
+        // words straight from the text: the 2-bit plane store is only built for reads that stay on the device
+        PG_TRY(pg_extract_ascii_launch(ctx, md, d_bytes, d_off + r0, r1 - r0, d_words, d_nwords + r0, d_flags + 2 * r0));
         return job.fetch_counts(r0, r1, ev);
     };
     auto download = [&](int64_t r0, int64_t r1) -> int {

@@ -67,8 +67,9 @@ __device__ __forceinline__ uint32_t pg_spread8(uint32_t x)
 
 // K3b: one warp per read: word list (A1), orientation (A3), in-place reverse
 // complement of the list when the reverse strand has the larger prior sum.
+template <bool ASCII>
 __global__ void __launch_bounds__(256)
-k_extract(const uint32_t *__restrict__ planes, const int64_t *__restrict__ off, int64_t nreads,
+k_extract(const uint32_t *__restrict__ planes, const char *__restrict__ bytes, const int64_t *__restrict__ off, int64_t nreads,
           const float *__restrict__ logPrior, uint16_t *__restrict__ words,
           int32_t *__restrict__ nwords, uint8_t *__restrict__ flags /* [2*nreads]: reversed, status */)
 {
@@ -80,7 +81,7 @@ k_extract(const uint32_t *__restrict__ planes, const int64_t *__restrict__ off, 
         if (lane == 0) { nwords[i] = 0; flags[2 * i] = 0; flags[2 * i + 1] = 1; }
         return;
     }
-    const uint32_t *src = planes + 3 * pg_chunk_start(o, i);
+    const uint32_t *src = ASCII ? NULL : planes + 3 * pg_chunk_start(o, i);
     uint16_t *w = words + o;
     const int64_t nchunks = (len + 31) >> 5;
 
@@ -88,7 +89,16 @@ k_extract(const uint32_t *__restrict__ planes, const int64_t *__restrict__ off, 
     int n = 0;
     uint32_t plo = 0, phi = 0, pva = 0;
     for (int64_t c = 0; c < nchunks; c++) {
-        uint32_t lo = src[3 * c + 0], hi = src[3 * c + 1], va = src[3 * c + 2];
+        uint32_t lo, hi, va;
+        if (ASCII) {                                // the three bit planes of k_pack, straight from the text
+            const int64_t p = (c << 5) + lane;
+            const int code = p < len ? pg_base_code2((unsigned char)bytes[o + p]) : -1;
+            va = __ballot_sync(0xffffffffu, code >= 0);
+            lo = __ballot_sync(0xffffffffu, code >= 0 && (code & 1));
+            hi = __ballot_sync(0xffffffffu, code >= 0 && (code & 2));
+        } else {
+            lo = src[3 * c + 0]; hi = src[3 * c + 1]; va = src[3 * c + 2];
+        }
         // bits [lane-7 .. lane] of the 64-bit stream (prev:cur), oldest base lowest
         // = bits [lane+25 .. lane+32] of (cur:prev); __funnelshift_r wraps its shift
         // mod 32, so the part that lies wholly inside `cur` is shifted directly.
@@ -212,8 +222,20 @@ int pg_extract_launch(pg_ctx *ctx, const pg_model *md, const uint32_t *d_planes,
 {
     if (count == 0) return PG_OK;
     const int wpb = 8;
-    k_extract<<<(unsigned)((count + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
-        d_planes, d_off, count, md->d_logPrior, d_words, d_nwords, d_flags);
+    k_extract<false><<<(unsigned)((count + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+        d_planes, NULL, d_off, count, md->d_logPrior, d_words, d_nwords, d_flags);
+    PG_LAUNCHED(ctx);
+    return PG_OK;
+}
+
+// the same from ASCII text on the device: packing and extraction in one pass (no plane store)
+int pg_extract_ascii_launch(pg_ctx *ctx, const pg_model *md, const char *d_bytes, const int64_t *d_off,
+                            int64_t count, uint16_t *d_words, int32_t *d_nwords, uint8_t *d_flags)
+{
+    if (count == 0) return PG_OK;
+    const int wpb = 8;
+    k_extract<true><<<(unsigned)((count + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
+        NULL, d_bytes, d_off, count, md->d_logPrior, d_words, d_nwords, d_flags);
     PG_LAUNCHED(ctx);
     return PG_OK;
 }
