@@ -270,6 +270,8 @@ int pg_model_derive_quantised(pg_model *md)
     memcpy(&vm, &stat[0], 4);
     md->vmax = (double)vm;
     md->q_ok = stat[1] <= PG_Q_MAX;      // no entry was clamped: upper bounds hold for every genus
+    // field widths of the certified bookkeeping: part ids in 12 bits (k_guess_bm), block ids in 13 (items)
+    if (PG_PARTS * md->ntile64 >= 4096) md->q_ok = false;       // > ~50 000 genera: mode 1 runs the strict kernels
     return PG_OK;
 }
 
