@@ -75,3 +75,34 @@ def test_megaclustable_cli_matches_golden(tmp_path):
         assert out.read_text() == spec["table"], name
     r = subprocess.run([str(BIN / "megaclustable"), "-m", "x"], capture_output=True, text=True)
     assert r.stdout == "Please enter the correct parameters.\n"
+
+
+@pytest.mark.skipif(not op.have_megaclust_reference(), reason="reference tree or perl absent")
+def test_product_number_reader_matches_perl(tmp_path):
+    """csrc/pg_perlnum.h is what the megaclust2 executable (thresholds from argv) and the CUDA kernel (fields of the
+    input) both use; its host build must read numbers like Perl does: to the last bit on ordinary decimals (up to
+    19 digits, |exponent| <= 22: one exact table entry, one IEEE operation), within 4 ulp beyond that (the header
+    says so: decimal strings that close to a threshold are outside the defined behaviour)."""
+    import ctypes
+
+    src = tmp_path / "pn.c"
+    src.write_text('#include "pg_perlnum.h"\ndouble pn(const char *s, int n) { return pg_perl_number(s, n); }\n')
+    so = tmp_path / "pn.so"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", str(REPO / "pangea-plus_b200" / "csrc"),
+                    "-o", str(so), str(src)], check=True)
+    lib = ctypes.CDLL(str(so))
+    lib.pn.restype = ctypes.c_double
+    lib.pn.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    samples = ["98.63", "1e-20", "1E-21x", " 937", "+200.0", ".5e-20", "5.", ".", "", "abc", "0x10", "1_000", "inf", "-Infinity",
+               "3e", "3e+", "12e3junk", "  -4.25e-3 ", "100", "0.0", "7e-81", "95", "94.99", "80", "1e-5", "2e-45", "250",
+               "99.50", "100.00", "0.001", "1e-180", "3.5e-7"]
+    script = "for (@ARGV) { my $v = $_ + 0; print(($v != $v) ? 'nan' : sprintf('%.17g', $v), \"\\n\") }"
+    got = subprocess.run(["perl", "-e", script, "--", *samples], capture_output=True, text=True).stdout.split("\n")
+    far = {"7e-81", "1e-180", "2e-45"}                      # scaled by more than 10^22: several roundings
+    for s, g in zip(samples, got):
+        v = lib.pn(s.encode(), len(s))
+        mine = "nan" if v != v else "%.17g" % v
+        if s in far:
+            assert abs(v - float(g)) <= 4 * abs(float(g)) * 2.0 ** -52, (s, mine, g)
+        else:
+            assert mine.lower() == g.lower(), (s, mine, g)
