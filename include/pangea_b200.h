@@ -111,6 +111,13 @@ int pg_train(pg_ctx *ctx, const pg_seqbatch *seqs_host, const int32_t *genus_of_
 int pg_train_dev(pg_ctx *ctx, const pg_seqbatch *seqs_dev, const int32_t *genus_of_seq_dev,
                  int G, pg_model **out);
 void pg_model_free(pg_model *m);
+/* Sharded / streamed training (BASELINE configs[3]): add the counts of one more batch to a model made
+ * by pg_model_create() -- or trained before -- without deriving tables.  The counts are integers added atomically, so
+ * after an integer sum all-reduce of pg_model_buffers() over the ranks (ncclAllReduce / torch.distributed) every rank
+ * holds exactly the counts of one pg_train() over the whole set; pg_model_commit() then derives the tables.
+ * genus_of_seq[i] belongs to record i of the batch (seqs->off may be a slice of a larger offset array). */
+int pg_train_accumulate(pg_ctx *ctx, pg_model *m, const pg_seqbatch *seqs_host, const int32_t *genus_of_seq_host);
+int pg_train_accumulate_dev(pg_ctx *ctx, pg_model *m, const pg_seqbatch *seqs_dev, const int32_t *genus_of_seq_dev);
 
 /* Lineage of every genus for the A9 vote: anc[g*depth + d] = taxonomy node id
  * at level d (root first), -1 beyond the genus' own level.  depth <= PG_MAX_DEPTH.
@@ -159,7 +166,11 @@ typedef struct {
                                  2 = the whole best block + lower bounds + items         */
     int32_t light_max;        /* cert_plan 0: open (task, block) pairs per read above which the
                                  read is redone under cert_plan 1; 0 = default, -1 = none */
-    int32_t reserved[4];
+    int32_t bound_level;      /* cert_plan 0 only, results never depend on it: which kernel bounds the blocks the
+                                 best part leaves: 0 = by model size (coarse 8-bit first level when the model has
+                                 more than one group of 28 blocks), 1 = always the 16-bit bounds, 2 = always the
+                                 coarse first level + exact second level */
+    int32_t reserved[3];
 } pg_classify_opts;
 
 /* 1 if the model's quantised table certifies every deficit (mode 1 is then the

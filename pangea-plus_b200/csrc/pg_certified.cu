@@ -143,6 +143,25 @@ __global__ void k_partmin(const uint16_t *__restrict__ q, int ntile64, uint16_t 
     }
 }
 
+// Coarse first-level bound table of models with more than one group of blocks (k_bound8): one byte per (word, block),
+// c = min(bm >> PG_C8_SHIFT, PG_C8_MAX).  Rounded DOWN and capped, so (sum of c) << PG_C8_SHIFT is still a lower bound
+// of every genus of the block; 16 draws x PG_C8_MAX < 256, so sixteen rows add up in packed 8-bit fields without a carry.
+#define PG_C8_SHIFT 6                    // units of 64 / 128 = 0.5 nat
+#define PG_C8_MAX   15u
+__global__ void k_bm8(const uint16_t *__restrict__ bm, int ntile64, int pitch, uint8_t *__restrict__ bm8)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int col = (int)(idx % (size_t)pitch);
+    const size_t w = idx / (size_t)pitch;
+    if (w >= PG_NWORDS) return;
+    uint32_t c = PG_C8_MAX;                            // padding columns close at once; sibling-part columns are rewritten per read
+    if (col < ntile64) {
+        const uint32_t v = bm[((size_t)(col / PG_GB) * PG_NWORDS + w) * 32 + (col % PG_GB)];
+        c = min(v >> PG_C8_SHIFT, PG_C8_MAX);
+    }
+    bm8[idx] = (uint8_t)c;
+}
+
 // Table layout of certified mode.  pos_host[p] = genus stored at table position p, or -1 for padding;
 // npos is a multiple of 64 (one 64-position block per 128-byte row segment).  NULL = the genus order of
 // the training file.  The quantised tables are rebuilt by pg_model_derive_quantised().
@@ -161,17 +180,22 @@ int pg_model_set_layout(pg_model *md, const int32_t *pos_host, int npos)
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (nblk != md->ntile64) {                           // a different block count: the tables are re-allocated
         cudaFree(md->d_perm); cudaFree(md->d_blockmask); cudaFree(md->d_qtable); cudaFree(md->d_bmtable); cudaFree(md->d_hmtable);
-        md->d_perm = NULL; md->d_blockmask = NULL; md->d_qtable = NULL; md->d_bmtable = NULL; md->d_hmtable = NULL;
+        cudaFree(md->d_bm8);
+        md->d_perm = NULL; md->d_blockmask = NULL; md->d_qtable = NULL; md->d_bmtable = NULL; md->d_hmtable = NULL; md->d_bm8 = NULL;
     }
     md->ntile64 = nblk;
     md->ngroup = (nblk + PG_GB - 1) / PG_GB;
     md->ngroup_h = (PG_PARTS * nblk + 31) / 32;
+    md->sib0 = (nblk + 3) & ~3;                                  // the four sibling-part columns start 4-byte aligned
+    md->bm8_pitch = (md->sib0 + PG_PARTS + 15) & ~15;
     if (!md->d_perm) {
         PG_CUDA(ctx, cudaMalloc(&md->d_perm, full.size() * 4));
         PG_CUDA(ctx, cudaMalloc(&md->d_blockmask, mask.size() * 8));
     }
-    PG_CUDA(ctx, cudaMemcpy(md->d_perm, full.data(), full.size() * 4, cudaMemcpyHostToDevice));
-    PG_CUDA(ctx, cudaMemcpy(md->d_blockmask, mask.data(), mask.size() * 8, cudaMemcpyHostToDevice));
+    // on the context's (non-blocking) stream, like every consumer; `full` and `mask` are locals: wait before returning
+    PG_CUDA(ctx, cudaMemcpyAsync(md->d_perm, full.data(), full.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(ctx, cudaMemcpyAsync(md->d_blockmask, mask.data(), mask.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PG_OK;
 }
 
@@ -262,6 +286,15 @@ int pg_model_derive_quantised(pg_model *md)
     k_partmin<<<(unsigned)(((size_t)md->ntile64 * PG_NWORDS + 255) / 256), 256, 0, ctx->stream>>>(md->d_qtable, md->ntile64,
                                                                                                   md->d_hmtable);
     PG_LAUNCHED(ctx);
+    if (!md->d_bm8) {
+        cudaError_t e = cudaMalloc(&md->d_bm8, (size_t)PG_NWORDS * md->bm8_pitch);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return pg_fail(ctx, PG_ENOMEM, "coarse bound table allocation failed: %s", cudaGetErrorString(e)); }
+    }
+    {
+        const size_t c8 = (size_t)PG_NWORDS * md->bm8_pitch;
+        k_bm8<<<(unsigned)((c8 + 255) / 256), 256, 0, ctx->stream>>>(md->d_bmtable, md->ntile64, md->bm8_pitch, md->d_bm8);
+        PG_LAUNCHED(ctx);
+    }
     unsigned int stat[2];
     PG_CUDA(ctx, cudaMemcpyAsync(stat, d_stat, 8, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -996,6 +1029,372 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
 #undef PG_SURVIVE
 }
 
+
+// ------------------------------------------------------------------ large models: coarse first-level bounds
+//
+// With more than one group of blocks (G > ~1 800) k_bound would stage the read's rows and walk the 100 sample lists
+// once per group of 28 blocks (8 times for 10 000 genera, 121 ns per read).  Nearly all of those blocks are FAR from
+// the read, and for them a much cheaper table proves the same thing: one byte per (word, block), c = min(bm >> 6, 15)
+// (k_bm8).  c << 6 <= bm, so LB8(task, block) = (sum of c over the task's draws) << 6 is still a lower bound of every
+// genus of the block.  A row of ALL blocks is ntile64 bytes (184 for 10 000 genera), so one CTA stages the read once
+// and a lane adds a 16-byte segment (16 blocks) per draw: sixteen draws accumulate in packed 8-bit fields without a
+// carry (16 x 15 < 256), then spill into packed 16-bit sums.  Early exits would not pay (a (task, block) pair closes
+// after ~20 of 60 draws, the 16 pairs of a lane never together), so the loop is straight-line.
+// Level 2: the few pairs the coarse bound leaves open (~2 % on the rdp_scale workload) are bounded again with the exact
+// 16-bit minima, gathered from the L2-resident bm / hm tables by 8 lanes per pair; what survives are the items.
+#define PG_B8_LIST 1536             // (task, segment, mask) entries per CTA after level 1
+#define PG_B8_KEEP 4096             // pairs per CTA after level 2 (kept in the dead row area)
+#define PG_B8_MAXSEG 16             // 16-byte segments (of 16 blocks) per CTA
+#define PG_B8_MAXBLOCK 448
+
+// grid (reads, column chunks); block = any multiple of 32 up to PG_B8_MAXBLOCK (the host picks the size that wastes
+// the fewest lanes in the last round of units).  Several CTAs per SM, so that the staging, the two barriers and the
+// latency-bound second level of one CTA hide behind the shared-memory loop of another.
+__global__ void __launch_bounds__(PG_B8_MAXBLOCK, 2)
+k_bound8(const uint8_t *__restrict__ bm8, int pitch_g, int nsegc, int pitch_s, const uint16_t *__restrict__ bm,
+         const uint16_t *__restrict__ hm, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
+         const int32_t *__restrict__ nwords, const uint8_t *__restrict__ flags, const int32_t *__restrict__ order,
+         int64_t slot0, const uint32_t *__restrict__ boot_pool, const int32_t *__restrict__ boot_off, int min_boot,
+         int ntile64, int sib0, double vmax, const unsigned long long *__restrict__ champ,
+         const int32_t *__restrict__ guess, unsigned long long *__restrict__ items, unsigned int *__restrict__ item_count,
+         unsigned int item_cap, uint8_t *__restrict__ heavy, unsigned int light_max)
+{
+    extern __shared__ uint4 sR8[];                  // (n+1) rows x pitch_s bytes; row n is zero
+    __shared__ uint32_t s_list[PG_B8_LIST];         // level 1: task << 21 | segment << 16 | mask of open cells
+    __shared__ uint32_t s_thr[PG_NUM_BOOT + 1];     // champion + margin per task (0xFFFFFFFF = no champion yet)
+    __shared__ uint32_t s_full[PG_B8_MAXSEG * 16];  // task 0: coarse sums per column
+    __shared__ unsigned int s_cnt1, s_cnt2, s_base;
+
+    const int tid = threadIdx.x, BLOCK = blockDim.x;
+    const int64_t read = order[blockIdx.x];
+    if (flags[2 * read + 1]) return;
+    const int n = nwords[read];
+    if (n == 0) return;
+    const size_t rc = (size_t)slot0 + blockIdx.x;
+    const uint16_t *w = words + off[read];
+    const int segbase = (int)blockIdx.y * nsegc;
+    const int nsc = min(nsegc, pitch_g / 16 - segbase);
+    char *rows = reinterpret_cast<char *>(sR8);
+
+    // ---- stage this chunk of the read's coarse rows: the word ids first (they are needed again by level 2), then one
+    // 16-byte copy per (row, segment)
+    uint16_t *sw = reinterpret_cast<uint16_t *>(rows + (size_t)(n + 1) * pitch_s);
+    for (int j = tid; j < n; j += BLOCK) sw[j] = w[j];
+    __syncthreads();
+    {
+        const unsigned long long magic = (0x100000000ULL + (unsigned long long)nsc - 1ULL) / (unsigned long long)nsc;   // c / nsc, exact for c < 2^28
+        const uint8_t *src = bm8 + (size_t)segbase * 16;
+        for (int c = tid; c < n * nsc; c += BLOCK) {
+            const int r = (int)(((unsigned long long)c * magic) >> 32), l = c - r * nsc;
+            pg_cp_async16(rows + (size_t)r * pitch_s + l * 16, src + (size_t)sw[r] * pitch_g + l * 16);
+        }
+    }
+    const int gs = guess[rc];
+    const int best = gs / PG_PARTS, own = gs % PG_PARTS;
+    const int col0 = segbase * 16, col1 = col0 + nsc * 16;
+    const bool sib_here = sib0 >= col0 && sib0 < col1;
+    const bool best_here = best >= col0 && best < col1;
+    int k = n >> 3;
+    if (k < min_boot) k = min_boot;
+    const int nb = (k + 3) >> 2;
+    for (int t = tid; t <= PG_NUM_BOOT; t += BLOCK) {
+        const unsigned long long cv = __ldg(champ + rc * (PG_NUM_BOOT + 1) + t);
+        s_thr[t] = (cv == PG_CHAMP_INIT) ? 0xFFFFFFFFu : (uint32_t)(cv >> 32) + pg_margin(t == 0 ? n : k, vmax);
+    }
+    for (int c = tid; c < PG_B8_MAXSEG * 16; c += BLOCK) s_full[c] = 0u;
+    if (tid < nsc * 4) reinterpret_cast<uint32_t *>(rows + (size_t)n * pitch_s)[tid] = 0u;
+    if (tid == 0) { s_cnt1 = 0u; s_cnt2 = 0u; }
+    // the best block was evaluated on one part only: its other parts compete like blocks of their own, in the four
+    // sibling columns (coarse part minima from hm, gathered while the copies are in flight); the best block's own
+    // column and the own part never compete: PG_C8_MAX
+    uint32_t sibv[2] = {0u, 0u};
+    if (sib_here) {
+        const uint16_t *hrow = hm + (size_t)((best * PG_PARTS) >> 5) * PG_NWORDS * 32 + ((best * PG_PARTS) & 31);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int j = tid + u * BLOCK;
+            if (j < n) {
+                const uint2 hv = __ldg(reinterpret_cast<const uint2 *>(hrow + (size_t)sw[j] * 32));
+                uint32_t p0 = min((hv.x & 0xFFFFu) >> PG_C8_SHIFT, PG_C8_MAX), p1 = min((hv.x >> 16) >> PG_C8_SHIFT, PG_C8_MAX);
+                uint32_t p2 = min((hv.y & 0xFFFFu) >> PG_C8_SHIFT, PG_C8_MAX), p3 = min((hv.y >> 16) >> PG_C8_SHIFT, PG_C8_MAX);
+                if (own == 0) p0 = PG_C8_MAX;
+                if (own == 1) p1 = PG_C8_MAX;
+                if (own == 2) p2 = PG_C8_MAX;
+                if (own == 3) p3 = PG_C8_MAX;
+                sibv[u] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+            }
+        }
+    }
+    pg_cp_async_wait_all();
+    __syncthreads();
+    if (sib_here || best_here) {
+        const uint16_t *hrow = hm + (size_t)((best * PG_PARTS) >> 5) * PG_NWORDS * 32 + ((best * PG_PARTS) & 31);
+        for (int j = tid, u = 0; j < n; j += BLOCK, u++) {
+            char *row = rows + (size_t)j * pitch_s;
+            if (best_here) row[best - col0] = (char)PG_C8_MAX;
+            if (sib_here) {
+                uint32_t pv;
+                if (u < 2) pv = sibv[u];
+                else {
+                    const uint2 hv = __ldg(reinterpret_cast<const uint2 *>(hrow + (size_t)sw[j] * 32));
+                    uint32_t p0 = min((hv.x & 0xFFFFu) >> PG_C8_SHIFT, PG_C8_MAX), p1 = min((hv.x >> 16) >> PG_C8_SHIFT, PG_C8_MAX);
+                    uint32_t p2 = min((hv.y & 0xFFFFu) >> PG_C8_SHIFT, PG_C8_MAX), p3 = min((hv.y >> 16) >> PG_C8_SHIFT, PG_C8_MAX);
+                    if (own == 0) p0 = PG_C8_MAX;
+                    if (own == 1) p1 = PG_C8_MAX;
+                    if (own == 2) p2 = PG_C8_MAX;
+                    if (own == 3) p3 = PG_C8_MAX;
+                    pv = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+                }
+                *reinterpret_cast<uint32_t *>(row + (sib0 - col0)) = pv;
+            }
+        }
+        __syncthreads();
+    }
+
+#define PG8_ADD(v_) { const uint4 t_ = (v_); a0 += t_.x; a1 += t_.y; a2 += t_.z; a3 += t_.w; }
+#define PG8_SPILL()                                                                                   \
+    { s[0] += a0 & 0x00FF00FFu; s[1] += (a0 >> 8) & 0x00FF00FFu; s[2] += a1 & 0x00FF00FFu; s[3] += (a1 >> 8) & 0x00FF00FFu;   \
+      s[4] += a2 & 0x00FF00FFu; s[5] += (a2 >> 8) & 0x00FF00FFu; s[6] += a3 & 0x00FF00FFu; s[7] += (a3 >> 8) & 0x00FF00FFu;   \
+      a0 = a1 = a2 = a3 = 0u; }
+    // sum of cell c (column 16*segment + c) in the packed 16-bit registers
+#define PG8_CELL(c) ((s[2 * ((c) >> 2) + ((c) & 1)] >> (16 * (((c) >> 1) & 1))) & 0xFFFFu)
+    // is column `col` a competitor, and as which block field?
+    auto field_of = [&](int col) -> int {
+        if (col < ntile64) return col != best ? col : -1;
+        const int part = col - sib0;
+        if (part >= 0 && part < PG_PARTS && part != own) return 0x8000 | (part << 13) | best;
+        return -1;
+    };
+
+    // ---- level 1.  Units: task 0 in chunks of 64 rows (combined through s_full), then one unit per (replicate, segment)
+    const uint4 *lists = reinterpret_cast<const uint4 *>(boot_pool + boot_off[n]);
+    const int n0u = ((n + 63) >> 6) * nsc;
+    const int nunit = n0u + (nb > 0 ? PG_NUM_BOOT * nsc : 0);
+    for (int u = tid; u < nunit; u += BLOCK) {
+        uint32_t s[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}, a0 = 0u, a1 = 0u, a2 = 0u, a3 = 0u;
+        if (u < n0u) {
+            const int ch = u / nsc, seg = u - ch * nsc;
+            const char *base = rows + seg * 16;
+            const int j1 = min(n, ch * 64 + 64);
+            for (int j = ch * 64; j < j1; j += 16) {
+#pragma unroll
+                for (int uu = 0; uu < 16; uu++)
+                    if (j + uu < j1) PG8_ADD(*reinterpret_cast<const uint4 *>(base + (size_t)(j + uu) * pitch_s))
+                PG8_SPILL()
+            }
+#pragma unroll
+            for (int c = 0; c < 16; c++) atomicAdd(&s_full[seg * 16 + c], PG8_CELL(c));
+            continue;
+        }
+        const int v = u - n0u;
+        const int task = v / nsc, seg = v - task * nsc;
+        const char *base = rows + seg * 16;
+        const uint4 *lp = lists + (size_t)(task >> 2) * nb * 4 + (task & 3);
+#define PG8_ROW(o) (*reinterpret_cast<const uint4 *>(base + ((o) >> 7) * pitch_s))
+        // list entries run one batch (four draws) ahead of the rows; a spill every four batches (16 draws x 15 < 256)
+        uint4 q = __ldg(lp);
+        for (int b = 0; b < nb; b++) {
+            const uint4 qc = q;
+            if (b + 1 < nb) q = __ldg(lp + (size_t)(b + 1) * 4);
+            const uint4 x0 = PG8_ROW(qc.x), x1 = PG8_ROW(qc.y), x2 = PG8_ROW(qc.z), x3 = PG8_ROW(qc.w);
+            PG8_ADD(x0) PG8_ADD(x1) PG8_ADD(x2) PG8_ADD(x3)
+            if ((b & 3) == 3) PG8_SPILL()
+        }
+        PG8_SPILL()
+#undef PG8_ROW
+        const uint32_t thr = s_thr[1 + task];
+        const uint32_t thr8 = min(thr >> PG_C8_SHIFT, 0xFFFFu);        // (sum << 6) <= thr  <=>  sum <= thr >> 6
+        const uint32_t m2 = __vminu2(__vminu2(__vminu2(s[0], s[1]), __vminu2(s[2], s[3])),
+                                     __vminu2(__vminu2(s[4], s[5]), __vminu2(s[6], s[7])));
+        if (min(m2 & 0xFFFFu, m2 >> 16) <= thr8) {
+            uint32_t mask = 0u;
+#pragma unroll
+            for (int c = 0; c < 16; c++)
+                if (PG8_CELL(c) <= thr8 && field_of(col0 + seg * 16 + c) >= 0) mask |= 1u << c;
+            if (mask) {
+                const unsigned int pos = atomicAdd(&s_cnt1, 1u);
+                if (pos < PG_B8_LIST) s_list[pos] = ((uint32_t)(1 + task) << 21) | ((uint32_t)seg << 16) | mask;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < nsc * 16) {                               // task 0
+        const uint32_t thr = s_thr[0];
+        if (s_full[tid] <= (thr >> PG_C8_SHIFT) && field_of(col0 + tid) >= 0) {
+            const unsigned int pos = atomicAdd(&s_cnt1, 1u);
+            if (pos < PG_B8_LIST) s_list[pos] = ((uint32_t)(tid >> 4) << 16) | (1u << (tid & 15));
+        }
+    }
+    __syncthreads();
+
+    // ---- level 2: exact 16-bit bound of every open pair, 8 lanes per list entry.  The staged rows are dead now:
+    // their memory takes the read's word ids and the list of surviving pairs.
+    const unsigned int cnt1 = s_cnt1;
+    const bool overflow = cnt1 > PG_B8_LIST;
+    if (!overflow && cnt1 == 0u) return;
+    uint32_t *s_keep = reinterpret_cast<uint32_t *>(rows);
+    const unsigned int keep_cap = min((unsigned int)PG_B8_KEEP, (unsigned int)(((size_t)(n + 1) * pitch_s) / 4));
+    if (!overflow) {
+        const int l = tid & 7;
+        const unsigned gmask = 0xFFu << (tid & 24);
+        const uint32_t *lists32 = reinterpret_cast<const uint32_t *>(lists);
+        for (unsigned int e = tid >> 3; e < cnt1; e += BLOCK >> 3) {
+            const uint32_t en = s_list[e];
+            const int task = (int)(en >> 21), seg = (int)((en >> 16) & 31u);
+            const uint32_t thr = s_thr[task];
+            const int t1 = task > 0 ? task - 1 : 0;
+            const uint32_t *lp32 = lists32 + ((size_t)(t1 >> 2) * nb * 4 + (t1 & 3)) * 4;
+            const int terms = task == 0 ? n : k;
+            // 64 terms per pass: lane l takes terms l, l + 8, ...; their word ids are looked up once for all the open
+            // cells of the entry, and a lane's gathers are in flight together
+            uint32_t sum[16];
+#pragma unroll
+            for (int c = 0; c < 16; c++) sum[c] = 0u;
+            for (int j0 = 0; j0 < terms; j0 += 64) {
+                uint32_t wj[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int j = j0 + l + 8 * i;
+                    wj[i] = 0xFFFFFFFFu;
+                    if (j < terms) {
+                        const uint32_t r = task == 0 ? (uint32_t)j : __ldg(lp32 + (size_t)(j >> 2) * 16 + (j & 3)) / PG_ROW_PITCH;
+                        wj[i] = sw[r];
+                    }
+                }
+                uint32_t mask = en & 0xFFFFu;
+                while (mask) {
+                    const int c = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int fld = field_of(col0 + seg * 16 + c);
+                    const uint16_t *tb;
+                    if (fld & 0x8000) {
+                        const int pb = best * PG_PARTS + ((fld >> 13) & 3);
+                        tb = hm + (size_t)(pb >> 5) * PG_NWORDS * 32 + (pb & 31);
+                    } else {
+                        tb = bm + (size_t)(fld / PG_GB) * PG_NWORDS * 32 + (fld % PG_GB);
+                    }
+                    uint32_t v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) v[i] = wj[i] != 0xFFFFFFFFu ? (uint32_t)__ldg(tb + (size_t)wj[i] * 32) : 0u;
+                    uint32_t acc = 0u;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) acc += v[i];
+#pragma unroll
+                    for (int cc = 0; cc < 16; cc++)
+                        if (cc == c) sum[cc] += acc;
+                }
+            }
+            uint32_t mask = en & 0xFFFFu;
+            while (mask) {
+                const int c = __ffs(mask) - 1;
+                mask &= mask - 1;
+                uint32_t tot = 0u;
+#pragma unroll
+                for (int cc = 0; cc < 16; cc++)
+                    if (cc == c) tot = sum[cc];
+                tot += __shfl_xor_sync(gmask, tot, 1);
+                tot += __shfl_xor_sync(gmask, tot, 2);
+                tot += __shfl_xor_sync(gmask, tot, 4);
+                if (l == 0 && tot <= thr) {
+                    const unsigned int pos = atomicAdd(&s_cnt2, 1u);
+                    if (pos < keep_cap) s_keep[pos] = ((uint32_t)task << 16) | (uint32_t)field_of(col0 + seg * 16 + c);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned int cnt = s_cnt2;
+    if (!overflow && cnt == 0u) return;
+    if (tid == 0) {
+        unsigned int b = 0xFFFFFFFFu;
+        if (!overflow && cnt <= light_max && cnt <= keep_cap) {
+            b = atomicAdd(item_count, cnt);
+            if (b > item_cap || cnt > item_cap - b) {          // buffer full: blank what fits, redo the read
+                for (unsigned int i = b; i < item_cap && i < b + cnt; i++) items[i] = (unsigned long long)PG_ITEM_NULL << 16;
+                b = 0xFFFFFFFFu;
+            }
+        }
+        if (b == 0xFFFFFFFFu) heavy[rc] = 1;
+        s_base = b;
+    }
+    __syncthreads();
+    const unsigned int gb = s_base;
+    if (gb == 0xFFFFFFFFu) return;
+    for (unsigned int i = tid; i < cnt; i += BLOCK)
+        items[gb + i] = ((unsigned long long)rc << 32) | s_keep[i];      // rc << 32 | task << 16 | block
+#undef PG8_ADD
+#undef PG8_SPILL
+#undef PG8_CELL
+}
+
+// The block to evaluate first, from the coarse table: 32 sampled words x every block column -> the PG_G8_CAND blocks
+// with the smallest coarse sums -> exact part minima (hm) of those blocks' parts -> the best part.  (k_guess_bm reads
+// the part minima of EVERY part: 23 groups x 32 words for 10 000 genera.)
+#define PG_G8_CAND 8
+__global__ void __launch_bounds__(256)
+k_guess8(const uint8_t *__restrict__ bm8, int pitch_g, const uint16_t *__restrict__ hm, const uint16_t *__restrict__ words,
+         const int64_t *__restrict__ off, const int32_t *__restrict__ nwords, const int32_t *__restrict__ order,
+         int nreads_b, int64_t slot0, int ntile64, int32_t *__restrict__ guess)
+{
+    extern __shared__ uint16_t s_sum[];             // [8 warps][pitch_g] coarse sums per column
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (slot >= nreads_b) return;
+    const int64_t read = order[slot];
+    const int n = nwords[read];
+    uint32_t best = 0u;
+    if (n > 0) {
+        uint16_t *mysum = s_sum + (size_t)warp * pitch_g;
+        const uint16_t *w = words + off[read];
+        const int ns = n < 32 ? n : 32, stride = n / ns;
+        const uint32_t wv = lane < ns ? (uint32_t)__ldg(w + lane * stride) : 0u;
+        // lane owns the 4-byte column groups lane, lane + 32, ... (every lane takes part in the shuffles)
+        const int ncg = pitch_g / 4;
+        for (int cg0 = 0; cg0 < ncg; cg0 += 32) {
+            const int cg = cg0 + lane;
+            uint32_t lo = 0u, hi = 0u;              // packed 16-bit sums of bytes {0,2} and {1,3}
+            for (int j = 0; j < ns; j++) {
+                const uint32_t wj = __shfl_sync(0xffffffffu, wv, j);
+                if (cg < ncg) {
+                    const uint32_t x = __ldg(reinterpret_cast<const uint32_t *>(bm8 + (size_t)wj * pitch_g) + cg);
+                    lo += x & 0x00FF00FFu;
+                    hi += (x >> 8) & 0x00FF00FFu;
+                }
+            }
+            if (cg < ncg) {
+                mysum[4 * cg + 0] = (uint16_t)(lo & 0xFFFFu); mysum[4 * cg + 1] = (uint16_t)(hi & 0xFFFFu);
+                mysum[4 * cg + 2] = (uint16_t)(lo >> 16);     mysum[4 * cg + 3] = (uint16_t)(hi >> 16);
+            }
+        }
+        __syncwarp();
+        // the PG_G8_CAND smallest (sum, column) keys, one per round; keys are distinct
+        uint32_t last = 0u, mycand = 0u;
+        bool first = true;
+        for (int r = 0; r < PG_G8_CAND; r++) {
+            uint32_t kmin = 0xFFFFFFFFu;
+            for (int c = lane; c < ntile64; c += 32) {
+                const uint32_t key = ((uint32_t)mysum[c] << 12) | (uint32_t)c;
+                if ((first || key > last) && key < kmin) kmin = key;
+            }
+            kmin = __reduce_min_sync(0xffffffffu, kmin);
+            if (kmin == 0xFFFFFFFFu) kmin = last;   // fewer than PG_G8_CAND blocks: repeat the last one
+            last = kmin;
+            first = false;
+            if ((lane >> 2) == r) mycand = kmin & 0xFFFu;
+        }
+        // lane = (candidate, part): exact part minima over the sampled words
+        const uint32_t pb = mycand * PG_PARTS + (lane & 3);
+        const uint16_t *tb = hm + (size_t)(pb >> 5) * PG_NWORDS * 32 + (pb & 31);
+        uint32_t acc = 0u;
+        for (int j = 0; j < ns; j++) {
+            const uint32_t wj = __shfl_sync(0xffffffffu, wv, j);
+            acc += __ldg(tb + (size_t)wj * 32);
+        }
+        best = __reduce_min_sync(0xffffffffu, (acc << 12) | pb) & 0xFFFu;      // acc < 2^17, pb < 2^12
+    }
+    if (lane == 0) guess[slot0 + slot] = (int32_t)best;
+}
+
 // One group of 8 lanes per item (read, block, task): the block's 64 exact sums straight from the
 // L2-resident table (an item is 60 rows of 128 bytes; staging the read's 486 rows would cost more),
 // stopping as soon as every partial sum is above champion + margin.
@@ -1391,7 +1790,41 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     // version 3 = plan 3 (best part of the best block, PG_PARTS reads per CTA, the default); 2 = plan 2 (whole best block);
     // 1 = plan 1 (every block, partial-sum pruning)
     unsigned nblk_y = (unsigned)md->ntile64;
-    if (d_guess && version == 3) {
+    // large models (more than one group of blocks): coarse first-level bounds over all blocks at once (k_bound8)
+    static int env_b8 = -2;                             // PG_BOUND8=0: never, 1: always (A/B switch)
+    if (env_b8 == -2) { const char *e = getenv("PG_BOUND8"); env_b8 = e ? atoi(e) : -1; }
+    const int blevel = env_b8 >= 0 ? (env_b8 ? 2 : 1) : cb.bound_level;
+    int nsegc = 0, pitch_s = 0, nchunk8 = 0, block8 = PG_B8_MAXBLOCK;
+    bool use8 = d_guess && version == 3 && md->d_bm8 && (blevel == 2 || (blevel == 0 && md->ngroup > 1));
+    if (use8) {
+        // column chunks sized for two CTAs of up to 448 threads per SM (a 10 000-genus model with 486-word reads: one
+        // chunk of 12 segments, 102 KB); four smaller CTAs per SM were measured: the 96-byte row pitch that fits costs
+        // 70 % more shared-memory wavefronts in bank conflicts
+        const int nseg_total = md->bm8_pitch / 16;
+        const size_t budget = 103 * 1024 - (size_t)nmax * 2;
+        int maxseg = (int)(budget / ((size_t)(nmax + 1) * 16));
+        if (maxseg > PG_B8_MAXSEG) maxseg = PG_B8_MAXSEG;
+        if (maxseg < 1) use8 = false;
+        else {
+            nchunk8 = (nseg_total + maxseg - 1) / maxseg;
+            nsegc = (nseg_total + nchunk8 - 1) / nchunk8;
+            pitch_s = nsegc * 16;
+            // an odd number of 16-byte units per row spreads the rows of a warp's tasks over all bank offsets
+            if (!(nsegc & 1) && (size_t)(nmax + 1) * (pitch_s + 16) <= budget) pitch_s += 16;
+            // block size: the one that leaves the fewest idle lanes in the last round of (task, segment) units
+            const int units = nsegc * (((nmax + 63) >> 6) + PG_NUM_BOOT);
+            double best_waste = 1e30;
+            for (int bsz = PG_B8_MAXBLOCK; bsz >= 256; bsz -= 32) {
+                const double waste = (double)((units + bsz - 1) / bsz) * bsz / units;
+                if (waste < best_waste - 1e-9) { best_waste = waste; block8 = bsz; }
+            }
+        }
+    }
+    if (use8) {
+        k_guess8<<<(nreads_b + 7) / 8, 256, (size_t)8 * md->bm8_pitch * 2, ctx->stream>>>(
+            md->d_bm8, md->bm8_pitch, md->d_hmtable, d_words, d_off, d_nwords, d_order, (int)nreads_b, slot0, md->ntile64, d_guess);
+        PG_LAUNCHED(ctx);
+    } else if (d_guess && version == 3) {
         k_guess_bm<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_hmtable, d_words, d_off, d_nwords, d_order, (int)nreads_b,
                                                                slot0, PG_PARTS * md->ntile64, 32, md->ngroup_h, d_guess);
         PG_LAUNCHED(ctx);
@@ -1437,6 +1870,15 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     PG_CUDA(ctx, cudaMemsetAsync(cb.counters + 2, 0, 4, ctx->stream));
     // (a two-reads-per-CTA k_bound with interleaved rows, like k_classify_h, was measured: same wavefronts,
     // 46 % more instructions, 28 % slower -- LDS.64 rows of 64 bytes gain nothing from the interleave)
+    if (use8) {
+        const size_t bsmem = (size_t)(nmax + 1) * pitch_s + (((size_t)nmax * 2 + 15) & ~(size_t)15);
+        PG_CUDA(ctx, cudaFuncSetAttribute(k_bound8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+        k_bound8<<<dim3(nreads_b, (unsigned)nchunk8), block8, bsmem, ctx->stream>>>(
+            md->d_bm8, md->bm8_pitch, nsegc, pitch_s, md->d_bmtable, md->d_hmtable, d_words, d_off, d_nwords, d_flags, d_order,
+            slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->ntile64, md->sib0, md->vmax, cb.champ, d_guess, cb.items,
+            cb.counters + 2, cb.item_cap, cb.heavy, (unsigned int)(cb.light_max == 0 ? PG_B8_KEEP : light_max));
+        PG_LAUNCHED(ctx);
+    } else {
     const size_t bsmem = (size_t)(nmax + 1) * 64;
     PG_CUDA(ctx, cudaFuncSetAttribute(k_bound<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
     k_bound<160><<<dim3(nreads_b, (unsigned)md->ngroup), 160, bsmem, ctx->stream>>>(
@@ -1444,6 +1886,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
         md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.counters + 2, cb.item_cap, cb.heavy,
         (unsigned int)light_max, version == 3 ? md->d_hmtable : NULL);
     PG_LAUNCHED(ctx);
+    }
     static int light_ctas = 0;                          // resident CTAs per SM of the persistent item kernel
     if (!light_ctas) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&light_ctas, k_light, 256, 0) != cudaSuccess || light_ctas < 1) light_ctas = 2;

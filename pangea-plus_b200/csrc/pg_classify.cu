@@ -268,7 +268,7 @@ static int ensure_boot_lists(pg_ctx *ctx, const std::vector<int> &need_n, int mi
         PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         PG_CUDA(ctx, cudaMalloc(&np, cap * sizeof(uint32_t)));
         if (ctx->d_boot_pool) {
-            PG_CUDA(ctx, cudaMemcpy(np, ctx->d_boot_pool, ctx->boot_used * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+            PG_CUDA(ctx, pg_copy_sync(ctx, np, ctx->d_boot_pool, ctx->boot_used * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
             PG_CUDA(ctx, cudaFree(ctx->d_boot_pool));
         }
         ctx->d_boot_pool = np;
@@ -379,6 +379,8 @@ struct ClassifyJob {
         d_order = (int32_t *)ctx->s_order.p;
         memset(&cb, 0, sizeof cb);
         cb.light_max = opts ? opts->light_max : 0;
+        cb.bound_level = opts ? opts->bound_level : 0;
+        if (cb.bound_level < 0 || cb.bound_level > 2) return pg_fail(ctx, PG_EINVAL, "unknown bound_level %d", cb.bound_level);
         if (certified) {
             PG_TRY(pg_scratch(ctx, &ctx->s_champ, (size_t)cmax * nkeys * 8));
             PG_TRY(pg_scratch(ctx, &ctx->s_ncand, (size_t)cmax * 4));
@@ -872,7 +874,7 @@ extern "C" int pg_boot_indices(pg_ctx *ctx, int32_t n, int32_t min_boot_words, u
     if (k < min_boot_words) k = min_boot_words;
     const int nb = (k + 3) >> 2, il = 32 / bucket_of(n).lpr;
     std::vector<uint32_t> tmp(pg_boot_list_entries(k, il));
-    PG_CUDA(ctx, cudaMemcpy(tmp.data(), ctx->d_boot_pool + ctx->h_boot_off[n], tmp.size() * 4, cudaMemcpyDeviceToHost));
+    PG_CUDA(ctx, pg_copy_sync(ctx, tmp.data(), ctx->d_boot_pool + ctx->h_boot_off[n], tmp.size() * 4, cudaMemcpyDeviceToHost));
     for (int run = 0; run < PG_NUM_BOOT; run++)
         for (int j = 0; j < k; j++) {
             size_t e = ((size_t)(run / il) * nb * il + (run % il)) * 4 + (size_t)(j >> 2) * il * 4 + (j & 3);

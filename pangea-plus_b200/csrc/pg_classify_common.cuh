@@ -106,6 +106,7 @@ struct PgCertBufs {
     unsigned long long *items;       // [item_cap] (read, block, task) still to evaluate exactly
     unsigned int        item_cap;
     int                 light_max;   // pg_classify_opts.light_max
+    int                 bound_level; // pg_classify_opts.bound_level
     unsigned int       *counters;    // [0] strict fallbacks, [1] heavy reads, [2] items of the bucket in flight, [3] items so far
     uint8_t            *heavy;       // [reads of the chunk] flag
     int32_t            *fb_list, *hv_list;   // [reads of the call] read indices, appended across chunks

@@ -113,8 +113,8 @@ extern "C" int pg_fasta_ingest(pg_ctx *ctx, const char *text_host, int64_t len, 
             ctx->launches++;
         }
         FA_TRY(pg_device_scan(ctx, d_cnt, nlines, d_pos));              // sequence bytes above each line
-        FA_CUDA(cudaMemcpy(&nrec, d_rec + nlines, 8, cudaMemcpyDeviceToHost));
-        FA_CUDA(cudaMemcpy(&total, d_pos + nlines, 8, cudaMemcpyDeviceToHost));
+        FA_CUDA(pg_copy_sync(ctx, &nrec, d_rec + nlines, 8, cudaMemcpyDeviceToHost));
+        FA_CUDA(pg_copy_sync(ctx, &total, d_pos + nlines, 8, cudaMemcpyDeviceToHost));
         *nrec_out = nrec;
         if (nrec > cap) { rc = pg_fail(ctx, PG_ERANGE, "pg_fasta_ingest: %lld records, room for %lld", (long long)nrec, (long long)cap); goto done; }
         FA_TRY(pg_scratch(ctx, &ctx->s_bytes, (size_t)total + 64));    // compacted sequence bytes
@@ -159,9 +159,9 @@ extern "C" int pg_fasta_last_bytes(pg_ctx *ctx, int64_t nrec, char *bytes_host, 
 {
     if (!ctx || nrec < 0 || !off_host) return pg_fail(ctx, PG_EINVAL, "pg_fasta_last_bytes: bad arguments");
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
-    PG_CUDA(ctx, cudaMemcpy(off_host, ctx->s_off.p, (size_t)(nrec + 1) * 8, cudaMemcpyDeviceToHost));
+    PG_CUDA(ctx, pg_copy_sync(ctx, off_host, ctx->s_off.p, (size_t)(nrec + 1) * 8, cudaMemcpyDeviceToHost));
     const int64_t total = off_host[nrec];
     if (total > cap) return pg_fail(ctx, PG_ERANGE, "pg_fasta_last_bytes: %lld bytes, room for %lld", (long long)total, (long long)cap);
-    if (total && bytes_host) PG_CUDA(ctx, cudaMemcpy(bytes_host, ctx->s_bytes.p, (size_t)total, cudaMemcpyDeviceToHost));
+    if (total && bytes_host) PG_CUDA(ctx, pg_copy_sync(ctx, bytes_host, ctx->s_bytes.p, (size_t)total, cudaMemcpyDeviceToHost));
     return PG_OK;
 }

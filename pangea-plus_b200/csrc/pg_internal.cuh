@@ -74,6 +74,11 @@ struct pg_model {
     unsigned long long *d_blockmask;   // [ntile64] bit i: position blk*64+i holds a genus
     uint16_t *d_bmtable;        // [ngroup][65536][32]   min over the 64 genera of block (group*32 + i)
     uint16_t *d_hmtable;        // [ngroup_h][65536][32]  min over each 32-position half block (2*block + half)
+    // coarse first-level bound of models with more than one group of blocks (k_bound8): per word one byte per block,
+    // min(bm >> PG_C8_SHIFT, PG_C8_MAX), row pitch bm8_pitch bytes (a multiple of 16); columns sib0 .. sib0+3 are left
+    // zero in the table -- k_bound8 fills them per read with the part minima of the read's best block
+    uint8_t  *d_bm8;            // [65536][bm8_pitch]
+    int      bm8_pitch, sib0;
     int      ngroup;            // ceil(ntile64 / 31): slot 31 of a bm row is spare (k_bound, plan 3)
     int      ngroup_h;          // ceil(2*ntile64 / 32)
     double   vmax;              // max |table entry| over real genera (fp32 error bound)
@@ -103,6 +108,16 @@ int  pg_pinned(pg_ctx *ctx, size_t bytes);
 // d_out[0..n) = exclusive scan of d_in, d_out[n] = total; synchronises the stream
 int  pg_device_scan(pg_ctx *ctx, const int64_t *d_in, int64_t n, int64_t *d_out);
 int  pg_pack_launch(pg_ctx *ctx, const char *d_bytes, const int64_t *d_off, int64_t count, uint32_t *d_planes);
+
+// A copy between host and device ORDERED WITH the context's stream: every kernel of the library runs on ctx->stream,
+// which is created non-blocking, so a plain cudaMemcpy (legacy stream) is ordered with nothing.  Enqueued on
+// ctx->stream and waited for, so pageable/local host buffers may be reused or freed on return.
+static inline cudaError_t pg_copy_sync(const pg_ctx *ctx, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind)
+{
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(ctx->stream);
+}
 
 #define PG_CUDA(ctx, call)                                                              \
     do {                                                                                \

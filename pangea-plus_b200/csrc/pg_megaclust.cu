@@ -256,14 +256,14 @@ extern "C" int pg_megaclust(pg_ctx *ctx, const char *text_host, int64_t len, con
     if (st[2] == 0) goto done;
     // order of first appearance (the table's own order depends on the hash)
     recs.resize((size_t)st[2] * 2);
-    MC_CUDA(cudaMemcpy(recs.data(), d_recs, recs.size() * 8, cudaMemcpyDeviceToHost));
+    MC_CUDA(pg_copy_sync(ctx, recs.data(), d_recs, recs.size() * 8, cudaMemcpyDeviceToHost));
     order.resize((size_t)st[2]);
     for (size_t i = 0; i < order.size(); i++) order[i] = i;
     std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return recs[2 * a] < recs[2 * b]; });
     {
         std::vector<unsigned long long> sorted(recs.size());
         for (size_t i = 0; i < order.size(); i++) { sorted[2 * i] = recs[2 * order[i]]; sorted[2 * i + 1] = recs[2 * order[i] + 1]; }
-        MC_CUDA(cudaMemcpy(d_recs, sorted.data(), sorted.size() * 8, cudaMemcpyHostToDevice));
+        MC_CUDA(pg_copy_sync(ctx, d_recs, sorted.data(), sorted.size() * 8, cudaMemcpyHostToDevice));
         MC_CUDA(cudaMalloc(&d_off, (size_t)st[2] * 8));
         MC_CUDA(cudaMalloc(&d_len, (size_t)st[2] * 4));
         k_mc_fields<<<(unsigned)((st[2] + 255) / 256), 256, 0, ctx->stream>>>(d_lines, d_recs, (int64_t)st[2], d_off, d_len);

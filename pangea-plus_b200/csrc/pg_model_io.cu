@@ -35,7 +35,7 @@ extern "C" int pg_model_save(const pg_model *md, const char *path, const void *b
     PG_TRY(pg_model_counts(md, m.data(), nw.data(), M.data(), &N));
     std::vector<int32_t> anc((size_t)G * md->depth);
     if (md->depth)
-        PG_CUDA(ctx, cudaMemcpy(anc.data(), md->d_anc, anc.size() * 4, cudaMemcpyDeviceToHost));
+        PG_CUDA(ctx, pg_copy_sync(ctx, anc.data(), md->d_anc, anc.size() * 4, cudaMemcpyDeviceToHost));
     std::vector<int64_t> idx(PG_NWORDS + 1);
     std::vector<int32_t> pg, pc;
     for (int w = 0; w < PG_NWORDS; w++) {
@@ -112,12 +112,12 @@ extern "C" int pg_model_load(pg_ctx *ctx, const char *path, pg_model **out, void
     if ((e = cudaMalloc(&d_idx, (PG_NWORDS + 1) * 8)) != cudaSuccess ||
         (e = cudaMalloc(&d_pg, (size_t)(npairs + 1) * 4)) != cudaSuccess ||
         (e = cudaMalloc(&d_pc, (size_t)(npairs + 1) * 4)) != cudaSuccess ||
-        (e = cudaMemcpy(d_idx, idx.data(), (PG_NWORDS + 1) * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(d_pg, pgx.data(), (size_t)npairs * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(d_pc, pcx.data(), (size_t)npairs * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(md->d_nw, nw.data(), PG_NWORDS * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(md->d_M, M.data(), (size_t)G * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-        (e = cudaMemcpy(md->d_N, &N64, 8, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        (e = pg_copy_sync(ctx, d_idx, idx.data(), (PG_NWORDS + 1) * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = pg_copy_sync(ctx, d_pg, pgx.data(), (size_t)npairs * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = pg_copy_sync(ctx, d_pc, pcx.data(), (size_t)npairs * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = pg_copy_sync(ctx, md->d_nw, nw.data(), PG_NWORDS * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = pg_copy_sync(ctx, md->d_M, M.data(), (size_t)G * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = pg_copy_sync(ctx, md->d_N, &N64, 8, cudaMemcpyHostToDevice)) != cudaSuccess) {
         cudaFree(d_idx); cudaFree(d_pg); cudaFree(d_pc);
         pg_model_free(md);
         free(b);

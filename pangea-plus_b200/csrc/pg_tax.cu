@@ -419,11 +419,11 @@ extern "C" int pg_tax_load(pg_ctx *ctx, const char *dir, pg_tax **out)
         return pg_fail(ctx, PG_ENOMEM, "pg_tax_load: device allocation failed: %s", cudaGetErrorString(e));
     }
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    PG_CUDA(ctx, cudaMemcpy(t->d_gi2tax, t->h_gi.data(), (size_t)t->ngi * 4, cudaMemcpyHostToDevice));
-    PG_CUDA(ctx, cudaMemcpy(t->d_parent, parent.data(), (size_t)t->nnodes * 4, cudaMemcpyHostToDevice));
-    PG_CUDA(ctx, cudaMemcpy(t->d_rank, rank.data(), (size_t)t->nnodes, cudaMemcpyHostToDevice));
-    PG_CUDA(ctx, cudaMemcpy(t->d_namepool, pool.data(), pool.size(), cudaMemcpyHostToDevice));
-    PG_CUDA(ctx, cudaMemcpy(t->d_nameoff, nameoff.data(), (size_t)(t->nnodes + 1) * 4, cudaMemcpyHostToDevice));
+    PG_CUDA(ctx, pg_copy_sync(ctx, t->d_gi2tax, t->h_gi.data(), (size_t)t->ngi * 4, cudaMemcpyHostToDevice));
+    PG_CUDA(ctx, pg_copy_sync(ctx, t->d_parent, parent.data(), (size_t)t->nnodes * 4, cudaMemcpyHostToDevice));
+    PG_CUDA(ctx, pg_copy_sync(ctx, t->d_rank, rank.data(), (size_t)t->nnodes, cudaMemcpyHostToDevice));
+    PG_CUDA(ctx, pg_copy_sync(ctx, t->d_namepool, pool.data(), pool.size(), cudaMemcpyHostToDevice));
+    PG_CUDA(ctx, pg_copy_sync(ctx, t->d_nameoff, nameoff.data(), (size_t)(t->nnodes + 1) * 4, cudaMemcpyHostToDevice));
 
     // lineage string of every taxid: lengths, scan, strings
     if (t->nnodes > 0) {
@@ -439,8 +439,8 @@ extern "C" int pg_tax_load(pg_ctx *ctx, const char *dir, pg_tax **out)
         PG_TRY(pg_device_scan(ctx, d_len, t->nnodes, t->d_linoff));
         int64_t total = 0;
         int flag = 0;
-        PG_CUDA(ctx, cudaMemcpy(&total, t->d_linoff + t->nnodes, 8, cudaMemcpyDeviceToHost));
-        PG_CUDA(ctx, cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost));
+        PG_CUDA(ctx, pg_copy_sync(ctx, &total, t->d_linoff + t->nnodes, 8, cudaMemcpyDeviceToHost));
+        PG_CUDA(ctx, pg_copy_sync(ctx, &flag, d_flag, 4, cudaMemcpyDeviceToHost));
         cudaFree(d_len);
         cudaFree(d_flag);
         if (flag) {

@@ -173,7 +173,7 @@ extern "C" void pg_model_free(pg_model *md)
     cudaFree(md->d_m); cudaFree(md->d_table); cudaFree(md->d_nw); cudaFree(md->d_M);
     cudaFree(md->d_N); cudaFree(md->d_logPrior); cudaFree(md->d_Pw); cudaFree(md->d_logLeave);
     cudaFree(md->d_anc); cudaFree(md->d_qtable); cudaFree(md->d_rowmax);
-    cudaFree(md->d_perm); cudaFree(md->d_bmtable); cudaFree(md->d_blockmask); cudaFree(md->d_hmtable);
+    cudaFree(md->d_perm); cudaFree(md->d_bmtable); cudaFree(md->d_blockmask); cudaFree(md->d_hmtable); cudaFree(md->d_bm8);
     delete md;
 }
 
@@ -205,11 +205,10 @@ extern "C" int pg_model_commit(pg_model *md)
     return PG_OK;
 }
 
-static int train_on_device(pg_ctx *ctx, const char *d_bytes, const int64_t *d_off, int64_t nseq,
-                           const int32_t *d_genus, int G, pg_model **out)
+// counts of one batch of sequences added to the model's integer arrays (no tables yet)
+static int count_on_device(pg_ctx *ctx, pg_model *md, const char *d_bytes, const int64_t *d_off, int64_t nseq,
+                           const int32_t *d_genus)
 {
-    pg_model *md = NULL;
-    PG_TRY(model_alloc(ctx, G, &md));
     int *d_bad = NULL;
     PG_CUDA(ctx, cudaMalloc(&d_bad, 4));
     PG_CUDA(ctx, cudaMemsetAsync(d_bad, 0, 4, ctx->stream));
@@ -217,7 +216,7 @@ static int train_on_device(pg_ctx *ctx, const char *d_bytes, const int64_t *d_of
     const int64_t step = 1 << 30;
     for (int64_t s0 = 0; s0 < nseq; s0 += step) {
         int64_t cnt = nseq - s0 < step ? nseq - s0 : step;
-        k_train_count<<<(unsigned)cnt, 256, 0, ctx->stream>>>(d_bytes, d_off + s0, d_genus + s0, cnt, G,
+        k_train_count<<<(unsigned)cnt, 256, 0, ctx->stream>>>(d_bytes, d_off + s0, d_genus + s0, cnt, md->G,
                                                              md->d_m, md->d_nw, md->d_M, md->d_N, d_bad);
         PG_LAUNCHED(ctx);
     }
@@ -225,14 +224,33 @@ static int train_on_device(pg_ctx *ctx, const char *d_bytes, const int64_t *d_of
     PG_CUDA(ctx, cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaFree(d_bad);
-    if (bad) {
-        pg_model_free(md);
-        return pg_fail(ctx, PG_EINVAL, "pg_train: genus_of_seq holds an index outside [0,%d)", G);
-    }
-    int r = pg_model_commit(md);
+    if (bad) return pg_fail(ctx, PG_EINVAL, "pg_train: genus_of_seq holds an index outside [0,%d)", md->G);
+    md->committed = false;
+    return PG_OK;
+}
+
+static int train_on_device(pg_ctx *ctx, const char *d_bytes, const int64_t *d_off, int64_t nseq,
+                           const int32_t *d_genus, int G, pg_model **out)
+{
+    pg_model *md = NULL;
+    PG_TRY(model_alloc(ctx, G, &md));
+    int r = count_on_device(ctx, md, d_bytes, d_off, nseq, d_genus);
+    if (r == PG_OK) r = pg_model_commit(md);
     if (r != PG_OK) { pg_model_free(md); return r; }
     *out = md;
     return PG_OK;
+}
+
+// Sharded / streamed training: the counts of one more batch of sequences, added to a model made by
+// pg_model_create() (or trained before).  Integer atomics, so the order of batches and the way the training set is
+// cut across GPUs do not matter: after an integer all-reduce of pg_model_buffers() every rank holds the counts of
+// the whole set, bit for bit those of a single pg_train() call.  Tables are derived by pg_model_commit().
+extern "C" int pg_train_accumulate_dev(pg_ctx *ctx, pg_model *md, const pg_seqbatch *seqs, const int32_t *genus_dev)
+{
+    if (!ctx || !md || !seqs || !genus_dev || seqs->count < 0 || md->ctx != ctx)
+        return pg_fail(ctx, PG_EINVAL, "pg_train_accumulate_dev: bad arguments");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    return count_on_device(ctx, md, seqs->bytes, seqs->off, seqs->count, genus_dev);
 }
 
 extern "C" int pg_train_dev(pg_ctx *ctx, const pg_seqbatch *seqs, const int32_t *genus_dev, int G,
@@ -272,6 +290,36 @@ extern "C" int pg_train(pg_ctx *ctx, const pg_seqbatch *seqs, const int32_t *gen
     return r;
 }
 
+extern "C" int pg_train_accumulate(pg_ctx *ctx, pg_model *md, const pg_seqbatch *seqs, const int32_t *genus_host)
+{
+    if (!ctx || !md || !seqs || !genus_host || seqs->count < 0 || md->ctx != ctx)
+        return pg_fail(ctx, PG_EINVAL, "pg_train_accumulate: bad arguments");
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = seqs->count;
+    if (n == 0) return PG_OK;
+    const int64_t base = seqs->off[0], total = seqs->off[n] - base;
+    char *d_bytes = NULL; int64_t *d_off = NULL; int32_t *d_genus = NULL;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_bytes, (size_t)total + 16)) != cudaSuccess ||
+        (e = cudaMalloc(&d_off, (size_t)(n + 1) * 8)) != cudaSuccess ||
+        (e = cudaMalloc(&d_genus, (size_t)(n + 1) * 4)) != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaFree(d_bytes); cudaFree(d_off); cudaFree(d_genus);
+        return pg_fail(ctx, PG_ENOMEM, "pg_train_accumulate: device allocation failed: %s", cudaGetErrorString(e));
+    }
+    std::vector<int64_t> off((size_t)n + 1);
+    for (int64_t i = 0; i <= n; i++) off[(size_t)i] = seqs->off[i] - base;     // a slice of a larger batch: rebase
+    int r = PG_OK;
+    if ((e = cudaMemcpyAsync(d_bytes, seqs->bytes + base, (size_t)total, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_off, off.data(), (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_genus, genus_host, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess)
+        r = pg_fail(ctx, PG_ECUDA, "pg_train_accumulate: upload failed: %s", cudaGetErrorString(e));
+    if (r == PG_OK) r = count_on_device(ctx, md, d_bytes, d_off, n, d_genus);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_bytes); cudaFree(d_off); cudaFree(d_genus);
+    return r;
+}
+
 extern "C" int pg_model_set_lineage(pg_model *md, const int32_t *anc_host, int depth)
 {
     if (!md || !anc_host || depth <= 0 || depth > PG_MAX_DEPTH)
@@ -282,7 +330,7 @@ extern "C" int pg_model_set_lineage(pg_model *md, const int32_t *anc_host, int d
     if (md->d_anc) { cudaFree(md->d_anc); md->d_anc = NULL; }
     size_t bytes = (size_t)md->G * depth * 4;
     PG_CUDA(ctx, cudaMalloc(&md->d_anc, bytes));
-    PG_CUDA(ctx, cudaMemcpy(md->d_anc, anc_host, bytes, cudaMemcpyHostToDevice));
+    PG_CUDA(ctx, pg_copy_sync(ctx, md->d_anc, anc_host, bytes, cudaMemcpyHostToDevice));
     md->depth = depth;
     // Certified mode lays the genera out in lineage order, so that the relatives of a read's genus
     // share its 64-genus block and every other block is dismissed by its lower bound

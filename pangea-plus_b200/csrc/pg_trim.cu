@@ -231,19 +231,19 @@ int pg_index_lines(pg_ctx *ctx, const char *d_text, int64_t n, int64_t **d_start
     }
     PG_TRY(pg_device_scan(ctx, d_cnt, nseg, d_off));
     int64_t nnl = 0;
-    PG_CUDA(ctx, cudaMemcpy(&nnl, d_off + nseg, 8, cudaMemcpyDeviceToHost));
+    PG_CUDA(ctx, pg_copy_sync(ctx, &nnl, d_off + nseg, 8, cudaMemcpyDeviceToHost));
     char last = '\n';
-    if (n) PG_CUDA(ctx, cudaMemcpy(&last, d_text + n - 1, 1, cudaMemcpyDeviceToHost));
+    if (n) PG_CUDA(ctx, pg_copy_sync(ctx, &last, d_text + n - 1, 1, cudaMemcpyDeviceToHost));
     const int64_t nlines = nnl + (n > 0 && last != '\n' ? 1 : 0);
     PG_CUDA(ctx, cudaMalloc(&d_start, (size_t)(nlines + 2) * 8));
     const int64_t zero = 0;
-    PG_CUDA(ctx, cudaMemcpy(d_start, &zero, 8, cudaMemcpyHostToDevice));
+    PG_CUDA(ctx, pg_copy_sync(ctx, d_start, &zero, 8, cudaMemcpyHostToDevice));
     if (nseg) {
         k_fill_line_starts<<<(unsigned)((nseg + 255) / 256), 256, 0, ctx->stream>>>(d_text, n, d_off, d_start);
         PG_LAUNCHED(ctx);
     }
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    PG_CUDA(ctx, cudaMemcpy(d_start + nlines, &n, 8, cudaMemcpyHostToDevice));     // end of the last line
+    PG_CUDA(ctx, pg_copy_sync(ctx, d_start + nlines, &n, 8, cudaMemcpyHostToDevice));     // end of the last line
     cudaFree(d_cnt);
     cudaFree(d_off);
     *d_start_out = d_start;
@@ -292,8 +292,8 @@ extern "C" int pg_trim_join(pg_ctx *ctx, const char *a_host, int64_t a_len, cons
     PG_TRY(pg_device_scan(ctx, d_tlen, nrec, d_toff));
     PG_TRY(pg_device_scan(ctx, d_slen, nrec, d_soff));
     int64_t ttot = 0, stot = 0;
-    PG_CUDA(ctx, cudaMemcpy(&ttot, d_toff + nrec, 8, cudaMemcpyDeviceToHost));
-    PG_CUDA(ctx, cudaMemcpy(&stot, d_soff + nrec, 8, cudaMemcpyDeviceToHost));
+    PG_CUDA(ctx, pg_copy_sync(ctx, &ttot, d_toff + nrec, 8, cudaMemcpyDeviceToHost));
+    PG_CUDA(ctx, pg_copy_sync(ctx, &stot, d_soff + nrec, 8, cudaMemcpyDeviceToHost));
     *out_len = ttot;
     int rc = PG_OK;
     if (ttot > out_cap) rc = pg_fail(ctx, PG_ERANGE, "pg_trim_join: output needs %lld bytes", (long long)ttot);

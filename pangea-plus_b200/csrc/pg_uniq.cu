@@ -116,8 +116,8 @@ extern "C" int pg_first_hits(pg_ctx *ctx, const char *text_host, int64_t len, ch
         UQ_CUDA(cudaGetLastError());
         UQ_TRY(pg_device_scan(ctx, d_klen64, nlines, d_off));
         UQ_TRY(pg_device_scan(ctx, d_flag, nlines, d_rank));
-        UQ_CUDA(cudaMemcpy(&total, d_off + nlines, 8, cudaMemcpyDeviceToHost));
-        UQ_CUDA(cudaMemcpy(&kept, d_rank + nlines, 8, cudaMemcpyDeviceToHost));
+        UQ_CUDA(pg_copy_sync(ctx, &total, d_off + nlines, 8, cudaMemcpyDeviceToHost));
+        UQ_CUDA(pg_copy_sync(ctx, &kept, d_rank + nlines, 8, cudaMemcpyDeviceToHost));
         *out_len = total;
         if (n_kept) *n_kept = kept;
         if (total > out_cap || (kept_lines_host && kept > lines_cap)) {

@@ -34,20 +34,45 @@ int main(int argc, char **argv)
 {
     const char *a = NULL, *b = NULL;
     int gap = 189, truncate = 11, device = 0;
-    /* Getopt::Std with 'a:b:g:t:q:qc:lc:j': -a -b -g -t -q -c take a value, -l and -j do not; the
-     * first non-option word ends the parse.  "-qc 25" is therefore -q with the value "c". */
-    for (int i = 1; i < argc; i++) {
-        const char *s = argv[i];
-        if (s[0] != '-' || !s[1]) break;
-        if (strcmp(s, "--device") == 0 && i + 1 < argc) { device = atoi(argv[++i]); continue; }
-        char o = s[1];
-        if (strchr("abgtqc", o)) {
-            const char *v = s[2] ? s + 2 : (i + 1 < argc ? argv[++i] : "");
-            if (o == 'a') a = v;
-            else if (o == 'b') b = v;
-            else if (o == 'g') gap = atoi(v);
-            else if (o == 't') truncate = atoi(v);
-        } else if (o != 'j' && o != 'l') break;
+    /* Getopt::Std::getopts('a:b:g:t:q:qc:lc:j'), restated: a word "-Xrest" is taken apart letter by letter.  A letter
+     * followed by ':' in the spec (a b g t q c) takes the rest of the word, or else the next word, as its value; l and j
+     * are switches and the rest of the word is parsed on ("-lc 80" = -l, then -c 80); an unknown letter is reported
+     * on stderr and skipped; "--" or the first word that is not an option ends the parse.  "-qc 25" is therefore -q
+     * with the value "c".  (--device N is this tool's own extension.) */
+    static const char spec[] = "a:b:g:t:q:qc:lc:j";
+    {
+        int i = 1;
+        char *word = NULL;                                /* the remainder of a bundled word, re-queued as "-rest" */
+        while (word || i < argc) {
+            const char *s = word ? word : argv[i];
+            if (!word && strcmp(s, "--device") == 0 && i + 1 < argc) { device = atoi(argv[i + 1]); i += 2; continue; }
+            if (s[0] != '-' || !s[1]) break;
+            if (strcmp(s, "--") == 0) break;
+            const char first = s[1];
+            const char *rest = s + 2;
+            const char *pos = strchr(spec, first);
+            char *next_word = NULL;
+            if (pos && pos[1] == ':') {
+                const char *v = rest;
+                if (!word) i++;
+                if (!*v) v = i < argc ? argv[i++] : "";
+                if (first == 'a') a = v;
+                else if (first == 'b') b = v;
+                else if (first == 'g') gap = atoi(v);
+                else if (first == 't') truncate = atoi(v);
+            } else {
+                if (!pos) fprintf(stderr, "Unknown option: %c\n", first);
+                if (*rest) {
+                    next_word = (char *)malloc(strlen(rest) + 2);
+                    next_word[0] = '-';
+                    strcpy(next_word + 1, rest);
+                }
+                if (!word) i++;
+            }
+            free(word);
+            word = next_word;
+        }
+        free(word);
     }
     if (!a) {
         printf("Usage: perl trim2.pl \n\t-a raw illumina input file read 1\n\t-b raw illumina input file read 2 (if any) \n"

@@ -52,7 +52,7 @@ class _SeqBatch(C.Structure):
 
 class _Opts(C.Structure):
     _fields_ = [("min_boot_words", C.c_int32), ("mode", C.c_int32), ("cert_plan", C.c_int32),
-                ("light_max", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("light_max", C.c_int32), ("bound_level", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class _TrimOpts(C.Structure):
@@ -121,6 +121,11 @@ def load_library() -> C.CDLL:
     lib.pg_train_dev.argtypes = [vp, C.POINTER(_SeqBatch), vp, C.c_int, C.POINTER(vp)]
     lib.pg_model_free.argtypes = [vp]
     lib.pg_model_free.restype = None
+    lib.pg_train_accumulate.argtypes = [vp, vp, C.POINTER(_SeqBatch), vp]
+    lib.pg_train_accumulate_dev.argtypes = [vp, vp, C.POINTER(_SeqBatch), vp]
+    u64 = C.c_uint64
+    lib.pg_synth_members.argtypes = [vp, u64, vp, C.c_int, vp, vp, i64, i64, vp]
+    lib.pg_synth_reads.argtypes = [vp, u64, vp, vp, vp, i64, i64, i64, C.c_int, C.c_int, C.c_int, vp, vp]
     lib.pg_model_set_lineage.argtypes = [vp, vp, C.c_int]
     lib.pg_model_genera.argtypes = [vp]
     lib.pg_model_certifiable.argtypes = [vp]
@@ -328,6 +333,24 @@ class Context:
         self._chk(fn(self.h, C.byref(sb), _ptr(genus), G, C.byref(h)))
         return Model(self, h.value)
 
+    def train_accumulate(self, model: Model, data, off, genus, device: bool = False) -> None:
+        """add the counts of one more batch to `model` (sharded / streamed training); commit() derives the tables"""
+        sb = _SeqBatch(_ptr(data), _ptr(off), len(off) - 1)
+        if not device:
+            genus = np.ascontiguousarray(genus, dtype=np.int32)
+        fn = self.lib.pg_train_accumulate_dev if device else self.lib.pg_train_accumulate
+        self._chk(fn(self.h, model.h, C.byref(sb), _ptr(genus)))
+
+    # ---- synthetic workloads generated on the device (include/pangea_b200_synth.h; numpy twins in synth.py)
+    def synth_members(self, seed: int, centroids_dev, length: int, genus_dev, off_dev, first: int, count: int, bytes_dev) -> None:
+        self._chk(self.lib.pg_synth_members(self.h, seed, _ptr(centroids_dev), length, _ptr(genus_dev), _ptr(off_dev), first, count,
+                                            _ptr(bytes_dev)))
+
+    def synth_reads(self, seed: int, members_dev, member_off_dev, member_genus_dev, nmembers: int, first: int, count: int,
+                    out_dev, src_dev=None, read_len: int = 250, gap: int = 189, paired: bool = True) -> None:
+        self._chk(self.lib.pg_synth_reads(self.h, seed, _ptr(members_dev), _ptr(member_off_dev), _ptr(member_genus_dev), nmembers,
+                                          first, count, read_len, gap, int(paired), _ptr(out_dev), _ptr(src_dev)))
+
     def model_create(self, G: int) -> Model:
         h = C.c_void_p()
         self._chk(self.lib.pg_model_create(self.h, G, C.byref(h)))
@@ -351,18 +374,19 @@ class Context:
         return Reads(self, h.value)
 
     def classify(self, model: Model, data: np.ndarray, off: np.ndarray, mode: int = 0, min_boot_words: int = 0,
-                 want_boot: bool = False, out: np.ndarray | None = None, cert_plan: int = 0, light_max: int = 0):
+                 want_boot: bool = False, out: np.ndarray | None = None, cert_plan: int = 0, light_max: int = 0,
+                 bound_level: int = 0):
         n = len(off) - 1
         sb = _SeqBatch(_ptr(data), _ptr(off), n)
-        opts = _Opts(min_boot_words, mode, cert_plan, light_max)
+        opts = _Opts(min_boot_words, mode, cert_plan, light_max, bound_level)
         res = out if out is not None else np.zeros(n, RESULT_DTYPE)
         boot = np.zeros((n, PG_NUM_BOOT), np.int32) if want_boot else None
         self._chk(self.lib.pg_classify(self.h, model.h, C.byref(sb), C.byref(opts), _ptr(res), _ptr(boot)))
         return (res, boot) if want_boot else res
 
     def classify_packed(self, model: Model, reads: Reads, results_dev, boot_dev=None, mode: int = 0,
-                        min_boot_words: int = 0, cert_plan: int = 0, light_max: int = 0) -> None:
-        opts = _Opts(min_boot_words, mode, cert_plan, light_max)
+                        min_boot_words: int = 0, cert_plan: int = 0, light_max: int = 0, bound_level: int = 0) -> None:
+        opts = _Opts(min_boot_words, mode, cert_plan, light_max, bound_level)
         self._chk(self.lib.pg_classify_packed(self.h, model.h, reads.h, C.byref(opts), _ptr(results_dev), _ptr(boot_dev)))
 
     def extract_words(self, model: Model, data: np.ndarray, off: np.ndarray):

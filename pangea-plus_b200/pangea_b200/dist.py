@@ -22,6 +22,19 @@ def broadcast_buffers(tensors, src: int = 0) -> None:
         dist.broadcast(t, src=src)
 
 
+def allreduce_counts(tensors) -> None:
+    """sharded training (BASELINE configs[3]): every rank counted its own slice of the training set
+    into a model of its own; an integer SUM all-reduce of the count buffers (pg_model_buffers: m, n, M as int32, N as
+    int64) leaves every rank with the counts of the whole set -- integer adds commute, so the result is bit for bit
+    the one-rank result whatever the sharding.  `tensors`: uint8 views of the buffers, in pg_model_buffers() order."""
+    import torch
+    import torch.distributed as dist
+
+    for i, t in enumerate(tensors):
+        v = t.view(torch.int64 if i == 3 else torch.int32)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+
+
 def gather_records(local, n_total: int, rank: int, world: int, dst: int = 0):
     """gather per-rank result records (uint8 tensors of 64*count bytes) on `dst` in rank order.
     Shards may differ by one read, so every rank pads to the largest shard."""

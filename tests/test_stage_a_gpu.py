@@ -441,6 +441,18 @@ def test_config3_rdp_scale_genera(ctx):
     a, ba = ctx.classify(gm, data, off, mode=0, want_boot=True)
     b, bb = ctx.classify(gm, data, off, mode=1, want_boot=True)
     assert a.tobytes() == b.tobytes() and np.array_equal(ba, bb)
+    # joined pairs (two block groups of bounds per read and ~490 words): the coarse first level (default here) and
+    # the 16-bit bounds must both return the strict kernels' records, and a sample must match the oracle
+    data, off, src = synth.synth_reads(0x3000002, tr, 3000, paired=True, gap=40)
+    a, ba = ctx.classify(gm, data, off, mode=0, want_boot=True)
+    for kw in (dict(), dict(bound_level=1), dict(bound_level=2, light_max=40)):
+        b, bb = ctx.classify(gm, data, off, mode=1, want_boot=True, **kw)
+        st = ctx.classify_stats()
+        assert a.tobytes() == b.tobytes() and np.array_equal(ba, bb), kw
+        assert st["certified"] == 3000, st
+    ref = om.classify(data[: off[100]], off[:101])
+    assert np.array_equal(a["genus"][:100], ref["genus"]) and np.array_equal(ba[:100], ref["boot"])
+    assert np.array_equal(bits(a["score"][:100]), bits(ref["score"]))
     om.free()
     gm.free()
 
@@ -476,6 +488,11 @@ def test_certified_plans_agree(ctx, baseline_model):
     st = ctx.classify_stats()
     assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb)
     assert st["items"] > 0, st
+    # the coarse 8-bit first level + exact second level (the default of models with more than one block group)
+    got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True, bound_level=2)
+    st = ctx.classify_stats()
+    assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb)
+    assert st["certified"] == 6000 and st["items"] > 0 and st["heavy"] < 600, st
 
 
 def test_certified_without_lineage(ctx):
@@ -524,7 +541,8 @@ def test_certified_equals_strict_on_random_models(ctx, seed, genera, seqs, lengt
         reads.append(r.tobytes())
     data, off = pack_sequences(reads)
     want, wb = ctx.classify(gm, data, off, mode=0, want_boot=True)
-    for kw in (dict(), dict(cert_plan=1), dict(cert_plan=2), dict(light_max=5)):
+    for kw in (dict(), dict(cert_plan=1), dict(cert_plan=2), dict(light_max=5), dict(bound_level=1), dict(bound_level=2),
+               dict(bound_level=2, light_max=5)):
         got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True, **kw)
         assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb), kw
     om = ora.Model(tr["data"], tr["off"], tr["genus"], tr["G"])

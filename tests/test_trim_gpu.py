@@ -38,6 +38,15 @@ def test_trim_cli_like_the_readme(tmp_path):
     r = subprocess.run([str(BIN / "trim2"), "-a", "../input_A.txt", "-b", "../input_B.txt", "-g", "100", "-lc", "10"],
                        cwd=tmp_path / "Trim", capture_output=True, text=True, timeout=120)
     assert out.read_bytes() == (GOLD / "qseq_g100.expected.fasta").read_bytes()
+    # Getopt::Std bundling: "-lc 80" is -l then -c 80 and the parse goes on, so a -g AFTER it still counts; "-qc 25"
+    # is -q with the value "c" and leaves "25", a non-option word, which ends the parse (the -g after it is lost)
+    out.unlink()
+    r = subprocess.run([str(BIN / "trim2"), "-lc", "80", "-a", "../input_A.txt", "-b", "../input_B.txt", "-g", "100"],
+                       cwd=tmp_path / "Trim", capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and out.read_bytes() == (GOLD / "qseq_g100.expected.fasta").read_bytes()
+    r = subprocess.run([str(BIN / "trim2"), "-a", "../input_A.txt", "-b", "../input_B.txt", "-qc", "25", "-g", "100"],
+                       cwd=tmp_path / "Trim", capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and out.read_bytes() == (GOLD / "qseq_g189.expected.fasta").read_bytes()
     # FASTQ: records are echoed on stdout as well
     (tmp_path / "x.fastq").write_bytes((GOLD / "reads.fastq").read_bytes())
     r = subprocess.run([str(BIN / "trim2"), "-a", "x.fastq"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
