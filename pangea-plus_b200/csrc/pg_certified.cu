@@ -1795,7 +1795,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     if (env_b8 == -2) { const char *e = getenv("PG_BOUND8"); env_b8 = e ? atoi(e) : -1; }
     const int blevel = env_b8 >= 0 ? (env_b8 ? 2 : 1) : cb.bound_level;
     int nsegc = 0, pitch_s = 0, nchunk8 = 0, block8 = PG_B8_MAXBLOCK;
-    bool use8 = d_guess && version == 3 && md->d_bm8 && (blevel == 2 || (blevel == 0 && md->ngroup > 1));
+    bool use8 = d_guess && version == 3 && md->d_bm8 && blevel == 2;   // measured on 10 000 genera: k_bound 4.66 M reads/s, k_bound8 4.49 M
     if (use8) {
         // column chunks sized for two CTAs of up to 448 threads per SM (a 10 000-genus model with 486-word reads: one
         // chunk of 12 segments, 102 KB); four smaller CTAs per SM were measured: the 96-byte row pitch that fits costs
@@ -1820,7 +1820,11 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
             }
         }
     }
-    if (use8) {
+    // the coarse table also picks the block to evaluate first (k_guess8), whichever kernel bounds the rest
+    static int env_g8 = -2;                             // PG_GUESS8=0: k_guess_bm even for large models (A/B switch)
+    if (env_g8 == -2) { const char *e = getenv("PG_GUESS8"); env_g8 = e ? atoi(e) : -1; }
+    const bool guess8 = d_guess && version == 3 && md->d_bm8 && (use8 || (env_g8 != 0 && md->ngroup > 1));
+    if (guess8) {
         k_guess8<<<(nreads_b + 7) / 8, 256, (size_t)8 * md->bm8_pitch * 2, ctx->stream>>>(
             md->d_bm8, md->bm8_pitch, md->d_hmtable, d_words, d_off, d_nwords, d_order, (int)nreads_b, slot0, md->ntile64, d_guess);
         PG_LAUNCHED(ctx);

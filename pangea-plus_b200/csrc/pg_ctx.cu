@@ -64,6 +64,16 @@ extern "C" pg_ctx *pg_init(int device)
     }
     ctx->stream = ctx->own_stream;
     ctx->copy_stream = ctx->down_stream = NULL;
+    {
+        // keep the stream-ordered allocator's pool warm: transient buffers (pg_dev_alloc) come back without a trip
+        // to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+    }
     return ctx;
 }
 

@@ -149,7 +149,7 @@ extern "C" int pg_fasta_ingest(pg_ctx *ctx, const char *text_host, int64_t len, 
 done:
 #undef FA_CUDA
 #undef FA_TRY
-    cudaFree(d_start);
+    pg_dev_free(ctx, d_start);
     if (rc != PG_OK && rd) { pg_reads_free(rd); if (reads_out) *reads_out = NULL; }
     return rc;
 }

@@ -119,6 +119,18 @@ static inline cudaError_t pg_copy_sync(const pg_ctx *ctx, void *dst, const void 
     return cudaStreamSynchronize(ctx->stream);
 }
 
+// Transient device buffers: the stream-ordered allocator (cudaMallocAsync on the context's stream, pool kept warm by
+// pg_init) instead of cudaMalloc / cudaFree -- cudaFree synchronises the WHOLE device, which serialises the contexts
+// that share a GPU in a host pipeline (rdp_classifier runs two per device).
+static inline cudaError_t pg_dev_alloc(const pg_ctx *ctx, void **p, size_t bytes)
+{
+    return cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
+}
+static inline void pg_dev_free(const pg_ctx *ctx, void *p)
+{
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
 #define PG_CUDA(ctx, call)                                                              \
     do {                                                                                \
         cudaError_t e__ = (call);                                                       \

@@ -277,6 +277,6 @@ extern "C" int pg_megaclust(pg_ctx *ctx, const char *text_host, int64_t len, con
     }
 done:
 #undef MC_CUDA
-    cudaFree(d_start); cudaFree(d_off); cudaFree(d_len);
+    pg_dev_free(ctx, d_start); cudaFree(d_off); cudaFree(d_len);
     return rc;
 }

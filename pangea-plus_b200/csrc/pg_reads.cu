@@ -186,8 +186,8 @@ static int reads_alloc(pg_ctx *ctx, int64_t count, int64_t total_bytes, pg_reads
     r->total_bytes = total_bytes;
     r->nchunks_cap = (total_bytes >> 5) + count + 2;
     cudaError_t e;
-    if ((e = cudaMalloc(&r->d_off, (size_t)(count + 1) * 8)) != cudaSuccess ||
-        (e = cudaMalloc(&r->d_planes, (size_t)r->nchunks_cap * 12)) != cudaSuccess) {
+    if ((e = pg_dev_alloc(ctx, (void **)&r->d_off, (size_t)(count + 1) * 8)) != cudaSuccess ||
+        (e = pg_dev_alloc(ctx, (void **)&r->d_planes, (size_t)r->nchunks_cap * 12)) != cudaSuccess) {
         (void)cudaGetLastError();
         pg_reads_free(r);
         return pg_fail(ctx, PG_ENOMEM, "pg_reads: device allocation failed: %s", cudaGetErrorString(e));
@@ -200,9 +200,8 @@ extern "C" void pg_reads_free(pg_reads *r)
 {
     if (!r) return;
     cudaSetDevice(r->ctx->device);
-    cudaStreamSynchronize(r->ctx->stream);
-    cudaFree(r->d_off);
-    cudaFree(r->d_planes);
+    pg_dev_free(r->ctx, r->d_off);                       // stream-ordered: after everything queued on the context's stream
+    pg_dev_free(r->ctx, r->d_planes);
     delete r;
 }
 

@@ -39,7 +39,7 @@ int pg_device_scan(pg_ctx *ctx, const int64_t *d_in, int64_t n, int64_t *d_out)
 {
     const int64_t nb = (n + 1023) / 1024;
     int64_t *d_bs = NULL;
-    PG_CUDA(ctx, cudaMalloc(&d_bs, (size_t)(nb + 1) * 8));
+    PG_CUDA(ctx, pg_dev_alloc(ctx, (void **)&d_bs, (size_t)(nb + 1) * 8));
     if (nb > 0) {
         k_scan_block<<<(unsigned)nb, 1024, 0, ctx->stream>>>(d_in, n, d_out, d_bs);
         PG_LAUNCHED(ctx);
@@ -51,7 +51,7 @@ int pg_device_scan(pg_ctx *ctx, const int64_t *d_in, int64_t n, int64_t *d_out)
         PG_LAUNCHED(ctx);
     }
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_bs);
+    pg_dev_free(ctx, d_bs);
     return PG_OK;
 }
 

@@ -223,8 +223,8 @@ int pg_index_lines(pg_ctx *ctx, const char *d_text, int64_t n, int64_t **d_start
 {
     const int64_t nseg = (n + PG_SEG - 1) / PG_SEG;
     int64_t *d_cnt = NULL, *d_off = NULL, *d_start = NULL;
-    PG_CUDA(ctx, cudaMalloc(&d_cnt, (size_t)(nseg + 1) * 8));
-    PG_CUDA(ctx, cudaMalloc(&d_off, (size_t)(nseg + 2) * 8));
+    PG_CUDA(ctx, pg_dev_alloc(ctx, (void **)&d_cnt, (size_t)(nseg + 1) * 8));
+    PG_CUDA(ctx, pg_dev_alloc(ctx, (void **)&d_off, (size_t)(nseg + 2) * 8));
     if (nseg) {
         k_count_newlines<<<(unsigned)((nseg + 255) / 256), 256, 0, ctx->stream>>>(d_text, n, d_cnt);
         PG_LAUNCHED(ctx);
@@ -235,7 +235,7 @@ int pg_index_lines(pg_ctx *ctx, const char *d_text, int64_t n, int64_t **d_start
     char last = '\n';
     if (n) PG_CUDA(ctx, pg_copy_sync(ctx, &last, d_text + n - 1, 1, cudaMemcpyDeviceToHost));
     const int64_t nlines = nnl + (n > 0 && last != '\n' ? 1 : 0);
-    PG_CUDA(ctx, cudaMalloc(&d_start, (size_t)(nlines + 2) * 8));
+    PG_CUDA(ctx, pg_dev_alloc(ctx, (void **)&d_start, (size_t)(nlines + 2) * 8));
     const int64_t zero = 0;
     PG_CUDA(ctx, pg_copy_sync(ctx, d_start, &zero, 8, cudaMemcpyHostToDevice));
     if (nseg) {
@@ -244,9 +244,9 @@ int pg_index_lines(pg_ctx *ctx, const char *d_text, int64_t n, int64_t **d_start
     }
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     PG_CUDA(ctx, pg_copy_sync(ctx, d_start + nlines, &n, 8, cudaMemcpyHostToDevice));     // end of the last line
-    cudaFree(d_cnt);
-    cudaFree(d_off);
-    *d_start_out = d_start;
+    pg_dev_free(ctx, d_cnt);
+    pg_dev_free(ctx, d_off);
+    *d_start_out = d_start;                                // the caller releases it with pg_dev_free()
     *nlines_out = nlines;
     return PG_OK;
 }
@@ -313,7 +313,7 @@ extern "C" int pg_trim_join(pg_ctx *ctx, const char *a_host, int64_t a_len, cons
         }
     }
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_a); cudaFree(d_b); cudaFree(d_sa); cudaFree(d_sb); cudaFree(d_len); cudaFree(d_off);
+    cudaFree(d_a); cudaFree(d_b); pg_dev_free(ctx, d_sa); pg_dev_free(ctx, d_sb); cudaFree(d_len); cudaFree(d_off);
     cudaFree(d_text); cudaFree(d_seq);
     return rc;
 }

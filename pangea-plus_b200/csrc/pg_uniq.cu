@@ -136,6 +136,6 @@ extern "C" int pg_first_hits(pg_ctx *ctx, const char *text_host, int64_t len, ch
 done:
 #undef UQ_TRY
 #undef UQ_CUDA
-    cudaFree(d_start);
+    pg_dev_free(ctx, d_start);
     return rc;
 }

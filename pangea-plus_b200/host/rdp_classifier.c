@@ -5,6 +5,13 @@
  * classifiable read in input order, short reads reported on stdout and left out of the file
  * (SURVEY.md rows A0, A2, A9).  All arithmetic runs on the GPU through libpangea_b200.
  *
+ * --gpus N [--devices a,b,..]: the reads shard across N GPUs.  Device 0 loads the model file, its
+ * integer training counts are replicated once with ncclBroadcast (peer copies when a device is listed twice), every
+ * device derives its tables locally, and the query file is cut into record-aligned pieces that the devices take in
+ * turn; lines are written in input order.  The run is a pipeline: one thread reads pieces into pinned buffers, two
+ * contexts per device ingest + classify them (the copies of one overlap the kernels of the other), formatter threads
+ * turn records into text, and one thread writes the pieces in order.
+ *
  * The jar carries its training data inside; this tool cannot ship RDP's trainset, so the
  * model is a file: `-t model.pgm` (default: $PANGEA_RDP_MODEL, else ./rdp_model.pgm), made by
  *     rdp_classifier --train <training.fa> -t <model.pgm> [--ranks r0,r1,...]
@@ -23,9 +30,13 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
+#include <time.h>
+#include <unistd.h>
+#include <cuda_runtime_api.h>
+#include <nccl.h>
 #include "pangea_b200.h"
 #include "pg_host_common.h"
-#include <time.h>
 
 static double now_s(void)
 {
@@ -208,13 +219,390 @@ static int do_train(pg_ctx *ctx, const char *fasta_path, const char *model_path,
     return 0;
 }
 
+/* ------------------------------------------------------------------ pipeline plumbing */
+
+typedef struct {
+    int64_t    seq;                 /* position of the piece in the file */
+    char      *text;                /* pinned host buffer */
+    int64_t    len, textcap;
+    int64_t    nrec, cap;
+    int64_t   *hdr_off;
+    int32_t   *id_len;
+    pg_result *res;                 /* pinned */
+    int64_t    rescap;
+    char      *out, *msg;           /* formatted lines / stdout messages */
+    size_t     out_len, out_cap, msg_len, msg_cap;
+} piece_t;
+
+typedef struct {
+    piece_t       **item;
+    int             cap, head, count, closed;
+    pthread_mutex_t mu;
+    pthread_cond_t  cv;
+} queue_t;
+
+static void q_init(queue_t *q, int cap)
+{
+    memset(q, 0, sizeof *q);
+    q->item = (piece_t **)calloc((size_t)cap, sizeof(piece_t *));
+    q->cap = cap;
+    pthread_mutex_init(&q->mu, NULL);
+    pthread_cond_init(&q->cv, NULL);
+}
+static void q_push(queue_t *q, piece_t *p)
+{
+    pthread_mutex_lock(&q->mu);
+    q->item[(q->head + q->count) % q->cap] = p;          /* never more pieces in flight than cap */
+    q->count++;
+    pthread_cond_broadcast(&q->cv);
+    pthread_mutex_unlock(&q->mu);
+}
+static piece_t *q_pop(queue_t *q)                        /* NULL once the queue is closed and drained */
+{
+    pthread_mutex_lock(&q->mu);
+    while (q->count == 0 && !q->closed) pthread_cond_wait(&q->cv, &q->mu);
+    piece_t *p = NULL;
+    if (q->count) {
+        p = q->item[q->head];
+        q->head = (q->head + 1) % q->cap;
+        q->count--;
+    }
+    pthread_mutex_unlock(&q->mu);
+    return p;
+}
+static void q_close(queue_t *q)
+{
+    pthread_mutex_lock(&q->mu);
+    q->closed = 1;
+    pthread_cond_broadcast(&q->cv);
+    pthread_mutex_unlock(&q->mu);
+}
+
+typedef struct {
+    /* configuration */
+    const taxonomy *t;
+    int             ifmt;
+    pg_classify_opts opts;
+    int64_t         piece_bytes;
+    FILE           *fq, *fo;
+    /* queues */
+    queue_t         q_free, q_gpu, q_fmt, q_out;
+    int             npieces;
+    /* workers */
+    int             nworkers, nformat;
+    pg_ctx        **wctx;           /* one context per GPU worker */
+    pg_model      **wmodel;         /* the model of the worker's device (shared by the contexts of one device) */
+    pthread_mutex_t mu;
+    int             gpu_alive, fmt_alive, read_alive, failed;
+    int64_t         fsize, next_piece, total_pieces, textcap0;
+    char            err[512];
+    /* formatter tables */
+    char            conf_tab[101][8];
+    char          **tpiece;
+    size_t         *tpiece_len;
+    /* statistics */
+    int64_t         reads_total;
+    double          busy_read, busy_gpu, busy_ingest, busy_fmt, busy_write;
+} pipeline_t;
+
+static void pl_fail(pipeline_t *pl, const char *msg)
+{
+    pthread_mutex_lock(&pl->mu);
+    if (!pl->failed) { pl->failed = 1; snprintf(pl->err, sizeof pl->err, "%s", msg); }
+    pthread_mutex_unlock(&pl->mu);
+}
+
+static void *pinned_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) return NULL;
+    return p;
+}
+
+/* Readers.  Piece k of the file is the records that START in [k*P, (k+1)*P): its first byte is the first '>' at a line
+ * start at or after k*P (byte 0 for k = 0, so text before the first header stays with piece 0), its end is the start
+ * of piece k+1.  Every piece is therefore defined by the file alone and several threads can read pieces at once
+ * (pread); a thread takes a free buffer FIRST and the next piece index second, so the pieces in flight are always the
+ * lowest unwritten ones and the in-order writer never waits for a piece that has no buffer. */
+static int64_t record_start_at_or_after(int fd, int64_t pos, int64_t fsize)
+{
+    if (pos <= 0) return 0;
+    char win[65536 + 1];
+    int64_t at = pos - 1;                                   /* the byte before pos may be the '\n' of a "\n>" at pos */
+    while (at < fsize) {
+        const ssize_t got = pread(fd, win, sizeof win - 1, (off_t)at);
+        if (got <= 1) break;
+        for (ssize_t i = 0; i + 1 < got; i++)
+            if (win[i] == '\n' && win[i + 1] == '>') return at + i + 1;
+        at += got - 1;                                      /* keep the last byte: it may be the '\n' */
+    }
+    return fsize;
+}
+
+static void *reader_main(void *arg)
+{
+    pipeline_t *pl = (pipeline_t *)arg;
+    const int fd = fileno(pl->fq);
+    for (;;) {
+        piece_t *p = q_pop(&pl->q_free);
+        if (!p) break;
+        pthread_mutex_lock(&pl->mu);
+        const int64_t k = pl->next_piece < pl->total_pieces ? pl->next_piece++ : -1;
+        pthread_mutex_unlock(&pl->mu);
+        if (k < 0 || pl->failed) { q_push(&pl->q_free, p); break; }
+        const double t0 = now_s();
+        const int64_t a = record_start_at_or_after(fd, k * pl->piece_bytes, pl->fsize);
+        const int64_t e = k + 1 >= pl->total_pieces ? pl->fsize : record_start_at_or_after(fd, (k + 1) * pl->piece_bytes, pl->fsize);
+        const int64_t len = e > a ? e - a : 0;
+        if (!p->text || len > p->textcap) {                 /* buffers are pinned on first use (and when a piece outgrows them) */
+            if (p->text) cudaFreeHost(p->text);
+            p->textcap = len > pl->textcap0 ? len + len / 8 : pl->textcap0;
+            p->text = (char *)pinned_alloc((size_t)p->textcap + 1);
+            if (!p->text) { pl_fail(pl, "pinned allocation failed"); p->textcap = 0; }
+        }
+        int64_t have = 0;
+        while (p->text && have < len) {
+            const ssize_t got = pread(fd, p->text + have, (size_t)(len - have), (off_t)(a + have));
+            if (got <= 0) { pl_fail(pl, "read failed"); break; }
+            have += got;
+        }
+        p->len = p->text ? have : 0;
+        p->seq = k;
+        pthread_mutex_lock(&pl->mu);
+        pl->busy_read += now_s() - t0;
+        pthread_mutex_unlock(&pl->mu);
+        q_push(&pl->q_gpu, p);
+    }
+    pthread_mutex_lock(&pl->mu);
+    const int last = --pl->read_alive == 0;
+    pthread_mutex_unlock(&pl->mu);
+    if (last) q_close(&pl->q_gpu);
+    return NULL;
+}
+
+typedef struct { pipeline_t *pl; int idx; } worker_arg;
+
+/* GPU worker: FASTA ingest + classification of one piece at a time on its own context */
+static void *gpu_main(void *arg)
+{
+    worker_arg *wa = (worker_arg *)arg;
+    pipeline_t *pl = wa->pl;
+    pg_ctx *ctx = pl->wctx[wa->idx];
+    const pg_model *md = pl->wmodel[wa->idx];
+    for (;;) {
+        piece_t *p = q_pop(&pl->q_gpu);
+        if (!p) break;
+        if (pl->failed || p->len == 0) { p->nrec = 0; q_push(&pl->q_fmt, p); continue; }
+        double t0 = now_s();
+        pg_reads *reads = NULL;
+        if (p->cap == 0) p->cap = p->len / 32 + 1024;
+        int rc;
+        for (;;) {
+            if (!p->hdr_off) {
+                p->hdr_off = (int64_t *)malloc(sizeof(int64_t) * (size_t)p->cap);
+                p->id_len = (int32_t *)malloc(sizeof(int32_t) * (size_t)p->cap);
+            }
+            rc = pg_fasta_ingest(ctx, p->text, p->len, p->cap, &p->nrec, p->hdr_off, p->id_len, NULL, &reads);
+            if (rc == PG_ERANGE && p->nrec > p->cap) {
+                p->cap = p->nrec;
+                free(p->hdr_off); free(p->id_len);
+                p->hdr_off = NULL; p->id_len = NULL;
+                continue;
+            }
+            break;
+        }
+        const double t_ing = now_s() - t0;
+        if (rc == PG_OK && p->nrec + 1 > p->rescap) {
+            if (p->res) cudaFreeHost(p->res);
+            p->rescap = p->nrec + p->nrec / 8 + 1024;
+            p->res = (pg_result *)pinned_alloc(sizeof(pg_result) * (size_t)p->rescap);
+            if (!p->res) { rc = PG_ENOMEM; pl_fail(pl, "pinned allocation failed"); }
+        }
+        if (rc == PG_OK && p->nrec > 0) rc = pg_classify_packed_host(ctx, md, reads, &pl->opts, p->res, NULL);
+        if (reads) pg_reads_free(reads);
+        if (rc != PG_OK) { pl_fail(pl, pg_last_error(ctx)); p->nrec = 0; }
+        pthread_mutex_lock(&pl->mu);
+        pl->busy_gpu += now_s() - t0;
+        pl->busy_ingest += t_ing;
+        pl->reads_total += p->nrec;
+        pthread_mutex_unlock(&pl->mu);
+        q_push(&pl->q_fmt, p);
+    }
+    pthread_mutex_lock(&pl->mu);
+    int last = --pl->gpu_alive == 0;
+    pthread_mutex_unlock(&pl->mu);
+    if (last) q_close(&pl->q_fmt);
+    return NULL;
+}
+
+static void grow(char **buf, size_t *cap, size_t need)
+{
+    if (need <= *cap) return;
+    size_t n = *cap ? *cap : (size_t)1 << 20;
+    while (n < need) n *= 2;
+    *buf = (char *)realloc(*buf, n);
+    *cap = n;
+}
+
+/* formatter: records of one piece -> output lines (and the ShortSequenceException messages for stdout).  Lines are
+ * assembled from pieces prepared once per taxon ("\tname\trank\t") and once per vote count, a few memcpy()s each. */
+static void format_piece(pipeline_t *pl, piece_t *p)
+{
+    static const char *FIX[6] = {"domain", "phylum", "class", "order", "family", "genus"};
+    const taxonomy *t = pl->t;
+    const int ifmt = pl->ifmt;
+    size_t on = 0, mn = 0;
+#define OUT_STR(s, n) do { memcpy(p->out + on, (s), (n)); on += (n); } while (0)
+    for (int64_t i = 0; i < p->nrec; i++) {
+        const pg_result *r = &p->res[i];
+        const char *rid = p->text + p->hdr_off[i];
+        const size_t idlen = (size_t)p->id_len[i];
+        if (r->status) {
+            grow(&p->msg, &p->msg_cap, mn + idlen + 128);
+            mn += (size_t)sprintf(p->msg + mn, "ShortSequenceException: The length of sequence with recordID=%.*s is less than %d\n",
+                                  (int)idlen, rid, PG_MIN_SEQ_LEN);
+            continue;
+        }
+        int path[PG_MAX_DEPTH], np = 0;                   /* the genus' lineage, leaf first */
+        size_t need = idlen + 16;
+        for (int n = t->genus_node[r->genus]; n >= 0 && np < PG_MAX_DEPTH; n = t->parent[n]) {
+            path[np++] = n;
+            need += pl->tpiece_len[n] + 16;               /* "\tname\trank\t" + confidence; fixrank names a longer rank at most */
+        }
+        grow(&p->out, &p->out_cap, on + need);
+        OUT_STR(rid, idlen);
+        if (ifmt == 2) OUT_STR("\t\t\t\t", 4);           /* with the piece's own leading TAB: five */
+        else { OUT_STR("\t", 1); if (r->reversed) OUT_STR("-", 1); }
+        if (ifmt == 1) {
+            for (int k = 0; k < 6; k++) {
+                int pick = -1;
+                for (int j = np - 1; j >= 0 && pick < 0; j--)
+                    if (strcmp(t->rank[path[j]], FIX[k]) == 0) pick = j;
+                for (int kk = k + 1; kk < 6 && pick < 0; kk++)   /* missing rank: back-fill from the next lower one */
+                    for (int j = np - 1; j >= 0 && pick < 0; j--)
+                        if (strcmp(t->rank[path[j]], FIX[kk]) == 0) pick = j;
+                if (pick < 0) continue;
+                const char *c = pl->conf_tab[r->votes[t->depth[path[pick]]]];
+                const size_t nl = strlen(t->name[path[pick]]), rl = strlen(FIX[k]), cl = strlen(c);
+                grow(&p->out, &p->out_cap, on + nl + rl + cl + 8);
+                OUT_STR("\t", 1); OUT_STR(t->name[path[pick]], nl);
+                OUT_STR("\t", 1); OUT_STR(FIX[k], rl);
+                OUT_STR("\t", 1); OUT_STR(c, cl);
+            }
+        } else {
+            for (int j = np - 1; j >= 0; j--) {
+                if (ifmt == 2 && t->depth[path[j]] == 0) continue;       /* Root cells are blank in the 5-TAB layout */
+                const char *c = pl->conf_tab[r->votes[t->depth[path[j]]]];
+                OUT_STR(pl->tpiece[path[j]], pl->tpiece_len[path[j]]);
+                OUT_STR(c, strlen(c));
+            }
+        }
+        grow(&p->out, &p->out_cap, on + 2);
+        OUT_STR("\n", 1);
+    }
+#undef OUT_STR
+    p->out_len = on;
+    p->msg_len = mn;
+}
+
+static void *fmt_main(void *arg)
+{
+    pipeline_t *pl = (pipeline_t *)arg;
+    for (;;) {
+        piece_t *p = q_pop(&pl->q_fmt);
+        if (!p) break;
+        double t0 = now_s();
+        p->out_len = p->msg_len = 0;
+        if (!pl->failed) format_piece(pl, p);
+        pthread_mutex_lock(&pl->mu);
+        pl->busy_fmt += now_s() - t0;
+        pthread_mutex_unlock(&pl->mu);
+        q_push(&pl->q_out, p);
+    }
+    pthread_mutex_lock(&pl->mu);
+    int last = --pl->fmt_alive == 0;
+    pthread_mutex_unlock(&pl->mu);
+    if (last) q_close(&pl->q_out);
+    return NULL;
+}
+
+/* writer: pieces leave in file order whatever order they were finished in */
+static void *writer_main(void *arg)
+{
+    pipeline_t *pl = (pipeline_t *)arg;
+    piece_t **done = (piece_t **)calloc((size_t)pl->npieces, sizeof(piece_t *));
+    int64_t next = 0;
+    for (;;) {
+        piece_t *p = q_pop(&pl->q_out);
+        if (!p) break;
+        done[p->seq % pl->npieces] = p;
+        while (done[next % pl->npieces] && done[next % pl->npieces]->seq == next) {
+            piece_t *w = done[next % pl->npieces];
+            done[next % pl->npieces] = NULL;
+            double t0 = now_s();
+            if (!pl->failed) {
+                if (w->msg_len) fwrite(w->msg, 1, w->msg_len, stdout);
+                if (w->out_len && fwrite(w->out, 1, w->out_len, pl->fo) != w->out_len) pl_fail(pl, "write failed");
+            }
+            pl->busy_write += now_s() - t0;
+            next++;
+            q_push(&pl->q_free, w);
+        }
+    }
+    free(done);
+    return NULL;
+}
+
+/* counts of device 0's model -> the models of the other devices: one ncclBroadcast per buffer (NVLink / NVSwitch);
+ * a device that is listed twice cannot be two NCCL ranks, so such layouts use peer copies */
+static int replicate_counts(int ndev, const int *dev, pg_model **models, char *err, size_t errlen)
+{
+    void *ptr[16][8];
+    size_t nbytes[8];
+    int nbuf = 0;
+    for (int r = 0; r < ndev; r++)
+        if (pg_model_buffers(models[r], ptr[r], nbytes, 8, &nbuf) != PG_OK) { snprintf(err, errlen, "pg_model_buffers failed"); return 1; }
+    int distinct = 1;
+    for (int a = 0; a < ndev; a++)
+        for (int b = a + 1; b < ndev; b++)
+            if (dev[a] == dev[b]) distinct = 0;
+    if (!distinct) {
+        for (int r = 1; r < ndev; r++)
+            for (int b = 0; b < nbuf; b++)
+                if (cudaMemcpyPeer(ptr[r][b], dev[r], ptr[0][b], dev[0], nbytes[b]) != cudaSuccess) { snprintf(err, errlen, "peer copy failed"); return 1; }
+        cudaDeviceSynchronize();
+        return 0;
+    }
+    ncclComm_t comms[16];
+    cudaStream_t streams[16];
+    ncclResult_t nr = ncclCommInitAll(comms, ndev, dev);
+    if (nr != ncclSuccess) { snprintf(err, errlen, "ncclCommInitAll: %s", ncclGetErrorString(nr)); return 1; }
+    for (int r = 0; r < ndev; r++) { cudaSetDevice(dev[r]); cudaStreamCreateWithFlags(&streams[r], cudaStreamNonBlocking); }
+    for (int b = 0; b < nbuf && nr == ncclSuccess; b++) {
+        ncclGroupStart();
+        for (int r = 0; r < ndev; r++) {
+            cudaSetDevice(dev[r]);
+            ncclResult_t x = ncclBroadcast(ptr[r][b], ptr[r][b], nbytes[b], ncclUint8, 0, comms[r], streams[r]);
+            if (x != ncclSuccess) nr = x;
+        }
+        ncclResult_t x = ncclGroupEnd();
+        if (x != ncclSuccess) nr = x;
+    }
+    for (int r = 0; r < ndev; r++) { cudaSetDevice(dev[r]); cudaStreamSynchronize(streams[r]); cudaStreamDestroy(streams[r]); ncclCommDestroy(comms[r]); }
+    if (nr != ncclSuccess) { snprintf(err, errlen, "ncclBroadcast: %s", ncclGetErrorString(nr)); return 1; }
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     static struct option lo[] = {{"train", required_argument, 0, 'T'}, {"ranks", required_argument, 0, 'R'},
                                  {"genus-token", required_argument, 0, 'K'}, {"device", required_argument, 0, 'G'},
-                                 {"strict", no_argument, 0, 'S'}, {"min-boot-words", required_argument, 0, 'M'}, {0, 0, 0, 0}};
-    const char *q = NULL, *o = NULL, *model = NULL, *fmt = "allrank", *train = NULL, *ranks = NULL;
-    int device = 0, genus_token = 0, strict = 0, min_boot = 0;
+                                 {"strict", no_argument, 0, 'S'}, {"min-boot-words", required_argument, 0, 'M'},
+                                 {"gpus", required_argument, 0, 'N'}, {"devices", required_argument, 0, 'D'},
+                                 {"contexts-per-gpu", required_argument, 0, 'C'}, {"format-threads", required_argument, 0, 'F'},
+                                 {0, 0, 0, 0}};
+    const char *q = NULL, *o = NULL, *model = NULL, *fmt = "allrank", *train = NULL, *ranks = NULL, *devlist = NULL;
+    int device = 0, genus_token = 0, strict = 0, min_boot = 0, ngpu = 1, per_gpu = 2, nformat = 0;
     for (;;) {
         int c = getopt_long(argc, argv, "q:o:t:f:g:", lo, NULL);
         if (c == -1) break;
@@ -230,165 +618,168 @@ int main(int argc, char **argv)
         case 'G': device = atoi(optarg); break;
         case 'S': strict = 1; break;
         case 'M': min_boot = atoi(optarg); break;
+        case 'N': ngpu = atoi(optarg); break;
+        case 'D': devlist = optarg; break;
+        case 'C': per_gpu = atoi(optarg); break;
+        case 'F': nformat = atoi(optarg); break;
         default: break;
         }
     }
     if (!model) model = getenv("PANGEA_RDP_MODEL");
     if (!model) model = "rdp_model.pgm";
     if (!train && (!q || !o)) {
-        printf("Usage: rdp_classifier -q <query.fa> -o <out.txt> [-t model.pgm] [-f allrank|fixrank|pangea]\n"
+        printf("Usage: rdp_classifier -q <query.fa> -o <out.txt> [-t model.pgm] [-f allrank|fixrank|pangea] [--gpus N] [--devices a,b,...]\n"
                "       rdp_classifier --train <training.fa> -t <model.pgm> [--ranks r0,r1,...] [--genus-token N]\n");
         return 0;
     }
     int ifmt = strcmp(fmt, "allrank") == 0 ? 0 : strcmp(fmt, "fixrank") == 0 ? 1 : strcmp(fmt, "pangea") == 0 ? 2 : -1;
     if (ifmt < 0) { fprintf(stderr, "rdp_classifier: unknown format %s\n", fmt); return 1; }
+    if (ngpu < 1 || ngpu > 16 || per_gpu < 1 || per_gpu > 4) { fprintf(stderr, "rdp_classifier: --gpus 1..16, --contexts-per-gpu 1..4\n"); return 1; }
+    int dev[16];
+    for (int r = 0; r < ngpu; r++) dev[r] = device + r;
+    if (devlist) {
+        char *dl = strdup(devlist);
+        int r = 0;
+        for (char *tok = strtok(dl, ","); tok && r < 16; tok = strtok(NULL, ",")) dev[r++] = atoi(tok);
+        if (r != ngpu) { fprintf(stderr, "rdp_classifier: --devices lists %d devices, --gpus says %d\n", r, ngpu); return 1; }
+        free(dl);
+    }
     const int timing = getenv("PG_TIMING") != NULL;
-    double t0 = now_s(), t1;
-    pg_ctx *ctx = pg_init(device);
-    if (!ctx) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(NULL)); return 1; }
+    double t0 = now_s(), t1, t_begin = t0;
 #define LAP(what) do { if (timing) { t1 = now_s(); fprintf(stderr, "[timing] %-22s %.3f s\n", what, t1 - t0); t0 = t1; } } while (0)
+    const int nworkers = train ? 1 : ngpu * per_gpu;
+    pg_ctx **wctx = (pg_ctx **)calloc((size_t)nworkers, sizeof(pg_ctx *));
+    for (int w = 0; w < nworkers; w++) {
+        wctx[w] = pg_init(dev[w % ngpu]);                /* workers 0..ngpu-1 own the models of their devices */
+        if (!wctx[w]) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(NULL)); return 1; }
+    }
     LAP("pg_init");
     if (train) {
-        int rc = do_train(ctx, train, model, ranks, genus_token);
-        pg_shutdown(ctx);
+        int rc = do_train(wctx[0], train, model, ranks, genus_token);
+        pg_shutdown(wctx[0]);
         return rc;
     }
 
-    pg_model *md = NULL;
+    /* ---- the model: device 0 reads the file; the other devices get its integer counts and derive their own tables */
+    pg_model **models = (pg_model **)calloc((size_t)ngpu, sizeof(pg_model *));
     void *blob = NULL;
     int64_t blen = 0;
-    if (pg_model_load(ctx, model, &md, &blob, &blen) != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx)); return 1; }
+    if (pg_model_load(wctx[0], model, &models[0], &blob, &blen) != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(wctx[0])); return 1; }
     taxonomy t;
     if (!blob || tax_from_blob((const char *)blob, blen, &t)) { fprintf(stderr, "rdp_classifier: %s has no taxonomy section\n", model); return 1; }
     LAP("model load");
-    /* the query file goes to the device as text: records, ids and the packed read store come from the GPU
-     * (pg_fasta_ingest); the host keeps the text only to print the ids */
-    FILE *fq = fopen(q, "rb");
-    if (!fq) { fprintf(stderr, "rdp_classifier: cannot read %s\n", q); return 1; }
-    FILE *fo = fopen(o, "w");
-    if (!fo) { fprintf(stderr, "rdp_classifier: cannot write %s\n", o); return 1; }
-    pg_classify_opts opts;
-    memset(&opts, 0, sizeof opts);
-    opts.min_boot_words = min_boot;
-    opts.mode = strict ? 0 : 1;
-    /* Files of any size: the text is handed over in pieces of about 1 GiB cut at record boundaries (a line
-     * starting with '>'), so the device never holds more than one piece with its word ids and records.
-     * PG_CLI_PIECE_BYTES overrides the size (tests). */
-    int64_t piece_bytes = (int64_t)1 << 30;
-    if (getenv("PG_CLI_PIECE_BYTES") && atoll(getenv("PG_CLI_PIECE_BYTES")) > 0) piece_bytes = atoll(getenv("PG_CLI_PIECE_BYTES"));
-    int64_t *hdr_off = NULL;
-    int32_t *id_len = NULL;
-    pg_result *res = NULL;
-    int64_t cap = 0, rescap = 0;
-    static const char *FIX[6] = {"domain", "phylum", "class", "order", "family", "genus"};
-    /* Output is assembled from pieces prepared once per taxon ("\tname\trank\t") and once per vote
-     * count (the 101 possible confidences), so a line costs a few memcpy()s, not a dozen fprintf()s. */
-    char conf_tab[101][8];
-    for (int v = 0; v <= 100; v++) pg_fmt_conf(v, conf_tab[v]);
-    char **piece = (char **)malloc(sizeof(char *) * (size_t)t.nnodes);
-    size_t *piece_len = (size_t *)malloc(sizeof(size_t) * (size_t)t.nnodes);
+    if (ngpu > 1) {
+        int32_t *anc = tax_lineage_table(&t);
+        for (int r = 1; r < ngpu; r++) {
+            if (pg_model_create(wctx[r], t.G, &models[r]) != PG_OK || pg_model_set_lineage(models[r], anc, t.maxdepth) != PG_OK) {
+                fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(wctx[r]));
+                return 1;
+            }
+        }
+        for (int r = 0; r < ngpu; r++) pg_sync(wctx[r]);
+        char err[256];
+        if (replicate_counts(ngpu, dev, models, err, sizeof err)) { fprintf(stderr, "rdp_classifier: %s\n", err); return 1; }
+        for (int r = 1; r < ngpu; r++)
+            if (pg_model_commit(models[r]) != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(wctx[r])); return 1; }
+        free(anc);
+        LAP("model replication");
+    }
+
+    pipeline_t pl;
+    memset(&pl, 0, sizeof pl);
+    pl.t = &t;
+    pl.ifmt = ifmt;
+    pl.opts.min_boot_words = min_boot;
+    pl.opts.mode = strict ? 0 : 1;
+    /* pieces of about 64 MiB (PG_CLI_PIECE_BYTES overrides, tests): large enough for full chunks of reads on the device,
+     * small enough that ten of them -- three being read, one per device context, the rest with the formatters and the
+     * writer -- stay pinned without a long start-up */
+    pl.piece_bytes = (int64_t)64 << 20;
+    if (getenv("PG_CLI_PIECE_BYTES") && atoll(getenv("PG_CLI_PIECE_BYTES")) > 0) pl.piece_bytes = atoll(getenv("PG_CLI_PIECE_BYTES"));
+    pl.fq = fopen(q, "rb");
+    if (!pl.fq) { fprintf(stderr, "rdp_classifier: cannot read %s\n", q); return 1; }
+    pl.fo = fopen(o, "w");
+    if (!pl.fo) { fprintf(stderr, "rdp_classifier: cannot write %s\n", o); return 1; }
+    setvbuf(pl.fo, NULL, _IONBF, 0);                      /* pieces are written whole */
+    if (nformat <= 0) {
+        long nc = sysconf(_SC_NPROCESSORS_ONLN);
+        nformat = nc > 16 ? 8 : (nc > 4 ? 4 : 2);
+        if (nformat < ngpu * 3) nformat = ngpu * 3;
+    }
+    pl.nworkers = nworkers;
+    pl.nformat = nformat;
+    pl.wctx = wctx;
+    pl.wmodel = (pg_model **)calloc((size_t)nworkers, sizeof(pg_model *));
+    for (int w = 0; w < nworkers; w++) pl.wmodel[w] = models[w % ngpu];
+    pl.gpu_alive = nworkers;
+    pl.fmt_alive = nformat;
+    pthread_mutex_init(&pl.mu, NULL);
+    for (int v = 0; v <= 100; v++) pg_fmt_conf(v, pl.conf_tab[v]);
+    pl.tpiece = (char **)malloc(sizeof(char *) * (size_t)t.nnodes);
+    pl.tpiece_len = (size_t *)malloc(sizeof(size_t) * (size_t)t.nnodes);
     for (int k = 0; k < t.nnodes; k++) {
         size_t n = strlen(t.name[k]) + strlen(t.rank[k]) + 4;
-        piece[k] = (char *)malloc(n);
-        piece_len[k] = (size_t)snprintf(piece[k], n, "\t%s\t%s\t", t.name[k], t.rank[k]);
+        pl.tpiece[k] = (char *)malloc(n);
+        pl.tpiece_len[k] = (size_t)snprintf(pl.tpiece[k], n, "\t%s\t%s\t", t.name[k], t.rank[k]);
     }
-    size_t ocap = (size_t)8 << 20, on = 0;
-    char *obuf = (char *)malloc(ocap);
-    /* the file is read piece by piece: host memory holds one piece (plus the head of the next record) */
-    int64_t bufcap = piece_bytes + 4096, have = 0;
-    char *qbuf = (char *)malloc((size_t)bufcap + 1);
-    int at_eof = 0;
-    for (;;) {
-        while (!at_eof && have < bufcap) {
-            size_t got = fread(qbuf + have, 1, (size_t)(bufcap - have), fq);
-            if (got == 0) at_eof = 1;
-            have += (int64_t)got;
-        }
-        if (have == 0) break;
-        int64_t p1 = have;
-        if (!at_eof) {                                     /* cut at the start of the last record in the buffer */
-            int64_t c = have - 1;
-            while (c > 0 && !(qbuf[c] == '>' && qbuf[c - 1] == '\n')) c--;
-            if (c > 0) p1 = c;
-            else {                                         /* one record longer than the buffer: make room, read on */
-                bufcap *= 2;
-                qbuf = (char *)realloc(qbuf, (size_t)bufcap + 1);
-                continue;
-            }
-        }
-        const char *ptext = qbuf;
-        const int64_t plen = p1;
-        int64_t nrec = 0;
-        pg_reads *reads = NULL;
-        if (cap == 0) cap = plen / 32 + 1024;
-        for (;;) {
-            hdr_off = (int64_t *)realloc(hdr_off, sizeof(int64_t) * (size_t)cap);
-            id_len = (int32_t *)realloc(id_len, sizeof(int32_t) * (size_t)cap);
-            int rc = pg_fasta_ingest(ctx, ptext, plen, cap, &nrec, hdr_off, id_len, NULL, &reads);
-            if (rc == PG_ERANGE && nrec > cap) { cap = nrec; continue; }
-            if (rc != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx)); return 1; }
-            break;
-        }
-        LAP("FASTA ingest (GPU)");
-        if (nrec + 1 > rescap) { rescap = nrec + 1; res = (pg_result *)realloc(res, sizeof(pg_result) * (size_t)rescap); }
-        if (nrec > 0 && pg_classify_packed_host(ctx, md, reads, &opts, res, NULL) != PG_OK) {
-            fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx));
-            return 1;
-        }
-        pg_reads_free(reads);
-        LAP("pg_classify_packed");
-#define OUT_ROOM(need) do { if (on + (need) > ocap) { fwrite(obuf, 1, on, fo); on = 0; } } while (0)
-#define OUT_STR(s, n) do { memcpy(obuf + on, (s), (n)); on += (n); } while (0)
-    for (int64_t i = 0; i < nrec; i++) {
-        const pg_result *r = &res[i];
-        const char *rid = ptext + hdr_off[i];
-        const size_t idlen = (size_t)id_len[i];
-        if (r->status) {
-            printf("ShortSequenceException: The length of sequence with recordID=%.*s is less than %d\n", (int)idlen, rid, PG_MIN_SEQ_LEN);
-            continue;
-        }
-        int path[PG_MAX_DEPTH], np = 0;                   /* the genus' lineage, leaf first */
-        for (int n = t.genus_node[r->genus]; n >= 0 && np < PG_MAX_DEPTH; n = t.parent[n]) path[np++] = n;
-        OUT_ROOM(idlen + 16 + (size_t)np * 256);
-        OUT_STR(rid, idlen);
-        if (ifmt == 2) OUT_STR("\t\t\t\t", 4);           /* with the piece's own leading TAB: five */
-        else { OUT_STR("\t", 1); if (r->reversed) OUT_STR("-", 1); }
-        if (ifmt == 1) {
-            for (int k = 0; k < 6; k++) {
-                int pick = -1;
-                for (int j = np - 1; j >= 0 && pick < 0; j--)
-                    if (strcmp(t.rank[path[j]], FIX[k]) == 0) pick = j;
-                for (int kk = k + 1; kk < 6 && pick < 0; kk++)   /* missing rank: back-fill from the next lower one */
-                    for (int j = np - 1; j >= 0 && pick < 0; j--)
-                        if (strcmp(t.rank[path[j]], FIX[kk]) == 0) pick = j;
-                if (pick < 0) continue;
-                const char *c = conf_tab[r->votes[t.depth[path[pick]]]];
-                on += (size_t)sprintf(obuf + on, "\t%s\t%s\t%s", t.name[path[pick]], FIX[k], c);
-            }
-        } else {
-            for (int j = np - 1; j >= 0; j--) {
-                if (ifmt == 2 && t.depth[path[j]] == 0) continue;        /* Root cells are blank in the 5-TAB layout */
-                const char *c = conf_tab[r->votes[t.depth[path[j]]]];
-                OUT_STR(piece[path[j]], piece_len[path[j]]);
-                OUT_STR(c, strlen(c));
-            }
-        }
-        OUT_STR("\n", 1);
+    fseek(pl.fq, 0, SEEK_END);
+    pl.fsize = ftell(pl.fq);
+    fseek(pl.fq, 0, SEEK_SET);
+    pl.total_pieces = pl.fsize > 0 ? (pl.fsize + pl.piece_bytes - 1) / pl.piece_bytes : 0;
+    /* a piece holds the records that start inside its window, so it can run a record past it; small files: one piece
+     * is all there is -- size the buffers by the file */
+    pl.textcap0 = pl.piece_bytes + pl.piece_bytes / 16 + 65536;
+    if (pl.fsize + 4096 < pl.textcap0) pl.textcap0 = pl.fsize + 4096;
+    const int nreaders = pl.total_pieces > 2 ? 3 : 1;
+    pl.read_alive = nreaders;
+    pl.npieces = nworkers + nformat + nreaders + 1;
+    if (pl.total_pieces < pl.npieces) pl.npieces = (int)(pl.total_pieces > 0 ? pl.total_pieces : 1);
+    q_init(&pl.q_free, pl.npieces + 1);
+    q_init(&pl.q_gpu, pl.npieces + 1);
+    q_init(&pl.q_fmt, pl.npieces + 1);
+    q_init(&pl.q_out, pl.npieces + 1);
+    piece_t *pieces = (piece_t *)calloc((size_t)pl.npieces, sizeof(piece_t));
+    cudaSetDevice(dev[0]);
+    for (int i = 0; i < pl.npieces; i++) {
+        /* pinned up front: cudaHostAlloc takes the driver's lock and would stall the device contexts mid-run */
+        pieces[i].textcap = pl.textcap0;
+        pieces[i].text = (char *)pinned_alloc((size_t)pl.textcap0 + 1);
+        pieces[i].rescap = pl.textcap0 / 256 + 1024;
+        pieces[i].res = (pg_result *)pinned_alloc(sizeof(pg_result) * (size_t)pieces[i].rescap);
+        if (!pieces[i].text || !pieces[i].res) { fprintf(stderr, "rdp_classifier: pinned allocation failed\n"); return 1; }
+        q_push(&pl.q_free, &pieces[i]);
     }
-        LAP("format + write");
-        memmove(qbuf, qbuf + p1, (size_t)(have - p1));    /* the head of the next record moves to the front */
-        have -= p1;
+    LAP("buffers");
+
+    pthread_t th_reader[4], th_writer, *th_gpu = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nworkers),
+              *th_fmt = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nformat);
+    worker_arg *wa = (worker_arg *)malloc(sizeof(worker_arg) * (size_t)nworkers);
+    const double t_pipe = now_s();
+    pthread_create(&th_writer, NULL, writer_main, &pl);
+    for (int f = 0; f < nformat; f++) pthread_create(&th_fmt[f], NULL, fmt_main, &pl);
+    for (int w = 0; w < nworkers; w++) { wa[w].pl = &pl; wa[w].idx = w; pthread_create(&th_gpu[w], NULL, gpu_main, &wa[w]); }
+    for (int r = 0; r < nreaders; r++) pthread_create(&th_reader[r], NULL, reader_main, &pl);
+    for (int r = 0; r < nreaders; r++) pthread_join(th_reader[r], NULL);
+    for (int w = 0; w < nworkers; w++) pthread_join(th_gpu[w], NULL);
+    for (int f = 0; f < nformat; f++) pthread_join(th_fmt[f], NULL);
+    pthread_join(th_writer, NULL);
+    q_close(&pl.q_free);
+    const double dt = now_s() - t_pipe;
+    fclose(pl.fq);
+    fclose(pl.fo);
+    if (pl.failed) { fprintf(stderr, "rdp_classifier: %s\n", pl.err); return 1; }
+    if (timing)
+        fprintf(stderr, "[timing] pipeline %.3f s for %lld reads = %.2f M reads/s (%d GPUs x %d contexts, %d formatter threads; busy: "
+                        "read %.3f, gpu %.3f (ingest %.3f), format %.3f, write %.3f s); whole run %.3f s\n",
+                dt, (long long)pl.reads_total, 1e-6 * (double)pl.reads_total / dt, ngpu, per_gpu, nformat, pl.busy_read, pl.busy_gpu,
+                pl.busy_ingest, pl.busy_fmt, pl.busy_write, now_s() - t_begin);
+    for (int i = 0; i < pl.npieces; i++) {
+        if (pieces[i].text) cudaFreeHost(pieces[i].text);
+        if (pieces[i].res) cudaFreeHost(pieces[i].res);
+        free(pieces[i].hdr_off); free(pieces[i].id_len); free(pieces[i].out); free(pieces[i].msg);
     }
-    fclose(fq);
-    fwrite(obuf, 1, on, fo);
-    free(obuf);
-    fclose(fo);
-    free(res);
     pg_free(blob);
-    free(qbuf);
-    free(hdr_off);
-    free(id_len);
-    pg_model_free(md);
-    pg_shutdown(ctx);
+    for (int r = 0; r < ngpu; r++) pg_model_free(models[r]);
+    for (int w = 0; w < nworkers; w++) pg_shutdown(wctx[w]);
     return 0;
 }

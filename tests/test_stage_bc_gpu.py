@@ -2,6 +2,7 @@
 the drop-in executables.  Expected outputs: the golden files produced by the reference's own
 Perl/C (tests/golden/make_golden.py), the reference's tax_class binary (oracle/_ref, compiled
 from ncbitc.c), and the C restatements in oracle/ on larger seeded inputs."""
+import os
 import shutil
 import subprocess
 from pathlib import Path
@@ -278,3 +279,53 @@ def test_rdp_classifier_cli_genus_token_mode(tmp_path):
     hit = sum(1 for l, h in zip(lines, hdr) if l.split("\t")[5] == h.split()[1])
     assert hit >= 0.9 * len(ids)                                             # self-classification
     assert all(l.split("\t")[2:5] == ["Root", "rootrank", "1.0"] for l in lines)
+
+
+def test_rdp_classifier_cli_multi_gpu_equals_single(tmp_path):
+    """rdp_classifier --gpus N: the model counts are replicated from device 0 (ncclBroadcast between distinct GPUs, peer
+    copies when the box has one GPU and it is listed twice), the query file is cut into record-aligned pieces that the
+    device contexts take in turn, and the lines come out in input order: the file must be byte-identical to the
+    one-GPU file whatever the piece size, and the records must be the oracle's."""
+    import torch
+
+    import oracle_rdp as ora
+    from pangea_b200 import synth
+
+    tr = synth.synth16s(seed=71, seqs=400, genera=140, length=800)
+    write_training_fasta(tmp_path / "train.fa", tr)
+    model = tmp_path / "m.pgm"
+    run([BIN / "rdp_classifier", "--train", tmp_path / "train.fa", "-t", model])
+    data, off, src = synth.synth_reads(72, tr, 5000, paired=True)
+    with open(tmp_path / "q.fa", "w") as f:
+        for i in range(5000):
+            f.write(f">r{i:07d}:AB\n{data[off[i]:off[i + 1]].tobytes().decode()}\n")
+            if i % 997 == 0:
+                f.write(f">short{i}\nACGTACGT\n")
+    one = tmp_path / "one.txt"
+    r1 = run([BIN / "rdp_classifier", "-q", tmp_path / "q.fa", "-o", one, "-t", model, "--contexts-per-gpu", "1"])
+    ndev = torch.cuda.device_count()
+    devs = "0,1" if ndev >= 2 else "0,0"
+    env = dict(os.environ, PG_CLI_PIECE_BYTES="300000")          # ~430 reads per piece: a dozen pieces in flight
+    for extra in (["--gpus", "2", "--devices", devs], ["--gpus", "2", "--devices", devs, "--contexts-per-gpu", "1", "--format-threads", "1"],
+                  ["--gpus", "1"]):
+        out = tmp_path / "multi.txt"
+        r2 = subprocess.run([str(BIN / "rdp_classifier"), "-q", str(tmp_path / "q.fa"), "-o", str(out), "-t", str(model)] + extra,
+                            capture_output=True, text=True, env=env, timeout=600)
+        assert r2.returncode == 0, r2.stderr
+        assert out.read_bytes() == one.read_bytes(), extra
+        assert r2.stdout == r1.stdout and r2.stdout.count("ShortSequenceException") == 6
+    # the lines carry the oracle's assignments
+    first = {}
+    for g in tr["genus"]:
+        first.setdefault(int(g), len(first))
+    genus_cli = np.array([first[int(g)] for g in tr["genus"]], np.int32)
+    om = ora.Model(tr["data"], tr["off"], genus_cli, tr["G"])
+    ref = om.classify(data[: off[300]], off[:301])
+    order = sorted(first, key=first.get)
+    lines = one.read_text().split("\n")[:-1]
+    assert len(lines) == 5000
+    for i in range(300):
+        cells = lines[i].split("\t")
+        assert cells[0] == f"r{i:07d}:AB" and cells[1] == ("-" if ref[i]["reversed"] else "")
+        assert cells[-3] == tr["node_names"][tr["anc"][order[ref[i]["genus"]]][-1]]
+    om.free()

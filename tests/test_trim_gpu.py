@@ -46,7 +46,7 @@ def test_trim_cli_like_the_readme(tmp_path):
     assert r.returncode == 0 and out.read_bytes() == (GOLD / "qseq_g100.expected.fasta").read_bytes()
     r = subprocess.run([str(BIN / "trim2"), "-a", "../input_A.txt", "-b", "../input_B.txt", "-qc", "25", "-g", "100"],
                        cwd=tmp_path / "Trim", capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0 and out.read_bytes() == (GOLD / "qseq_g189.expected.fasta").read_bytes()
+    assert r.returncode == 0 and out.read_bytes() == (GOLD / "qseq_default.expected.fasta").read_bytes()
     # FASTQ: records are echoed on stdout as well
     (tmp_path / "x.fastq").write_bytes((GOLD / "reads.fastq").read_bytes())
     r = subprocess.run([str(BIN / "trim2"), "-a", "x.fastq"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
