@@ -169,13 +169,19 @@ typedef struct {
     int32_t bound_level;      /* cert_plan 0 only, results never depend on it: which kernel bounds the blocks the
                                  best part leaves: 0 or 1 = the 16-bit bounds, one CTA per (read, group of 28 blocks);
                                  2 = a coarse 8-bit first level over all blocks + an exact second level (measured
-                                 no faster on 10 000 genera, kept for models with many more groups) */
+                                 no faster on 10 000 genera, kept for models with many more groups); 3 = the 16-bit
+                                 bounds over the table's 16-position PARTS instead of its 64-position blocks (four times
+                                 the columns, far stronger bounds when genera have hundreds of training members) */
     int32_t reserved[3];
 } pg_classify_opts;
 
 /* 1 if the model's quantised table certifies every deficit (mode 1 is then the
  * certified path; otherwise mode 1 silently runs the strict kernels). */
 int pg_model_certifiable(const pg_model *m);
+/* Which columns the certified path's lower bounds use for this model: 0 = the 64-position blocks, 1 = the 16-position
+ * parts, -1 = not decided yet.  Models with more than one group of blocks are timed both ways on the head of the first
+ * batch they classify (bound_level 0); results never depend on it. */
+int pg_model_bound_columns(const pg_model *m);
 /* How the reads of the last pg_classify*() call were routed: through the certified
  * kernels, through the strict kernels, and handed back from certified to strict. */
 int pg_classify_stats(const pg_ctx *ctx, int64_t *certified_reads, int64_t *strict_reads, int64_t *handed_back);

@@ -259,6 +259,8 @@ int pg_model_derive_quantised(pg_model *md)
 {
     pg_ctx *ctx = md->ctx;
     md->q_ok = false;
+    md->bounds_tuned = false;
+    md->part_bounds = false;
     if (!md->d_perm) PG_TRY(pg_model_set_layout(md, NULL, 0));
     const size_t cells = (size_t)md->ntile64 * PG_NWORDS * 64;
     const size_t bmcells = (size_t)md->ngroup * PG_NWORDS * 32;
@@ -839,7 +841,11 @@ k_guess_bm(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, 
     if (lane == 0) guess[slot0 + slot] = (int32_t)best;
 }
 
-template <int BLOCK>
+// PART = true: the columns are the 16-position PARTS of the table (hm rows, 32 parts per group) instead of its 64-position
+// blocks.  Four times the columns, but a part's minimum is much larger than its block's when every genus holds
+// thousands of once-seen words (a training set with hundreds of members per genus): there the block bounds are too
+// weak to dismiss far blocks and the part bounds are not.  The open pairs come out as part items.
+template <int BLOCK, bool PART>
 __global__ void __launch_bounds__(BLOCK)      // (a 64-register budget for 6 CTAs/SM was measured: no gain)
 k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
         const int32_t *__restrict__ nwords, const uint8_t *__restrict__ flags, const int32_t *__restrict__ order,
@@ -869,7 +875,7 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     // while the cp.async copies are in flight, stored once they have landed)
     const int gs = guess[rc];
     const int best = hm ? gs / PG_PARTS : gs, own = hm ? gs % PG_PARTS : 0;
-    const bool sib_here = hm && best / PG_GB == grp;
+    const bool sib_here = !PART && hm && best / PG_GB == grp;
     const uint16_t *hrow = hm ? hm + (size_t)((best * PG_PARTS) >> 5) * PG_NWORDS * 32 + ((best * PG_PARTS) & 31) : NULL;
     uint2 hv[4];
     if (sib_here) {
@@ -897,12 +903,18 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     }
 
     const int unit = tid >> 3, hl = tid & 7;
-    const int b0 = grp * PG_GB + 4 * hl;
+    const int b0 = grp * (PART ? 32 : PG_GB) + 4 * hl;
     bool ok[4];
     int okblk[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int slot = 4 * hl + i;
+        if (PART) {                                 // column = part b0 + i of the table; the read's own part is never tested
+            const int p = b0 + i;
+            ok[i] = p < PG_PARTS * ntile64 && p != gs;
+            okblk[i] = 0x8000 | ((p % PG_PARTS) << 13) | (p / PG_PARTS);
+            continue;
+        }
         okblk[i] = b0 + i;
         ok[i] = slot < PG_GB && b0 + i < ntile64 && b0 + i != best;
         if (slot >= PG_GB) {                        // part item: that sibling part of the best block only
@@ -998,10 +1010,16 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
         const int blk = grp * PG_GB + tid;
         const unsigned long long cv = __ldg(mychamp);
         const unsigned long long thr = (cv == PG_CHAMP_INIT) ? ~0ULL : (cv >> 32) + pg_margin(n, vmax);
+        if (PART) {
+            const int p = grp * 32 + tid;
+            if (p < PG_PARTS * ntile64 && p != gs && (unsigned long long)s_full[tid] <= thr)
+                PG_SURVIVE(0, 0x8000 | ((p % PG_PARTS) << 13) | (p / PG_PARTS))
+        } else {
         const bool real = tid < PG_GB && blk < ntile64 && blk != best;
         const int part = tid - PG_GB;
         if ((real || (tid >= PG_GB && sib_here && part != own)) && (unsigned long long)s_full[tid] <= thr)
             PG_SURVIVE(0, real ? blk : (0x8000 | (part << 13) | best))
+        }
     }
     __syncthreads();
     const unsigned int cnt = s_cnt;
@@ -1884,11 +1902,22 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
         PG_LAUNCHED(ctx);
     } else {
     const size_t bsmem = (size_t)(nmax + 1) * 64;
-    PG_CUDA(ctx, cudaFuncSetAttribute(k_bound<160>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
-    k_bound<160><<<dim3(nreads_b, (unsigned)md->ngroup), 160, bsmem, ctx->stream>>>(
+    static int env_part = -2;                           // PG_BOUND_PART=0/1: block / part columns (A/B switch)
+    if (env_part == -2) { const char *e = getenv("PG_BOUND_PART"); env_part = e ? atoi(e) : -1; }
+    const bool part_cols = version == 3 && (env_part >= 0 ? env_part != 0 : (blevel == 3 || (blevel == 0 && (cb.force_part >= 0 ? cb.force_part != 0 : md->part_bounds))));
+    if (part_cols) {
+        PG_CUDA(ctx, cudaFuncSetAttribute(k_bound<160, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+        k_bound<160, true><<<dim3(nreads_b, (unsigned)md->ngroup_h), 160, bsmem, ctx->stream>>>(
+            md->d_hmtable, d_words, d_off, d_nwords, d_flags, d_order, slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot,
+            md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.counters + 2, cb.item_cap, cb.heavy,
+            (unsigned int)light_max, md->d_hmtable);
+    } else {
+    PG_CUDA(ctx, cudaFuncSetAttribute(k_bound<160, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    k_bound<160, false><<<dim3(nreads_b, (unsigned)md->ngroup), 160, bsmem, ctx->stream>>>(
         md->d_bmtable, d_words, d_off, d_nwords, d_flags, d_order, slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot,
         md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.counters + 2, cb.item_cap, cb.heavy,
         (unsigned int)light_max, version == 3 ? md->d_hmtable : NULL);
+    }
     PG_LAUNCHED(ctx);
     }
     static int light_ctas = 0;                          // resident CTAs per SM of the persistent item kernel

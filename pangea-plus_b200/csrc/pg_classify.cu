@@ -380,14 +380,18 @@ struct ClassifyJob {
         memset(&cb, 0, sizeof cb);
         cb.light_max = opts ? opts->light_max : 0;
         cb.bound_level = opts ? opts->bound_level : 0;
-        if (cb.bound_level < 0 || cb.bound_level > 2) return pg_fail(ctx, PG_EINVAL, "unknown bound_level %d", cb.bound_level);
+        cb.force_part = -1;
+        if (cb.bound_level < 0 || cb.bound_level > 3) return pg_fail(ctx, PG_EINVAL, "unknown bound_level %d", cb.bound_level);
         if (certified) {
             PG_TRY(pg_scratch(ctx, &ctx->s_champ, (size_t)cmax * nkeys * 8));
             PG_TRY(pg_scratch(ctx, &ctx->s_ncand, (size_t)cmax * 4));
             PG_TRY(pg_scratch(ctx, &ctx->s_candl, (size_t)cmax * PG_CANDCAP * 8));
             PG_TRY(pg_scratch(ctx, &ctx->s_fb, (size_t)count * 4 + 16));
             PG_TRY(pg_scratch(ctx, &ctx->s_guess, (size_t)cmax * 4));
-            cb.item_cap = (unsigned int)(cmax * 64 < 4096 ? 4096 : cmax * 64);
+            // room for 512 open (task, block) pairs per read of a chunk on average (268 MB for 2^16 reads): a full buffer
+            // sends reads to the all-block kernel, which costs far more than the items would (models with hundreds of
+            // members per genus leave ~200 pairs per read open)
+            cb.item_cap = (unsigned int)(cmax * 512 < 4096 ? 4096 : cmax * 512);
             PG_TRY(pg_scratch(ctx, &ctx->s_items, (size_t)cb.item_cap * 8));
             PG_TRY(pg_scratch(ctx, &ctx->s_heavy, (size_t)count * 4 + (size_t)cmax + 64));
             cb.champ = (unsigned long long *)ctx->s_champ.p;
@@ -521,6 +525,49 @@ struct ClassifyJob {
         return PG_OK;
     }
 
+    // Block or part columns for the lower bounds?  Which is faster depends on the MODEL (with a few training members
+    // per genus a 64-genus block minimum dismisses far blocks; with hundreds, once-seen words fill every genus and only
+    // the 16-position part minima do), so a model with more than one group of blocks is tried both ways, once, on the
+    // head of the first batch it classifies.  Results never depend on the choice; the trial's records are rewritten
+    // by the real pass.
+    int tune_bounds(int64_t r0, int64_t r1)
+    {
+        if (md->bounds_tuned || !certified || cert_version != 3 || cb.bound_level != 0 || md->ngroup < 2) return PG_OK;
+        if (r0 != 0 || r1 - r0 < 2048) return PG_OK;                 // counters must still be zero; too few reads say nothing
+        const int64_t cn = r1 - r0 < 8192 ? r1 - r0 : 8192;
+        bucket_sort(NULL, r0, cn, h_order + r0);
+        cudaEvent_t ev[3];
+        for (int i = 0; i < 3; i++) ev[i] = take_event(ctx);
+        float ms[2] = {0.f, 0.f};
+        unsigned int hv[2] = {0u, 0u};
+        for (int rep = 0; rep < 2; rep++) {                          // the first round warms the sample lists and the caches
+            PG_CUDA(ctx, cudaMemsetAsync(cb.counters, 0, 16, ctx->stream));
+            for (int mode = 0; mode < 2; mode++) {
+                cb.force_part = mode;
+                PG_CUDA(ctx, cudaEventRecord(ev[mode], ctx->stream));
+                PG_TRY(run_pass(h_order + r0, cn, 3, false));
+                PG_CUDA(ctx, cudaEventRecord(ev[mode + 1], ctx->stream));
+                PG_CUDA(ctx, cudaMemcpyAsync(&hv[mode], cb.counters + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            }
+            PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            PG_CUDA(ctx, cudaEventElapsedTime(&ms[0], ev[0], ev[1]));
+            PG_CUDA(ctx, cudaEventElapsedTime(&ms[1], ev[1], ev[2]));
+        }
+        // reads the bounds leave too many open pairs for are redone later by the all-block kernel (finish()); its cost
+        // is not in the timed passes: about 22 ns per read and block (2.05 M reads/s on 20 blocks, 0.28 M on 184)
+        const double redo_ms = 22e-6 * (double)md->ntile64;
+        const double cost0 = ms[0] + redo_ms * (double)hv[0], cost1 = ms[1] + redo_ms * (double)(hv[1] - hv[0]);
+        for (int i = 0; i < 3; i++) ctx->ev_free.push_back(ev[i]);
+        cb.force_part = -1;
+        md->part_bounds = cost1 < cost0;
+        if (getenv("PG_TIMING"))
+            fprintf(stderr, "[pg_classify] bound columns of this model: blocks %.3f ms + %u reads to redo, parts %.3f ms + %u on %lld reads -> %s\n",
+                    ms[0], hv[0], ms[1], hv[1] - hv[0], (long long)cn, md->part_bounds ? "parts" : "blocks");
+        md->bounds_tuned = true;
+        PG_CUDA(ctx, cudaMemsetAsync(cb.counters, 0, 16, ctx->stream));      // the trial's fallback lists are void
+        return PG_OK;
+    }
+
     // enqueue the classification of reads [r0, r1); their word counts must have landed (fetch_counts)
     int range(int64_t r0, int64_t r1, cudaEvent_t counts_ready)
     {
@@ -534,6 +581,7 @@ struct ClassifyJob {
             if (!seen[n]) { seen[n] = 1; need.push_back(n); }
         }
         if (!need.empty()) PG_TRY(ensure_boot_lists(ctx, need, min_boot));
+        PG_TRY(tune_bounds(r0, r1));
         for (int64_t c0 = r0; c0 < r1; c0 += CHUNK) {
             const int64_t cn = r1 - c0 < CHUNK ? r1 - c0 : CHUNK;
             bucket_sort(NULL, c0, cn, h_order + c0);

@@ -79,6 +79,9 @@ struct pg_model {
     // zero in the table -- k_bound8 fills them per read with the part minima of the read's best block
     uint8_t  *d_bm8;            // [65536][bm8_pitch]
     int      bm8_pitch, sib0;
+    // bound the table's 16-position parts instead of its 64-position blocks (k_bound<.., true>)?  Decided once per model
+    // by timing both on the first chunk of reads it classifies (results do not depend on it); mutable for that reason
+    mutable bool part_bounds, bounds_tuned;
     int      ngroup;            // ceil(ntile64 / 31): slot 31 of a bm row is spare (k_bound, plan 3)
     int      ngroup_h;          // ceil(2*ntile64 / 32)
     double   vmax;              // max |table entry| over real genera (fp32 error bound)

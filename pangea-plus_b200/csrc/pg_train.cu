@@ -342,6 +342,7 @@ extern "C" int pg_model_set_lineage(pg_model *md, const int32_t *anc_host, int d
 
 extern "C" int pg_model_genera(const pg_model *md) { return md ? md->G : 0; }
 extern "C" int pg_model_certifiable(const pg_model *md) { return md && md->q_ok ? 1 : 0; }
+extern "C" int pg_model_bound_columns(const pg_model *md) { return !md || !md->bounds_tuned ? -1 : (md->part_bounds ? 1 : 0); }
 extern "C" int64_t pg_model_sequences(const pg_model *md) { return md ? md->N : 0; }
 
 extern "C" int pg_model_buffers(pg_model *md, void **dev_ptrs, size_t *nbytes, int max, int *n)

@@ -129,6 +129,7 @@ def load_library() -> C.CDLL:
     lib.pg_model_set_lineage.argtypes = [vp, vp, C.c_int]
     lib.pg_model_genera.argtypes = [vp]
     lib.pg_model_certifiable.argtypes = [vp]
+    lib.pg_model_bound_columns.argtypes = [vp]
     lib.pg_classify_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.pg_classify_stats2.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.pg_model_sequences.restype = i64
@@ -213,6 +214,11 @@ class Model:
     @property
     def certifiable(self) -> bool:
         return bool(self.ctx.lib.pg_model_certifiable(self.h))
+
+    @property
+    def bound_columns(self) -> int:
+        """0 = block columns, 1 = part columns, -1 = not tuned yet (see pg_model_bound_columns)"""
+        return int(self.ctx.lib.pg_model_bound_columns(self.h))
 
     def set_lineage(self, anc: np.ndarray) -> None:
         anc = np.ascontiguousarray(anc, dtype=np.int32)

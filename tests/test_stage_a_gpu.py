@@ -445,7 +445,7 @@ def test_config3_rdp_scale_genera(ctx):
     # the 16-bit bounds must both return the strict kernels' records, and a sample must match the oracle
     data, off, src = synth.synth_reads(0x3000002, tr, 3000, paired=True, gap=40)
     a, ba = ctx.classify(gm, data, off, mode=0, want_boot=True)
-    for kw in (dict(), dict(bound_level=1), dict(bound_level=2, light_max=40)):
+    for kw in (dict(), dict(bound_level=1), dict(bound_level=2, light_max=40), dict(bound_level=3)):
         b, bb = ctx.classify(gm, data, off, mode=1, want_boot=True, **kw)
         st = ctx.classify_stats()
         assert a.tobytes() == b.tobytes() and np.array_equal(ba, bb), kw
@@ -542,7 +542,7 @@ def test_certified_equals_strict_on_random_models(ctx, seed, genera, seqs, lengt
     data, off = pack_sequences(reads)
     want, wb = ctx.classify(gm, data, off, mode=0, want_boot=True)
     for kw in (dict(), dict(cert_plan=1), dict(cert_plan=2), dict(light_max=5), dict(bound_level=1), dict(bound_level=2),
-               dict(bound_level=2, light_max=5)):
+               dict(bound_level=2, light_max=5), dict(bound_level=3), dict(bound_level=3, light_max=5)):
         got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True, **kw)
         assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb), kw
     om = ora.Model(tr["data"], tr["off"], tr["genus"], tr["G"])
