@@ -138,6 +138,17 @@ int pg_model_save(const pg_model *m, const char *path, const void *blob, int64_t
 int pg_model_load(pg_ctx *ctx, const char *path, pg_model **out, void **blob, int64_t *blob_len);
 void pg_free(void *p);
 
+/* A model given as TABLES instead of counts -- the form RDP's own trainset files hold (upstream
+ * files logWordPrior.txt, wordConditionalProbIndexArr.txt, genus_wordConditionalProbList.txt and the leaveCount
+ * attributes of bergeyTrainingTree.xml, loaded through rRNAClassifier.properties; call site README.md:119 `-t`):
+ * logPrior[65536], leave_count[G] (the genus nodes' leaveCount; logLeave = ln(leaveCount + 1) is derived on the device by
+ * the expression training uses), and the listed cells in word-major order -- word w owns entries
+ * idx[w] .. idx[w+1] (idx has 65537 entries), entry e is logp_of_entry[e] for genus genus_of_entry[e].  Every cell
+ * that is not listed is fp32(logPrior[w] - logLeave[g]) (row A4).  Such a model classifies like any other; it has no
+ * counts, so pg_model_save / pg_model_commit / pg_model_counts refuse it.  Host arrays in. */
+int pg_model_from_tables(pg_ctx *ctx, int G, const float *logPrior, const int32_t *leave_count, const int64_t *idx,
+                         const int32_t *genus_of_entry, const float *logp_of_entry, pg_model **out);
+
 /* Multi-GPU replication: the device buffers that define a model, for an
  * external broadcast (torch.distributed / ncclBroadcast).  A receiving rank
  * creates an empty model of the same G, broadcasts into its buffers, then

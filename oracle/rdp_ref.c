@@ -202,14 +202,16 @@ const float *rdp_model_logLeave(const rdp_model *md) { return md->logLeave; }
 const float *rdp_model_logP(const rdp_model *md)     { return md->logP; }
 
 /* ------------------------------------------------------------------ A3 */
+/* upstream TrainingInfo.isSeqReversed: one float accumulator over wordPairPriorDiffArr[w] = logWordPrior[w] -
+ * logWordPrior[reverse complement of w], in word order; the query is reversed iff the sum is negative. */
 int rdp_is_reversed(const rdp_model *md, const int32_t *words, int n)
 {
-    float fwd = 0.0f, rev = 0.0f;
+    float prior = 0.0f;
     for (int i = 0; i < n; i++) {
-        fwd += md->logPrior[words[i]];
-        rev += md->logPrior[rdp_revcomp_word(words[i])];
+        const float diff = md->logPrior[words[i]] - md->logPrior[rdp_revcomp_word(words[i])];
+        prior += diff;
     }
-    return rev > fwd;
+    return prior < 0.0f;
 }
 
 static char comp_base(char c)

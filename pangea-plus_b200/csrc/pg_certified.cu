@@ -67,8 +67,20 @@ __global__ void k_rowmax(const float *__restrict__ table, int G, int ntile, floa
     }
 }
 
-// one thread per (tile64, word, position-in-tile): exact in double (difference of two
-// fp32 values, power-of-two scale), rounded DOWN.  perm[] maps the table position to the genus.
+// one thread per (tile64, word, position-in-tile): q = floor((rowmax - x) * 128), EXACTLY.  Both operands are fp32
+// values of magnitude 0 or in [2^-24, 2^16): such a value is an integer multiple of 2^-47 below 2^63 * 2^-47, so
+// v * 2^47 is an exact int64, the difference of two of them is exact, and a right shift by 40 is the floor of the
+// difference in units of 1/128.  (The double subtraction this replaces is exact only while the binary exponents of the
+// two values differ by less than 29: a word held by nearly every one of ~3 M training sequences has a row maximum of
+// -2^-24 next to cells of -16.)  A table value outside that range (never produced by the training formulas) sets the
+// out-of-range flag, which switches certified mode off for the model.
+__device__ __forceinline__ bool pg_fixed47(float v, long long *out)
+{
+    const float a = fabsf(v);
+    if (!(a == 0.f || (a >= 5.9604644775390625e-08f && a < 65536.f))) return false;
+    *out = (long long)((double)v * 140737488355328.0);         // 2^47: exact, |result| < 2^63
+    return true;
+}
 __global__ void k_quantise(const float *__restrict__ table, const float *__restrict__ rowmax,
                            const int32_t *__restrict__ perm, int G, size_t total, uint16_t *__restrict__ q,
                            unsigned int *__restrict__ qmax)
@@ -82,9 +94,12 @@ __global__ void k_quantise(const float *__restrict__ table, const float *__restr
     unsigned int v = PG_Q_MAX;
     if (g < G) {
         const float x = table[((size_t)(g >> 5) * PG_NWORDS + w) * PG_GENUS_TILE + (g & 31)];
-        const double d = ((double)rowmax[w] - (double)x) * PG_Q_SCALE;
-        const double f = floor(d);
-        unsigned int u = f >= 4.0e9 ? 0xFFFFFFFFu : (unsigned int)f;
+        long long fr, fx;
+        unsigned int u = 0xFFFFFFFFu;                            // out of range: reported through qmax
+        if (pg_fixed47(rowmax[w], &fr) && pg_fixed47(x, &fx)) {
+            const long long d = (fr - fx) >> 40;                 // >= 0: rowmax is the row's maximum
+            u = d > 0xFFFFFFFELL ? 0xFFFFFFFEu : (unsigned int)d;
+        }
         atomicMax(qmax, u);
         v = u > PG_Q_MAX ? PG_Q_MAX : u;
     }

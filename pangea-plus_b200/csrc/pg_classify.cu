@@ -197,6 +197,30 @@ k_vote(const unsigned long long *__restrict__ best, int64_t nreads, int64_t slot
     if (lane >= 8 && lane < 12) raw[4 + lane] = 0u;             // _pad1
 }
 
+// ------------------------------------------------------------------ reads of a range in order of word count
+//
+// The launches of a range are sized per bucket of word counts, and reads of equal length should sit next to each other
+// (they share their sample lists).  The order array is a counting sort by n, done on the device: a histogram of the
+// range's word counts goes to the host (28 KB, fetched one range ahead -- the host needs it anyway to size the
+// launches and to know which sample lists to build), the start of every n comes back, and one pass scatters the read
+// indices.  The host never touches per-read data in the steady state.
+#define PG_HB (PG_MAX_WORDS + 2)                     // bins 0 .. PG_MAX_WORDS, and one for longer reads
+static __global__ void k_words_hist(const int32_t *__restrict__ nwords, int64_t cnt, int32_t *__restrict__ hist)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const int n = nwords[i];
+    atomicAdd(hist + (n > PG_MAX_WORDS ? PG_MAX_WORDS + 1 : n), 1);
+}
+static __global__ void k_words_scatter(const int32_t *__restrict__ nwords, int64_t cnt, int64_t first, const int32_t *__restrict__ start,
+                                       int32_t *__restrict__ cursor, int32_t *__restrict__ order)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const int n = nwords[i];
+    order[start[n] + atomicAdd(cursor + n, 1)] = (int32_t)(first + i);
+}
+
 // ------------------------------------------------------------------ host orchestration
 
 // block = 32 (full-sum warp) + groups*LPR: 20 groups x 5 replicates, 52 x 2, 100 x 1.
@@ -337,6 +361,10 @@ struct ClassifyJob {
     PgCertBufs cb;
     int32_t *h_n, *h_order;
     int64_t *h_off;
+    int32_t *h_hist;                             // [2][PG_HB] pinned: word-count histograms of the range in flight and the next
+    int32_t *d_hist, *d_start, *d_cursor;        // [2][PG_HB], [PG_HB], [PG_HB]
+    int64_t nfetch, nrange;
+    std::vector<int32_t> hstart;
     std::vector<char> seen;
     std::vector<int32_t> redone;                 // reads whose records were rewritten by finish()
     int64_t bcount[16], bstart[16], bmaxn[16];
@@ -367,10 +395,17 @@ struct ClassifyJob {
         CHUNK = !certified ? ((int64_t)1 << 20) : ((int64_t)1 << (chunk_override ? chunk_override : (cert_version == 1 ? 14 : 16)));
         cmax = count < CHUNK ? count : CHUNK;
         if (cmax < 1) cmax = 1;
-        PG_TRY(pg_pinned(ctx, (size_t)count * 16 + 128));
+        PG_TRY(pg_pinned(ctx, (size_t)count * 16 + 128 + 2 * PG_HB * 4));
         h_n = (int32_t *)ctx->h_pin;
         h_order = h_n + count;
         h_off = (int64_t *)(h_order + count + 2);        // rebased read offsets of pg_classify()'s uploads
+        h_hist = (int32_t *)(h_off + count + 2);
+        PG_TRY(pg_scratch(ctx, &ctx->s_hist, (size_t)4 * PG_HB * 4));
+        d_hist = (int32_t *)ctx->s_hist.p;
+        d_start = d_hist + 2 * PG_HB;
+        d_cursor = d_start + PG_HB;
+        nfetch = nrange = 0;
+        hstart.assign(PG_HB, 0);
         seen.assign(PG_MAX_WORDS + 1, 0);
         redone.clear();
         PG_TRY(pg_scratch(ctx, &ctx->s_best, (size_t)cmax * nkeys * 8));
@@ -411,6 +446,13 @@ struct ClassifyJob {
     // word counts of reads [r0, r1) to the host, asynchronously; *ev fires when they have landed
     int fetch_counts(int64_t r0, int64_t r1, cudaEvent_t *ev)
     {
+        int32_t *dh = d_hist + (nfetch & 1) * PG_HB, *hh = h_hist + (nfetch & 1) * PG_HB;
+        nfetch++;
+        PG_CUDA(ctx, cudaMemsetAsync(dh, 0, PG_HB * 4, ctx->stream));
+        k_words_hist<<<(unsigned)((r1 - r0 + 255) / 256), 256, 0, ctx->stream>>>(d_nwords + r0, r1 - r0, dh);
+        PG_LAUNCHED(ctx);
+        PG_CUDA(ctx, cudaMemcpyAsync(hh, dh, PG_HB * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        // the per-read counts follow for the fallback passes of finish(); nobody waits for them in the steady state
         PG_CUDA(ctx, cudaMemcpyAsync(h_n + r0, d_nwords + r0, (size_t)(r1 - r0) * 4, cudaMemcpyDeviceToHost, ctx->stream));
         *ev = take_event(ctx);
         PG_CUDA(ctx, cudaEventRecord(*ev, ctx->stream));
@@ -487,7 +529,8 @@ struct ClassifyJob {
     // near-tie lists, strict keys, guesses) is indexed by slot.
     int run_pass(const int32_t *h_list, int64_t cn, int plan, bool timed)
     {
-        PG_CUDA(ctx, cudaMemcpyAsync(d_order, h_list, (size_t)cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (h_list)                                         // NULL: the order array was built on the device (k_words_scatter)
+            PG_CUDA(ctx, cudaMemcpyAsync(d_order, h_list, (size_t)cn * 4, cudaMemcpyHostToDevice, ctx->stream));
         bool need_best = plan == 0 || !certified;           // strict keys: also for buckets the certified kernels do not take
         for (int b = 0; b < kNumBuckets; b++)
             if (bcount[b] && kBuckets[b].lpr != 8) need_best = true;
@@ -534,8 +577,8 @@ struct ClassifyJob {
     {
         if (md->bounds_tuned || !certified || cert_version != 3 || cb.bound_level != 0 || md->ngroup < 2) return PG_OK;
         if (r0 != 0 || r1 - r0 < 2048) return PG_OK;                 // counters must still be zero; too few reads say nothing
-        const int64_t cn = r1 - r0 < 8192 ? r1 - r0 : 8192;
-        bucket_sort(NULL, r0, cn, h_order + r0);
+        // the range's order array and buckets are in place (range()): the trial is the first range of the batch
+        const int64_t cn = r1 - r0;
         cudaEvent_t ev[3];
         for (int i = 0; i < 3; i++) ev[i] = take_event(ctx);
         float ms[2] = {0.f, 0.f};
@@ -545,7 +588,7 @@ struct ClassifyJob {
             for (int mode = 0; mode < 2; mode++) {
                 cb.force_part = mode;
                 PG_CUDA(ctx, cudaEventRecord(ev[mode], ctx->stream));
-                PG_TRY(run_pass(h_order + r0, cn, 3, false));
+                PG_TRY(run_pass(NULL, cn, 3, false));
                 PG_CUDA(ctx, cudaEventRecord(ev[mode + 1], ctx->stream));
                 PG_CUDA(ctx, cudaMemcpyAsync(&hv[mode], cb.counters + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
             }
@@ -573,21 +616,39 @@ struct ClassifyJob {
     {
         PG_CUDA(ctx, cudaEventSynchronize(counts_ready));
         ctx->ev_free.push_back(counts_ready);
+        const int32_t *hist = h_hist + (nrange & 1) * PG_HB;
+        nrange++;
+        const int64_t cn = r1 - r0;
+        if (cn > CHUNK) return pg_fail(ctx, PG_EINVAL, "internal: a range of %lld reads exceeds the chunk", (long long)cn);
+        if (hist[PG_MAX_WORDS + 1] > 0)
+            return pg_fail(ctx, PG_ERANGE, "%d read(s) of the batch have more than %d good words, the limit of this build", hist[PG_MAX_WORDS + 1],
+                           PG_MAX_WORDS);
+        // from the histogram: the sample lists still to build, the start of every n in the order array, the buckets
         std::vector<int> need;
-        for (int64_t i = r0; i < r1; i++) {
-            const int n = h_n[i];
-            if (n > PG_MAX_WORDS)
-                return pg_fail(ctx, PG_ERANGE, "read %lld has %d good words; the limit is %d", (long long)i, n, PG_MAX_WORDS);
-            if (!seen[n]) { seen[n] = 1; need.push_back(n); }
+        for (int b = 0; b < 16; b++) bcount[b] = bstart[b] = bmaxn[b] = 0;
+        {
+            int b = 0;
+            int32_t acc = 0;
+            for (int n = 0; n <= PG_MAX_WORDS; n++) {
+                const int32_t c = hist[n];
+                hstart[(size_t)n] = acc;
+                if (!c) continue;
+                if (!seen[n]) { seen[n] = 1; need.push_back(n); }
+                while (kBuckets[b].nmax < n) b++;
+                if (!bcount[b]) bstart[b] = acc;
+                bcount[b] += c;
+                bmaxn[b] = n;
+                acc += c;
+            }
         }
         if (!need.empty()) PG_TRY(ensure_boot_lists(ctx, need, min_boot));
+        // pageable source: staged before the call returns, so hstart may be rewritten for the next range
+        PG_CUDA(ctx, cudaMemcpyAsync(d_start, hstart.data(), PG_HB * 4, cudaMemcpyHostToDevice, ctx->stream));
+        PG_CUDA(ctx, cudaMemsetAsync(d_cursor, 0, PG_HB * 4, ctx->stream));
+        k_words_scatter<<<(unsigned)((cn + 255) / 256), 256, 0, ctx->stream>>>(d_nwords + r0, cn, r0, d_start, d_cursor, d_order);
+        PG_LAUNCHED(ctx);
         PG_TRY(tune_bounds(r0, r1));
-        for (int64_t c0 = r0; c0 < r1; c0 += CHUNK) {
-            const int64_t cn = r1 - c0 < CHUNK ? r1 - c0 : CHUNK;
-            bucket_sort(NULL, c0, cn, h_order + c0);
-            PG_TRY(run_pass(h_order + c0, cn, certified ? cert_version : 0, true));
-        }
-        return PG_OK;
+        return run_pass(NULL, cn, certified ? cert_version : 0, true);
     }
 
     // Deferred work, read once for the whole batch:

@@ -81,49 +81,77 @@ __global__ void k_rdp_prepare(char *__restrict__ rdp, const int64_t *__restrict_
     ntriples[r] = nt;
 }
 
-__global__ void k_hit_matches(const char *__restrict__ lin, const int64_t *__restrict__ lin_off, int64_t nhits,
-                              const int32_t *__restrict__ read_of_hit, const char *__restrict__ rdp,
-                              const int64_t *__restrict__ rdp_off, const Triple *__restrict__ triples,
-                              const int32_t *__restrict__ ntriples, int32_t *__restrict__ rankmatches,
-                              int32_t *__restrict__ blastcount, int *__restrict__ overflow)
+// One WARP per hit.  The lineage field is read once, 32 bytes per step, coalesced; separators become a ballot mask,
+// token starts and ends fall out of the mask and its shift by one (carried across steps), and their byte offsets go
+// to two small per-warp arrays in shared memory.  The (BLAST pair, RDP triple) comparisons are then spread over the
+// lanes.  (The first version gave every hit to one thread: two byte-by-byte passes over an uncoalesced line and 512
+// bytes of local arrays per thread.)
+#define PG_HM_WARPS 8
+__global__ void __launch_bounds__(32 * PG_HM_WARPS)
+k_hit_matches(const char *__restrict__ lin, const int64_t *__restrict__ lin_off, int64_t nhits,
+              const int32_t *__restrict__ read_of_hit, const char *__restrict__ rdp,
+              const int64_t *__restrict__ rdp_off, const Triple *__restrict__ triples,
+              const int32_t *__restrict__ ntriples, int32_t *__restrict__ rankmatches,
+              int32_t *__restrict__ blastcount, int *__restrict__ overflow)
 {
-    const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ short s_toff[PG_HM_WARPS][PG_MAX_TOKENS], s_tend[PG_HM_WARPS][PG_MAX_TOKENS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t h = (int64_t)blockIdx.x * PG_HM_WARPS + warp;
     if (h >= nhits) return;
     const char *s = lin + lin_off[h];
     const int n = (int)(lin_off[h + 1] - lin_off[h]);
+    short *toff = s_toff[warp], *tend = s_tend[warp];
+    // tokens = maximal runs of bytes that are neither [ ] ; nor whitespace
+    int ntok = 0, nend = 0;
+    unsigned prev_sep = 1u;                                 // "the byte before the line" counts as a separator
+    const unsigned lt = (1u << lane) - 1u;
+    for (int p0 = 0; p0 < n; p0 += 32) {
+        const int p = p0 + lane;
+        const bool sep = p >= n || pg_lin_sep(s[p]);
+        const unsigned sm = __ballot_sync(0xffffffffu, sep);
+        const unsigned before = (sm << 1) | prev_sep;       // bit i: byte p0+i-1 is a separator
+        const unsigned starts = ~sm & before;               // a token starts here
+        const unsigned ends = sm & ~before;                 // the first separator after a token: its end (exclusive)
+        if ((starts >> lane) & 1u) {
+            const int k = ntok + __popc(starts & lt);
+            if (k < PG_MAX_TOKENS) toff[k] = (short)p;
+        }
+        if ((ends >> lane) & 1u && p <= n) {
+            const int k = nend + __popc(ends & lt);
+            if (k < PG_MAX_TOKENS) tend[k] = (short)(p < n ? p : n);
+        }
+        ntok += __popc(starts);
+        nend += __popc(ends);
+        prev_sep = sm >> 31;
+    }
+    if (nend < ntok && lane == 0 && nend < PG_MAX_TOKENS) tend[nend] = (short)n;     // the line ends inside a token
+    if (ntok > PG_MAX_TOKENS && lane == 0) atomicExch(overflow, 1);
+    __syncwarp();
+    const int usable = ntok < PG_MAX_TOKENS ? ntok : PG_MAX_TOKENS;
     const int64_t r = read_of_hit[h];
     const Triple *tr = triples + r * PG_MAX_TRIPLES;
     const int nt = ntriples[r];
     const char *rs = rdp + rdp_off[r];
-    // tokens = maximal runs of bytes that are neither [ ] ; nor whitespace
-    short toff[PG_MAX_TOKENS], tlen[PG_MAX_TOKENS];
-    int ntok = 0, p = 0;
-    while (p < n) {
-        if (pg_lin_sep(s[p])) { p++; continue; }
-        int q = p;
-        while (q < n && !pg_lin_sep(s[q])) q++;
-        if (ntok < PG_MAX_TOKENS) { toff[ntok] = (short)p; tlen[ntok] = (short)(q - p); }
-        else atomicExch(overflow, 1);
-        ntok++;
-        p = q;
-    }
-    const int usable = ntok < PG_MAX_TOKENS ? ntok : PG_MAX_TOKENS;
+    const int npair = (usable + 1) >> 1;
     int matches = 0;
-    for (int a = 0; a < usable; a += 2) {
+    for (int c = lane; c < npair * nt; c += 32) {
+        const int a = 2 * (c / nt), b = c % nt;
+        const int alen = tend[a] - toff[a];
         int idx1 = -1;                                      // position in ("0".."6"), else undef
-        if (tlen[a] == 1 && s[toff[a]] >= '0' && s[toff[a]] <= '6') idx1 = s[toff[a]] - '0';
+        if (alen == 1 && s[toff[a]] >= '0' && s[toff[a]] <= '6') idx1 = s[toff[a]] - '0';
         const bool has_name = a + 1 < usable;
-        const int nl = has_name ? tlen[a + 1] : 0;          // undef compares as ""
+        const int nl = has_name ? tend[a + 1] - toff[a + 1] : 0;     // undef compares as ""
         const char *nm = has_name ? s + toff[a + 1] : s;
-        for (int b = 0; b < nt; b++) {
-            if (tr[b].rank != idx1 || tr[b].len != nl) continue;
-            bool eq = true;
-            for (int k = 0; k < nl; k++) if (nm[k] != rs[tr[b].off + k]) { eq = false; break; }
-            if (eq) matches++;
-        }
+        if (tr[b].rank != idx1 || tr[b].len != nl) continue;
+        bool eq = true;
+        for (int k = 0; k < nl; k++) if (nm[k] != rs[tr[b].off + k]) { eq = false; break; }
+        if (eq) matches++;
     }
-    rankmatches[h] = matches;
-    blastcount[h] = ntok;
+    matches = __reduce_add_sync(0xffffffffu, matches);
+    if (lane == 0) {
+        rankmatches[h] = matches;
+        blastcount[h] = ntok;
+    }
 }
 
 // Perl `$a gt $b` on non-negative integers: compare their decimal text
@@ -216,14 +244,14 @@ extern "C" int pg_consensus(pg_ctx *ctx, const pg_consensus_in *in, int64_t *win
     PG_CUDA(ctx, cudaMemcpyAsync(base + o_roff, in->rdp_off, (size_t)(R + 1) * 8, cudaMemcpyHostToDevice, st));
     if (rb) PG_CUDA(ctx, cudaMemcpyAsync(base + o_rdp, in->rdp_bytes, (size_t)rb, cudaMemcpyHostToDevice, st));
     PG_CUDA(ctx, cudaMemsetAsync(base + o_flag, 0, 4, st));
-    const unsigned rb_blocks = (unsigned)((R + 127) / 128), hb_blocks = (unsigned)((H + 127) / 128);
+    const unsigned rb_blocks = (unsigned)((R + 127) / 128);
     k_rdp_prepare<<<rb_blocks, 128, 0, st>>>(base + o_rdp, (const int64_t *)(base + o_roff), R, (Triple *)(base + o_tr),
                                             (int32_t *)(base + o_ntr), (int *)(base + o_flag));
     PG_LAUNCHED(ctx);
     k_read_of_hit<<<rb_blocks, 128, 0, st>>>((const int64_t *)(base + o_hoff), R, (int32_t *)(base + o_roh));
     PG_LAUNCHED(ctx);
     if (H) {
-        k_hit_matches<<<hb_blocks, 128, 0, st>>>(base + o_lin, (const int64_t *)(base + o_loff), H, (const int32_t *)(base + o_roh),
+        k_hit_matches<<<(unsigned)((H + PG_HM_WARPS - 1) / PG_HM_WARPS), 32 * PG_HM_WARPS, 0, st>>>(base + o_lin, (const int64_t *)(base + o_loff), H, (const int32_t *)(base + o_roh),
                                                 base + o_rdp, (const int64_t *)(base + o_roff), (const Triple *)(base + o_tr),
                                                 (const int32_t *)(base + o_ntr), (int32_t *)(base + o_rm), (int32_t *)(base + o_bc),
                                                 (int *)(base + o_flag));

@@ -42,8 +42,8 @@ struct pg_ctx {
         void  *p;
         size_t cap;
     } s_words, s_nwords, s_flags, s_best, s_order, s_results, s_boot, s_bytes, s_off, s_cand,
-      s_champ, s_ncand, s_candl, s_fb, s_guess, s_items, s_heavy;
-    static const int kNumScratch = 17;
+      s_champ, s_ncand, s_candl, s_fb, s_guess, s_items, s_heavy, s_hist;
+    static const int kNumScratch = 18;
     int64_t st_heavy, st_items;                        // certified v2: reads redone by the all-block kernel, light items
     // pinned host staging
     void  *h_pin;
@@ -60,6 +60,7 @@ struct pg_model {
     unsigned long long *d_N;    // [1]
     float   *d_table;           // [ntile][65536][32]   A4/A6 dense log table, genus-tiled
     float   *d_logPrior;        // [65536]
+    float   *d_pdiff;           // [65536]  logPrior[w] - logPrior[rc(w)]: the orientation test sums these (A3)
     float   *d_Pw;              // [65536]
     float   *d_logLeave;        // [ntile*32]
     int32_t *d_anc;             // [G][depth]
@@ -87,6 +88,7 @@ struct pg_model {
     double   vmax;              // max |table entry| over real genera (fp32 error bound)
     bool     q_ok;              // every deficit fits the 12-bit field: certificates are valid
     bool     committed;
+    bool     tables_only;       // built by pg_model_from_tables: log tables given, no counts behind them
 };
 
 struct pg_reads {
@@ -111,6 +113,7 @@ int  pg_pinned(pg_ctx *ctx, size_t bytes);
 // d_out[0..n) = exclusive scan of d_in, d_out[n] = total; synchronises the stream
 int  pg_device_scan(pg_ctx *ctx, const int64_t *d_in, int64_t n, int64_t *d_out);
 int  pg_pack_launch(pg_ctx *ctx, const char *d_bytes, const int64_t *d_off, int64_t count, uint32_t *d_planes);
+int  pg_prior_diff_launch(pg_ctx *ctx, pg_model *md);        // pg_reads.cu: d_pdiff from d_logPrior
 
 // A copy between host and device ORDERED WITH the context's stream: every kernel of the library runs on ctx->stream,
 // which is created non-blocking, so a plain cudaMemcpy (legacy stream) is ordered with nothing.  Enqueued on

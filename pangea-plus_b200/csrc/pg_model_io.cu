@@ -29,6 +29,7 @@ extern "C" int pg_model_save(const pg_model *md, const char *path, const void *b
 {
     if (!md || !path || blob_len < 0 || (blob_len > 0 && !blob)) return pg_fail(md ? md->ctx : NULL, PG_EINVAL, "pg_model_save: bad arguments");
     pg_ctx *ctx = md->ctx;
+    if (md->tables_only) return pg_fail(ctx, PG_EINVAL, "pg_model_save: this model was built from tables (pg_model_from_tables) and has no counts");
     const int G = md->G;
     std::vector<int32_t> m((size_t)PG_NWORDS * G), nw(PG_NWORDS), M(G);
     int64_t N = 0;
@@ -138,5 +139,97 @@ extern "C" int pg_model_load(pg_ctx *ctx, const char *path, pg_model **out, void
     *out = md;
     if (blob) *blob = b;
     if (blob_len) *blob_len = blen;
+    return PG_OK;
+}
+
+
+// ------------------------------------------------------------------ models given as TABLES (stock RDP trainset files)
+//
+// RDP ships its model as log tables, not counts -- logWordPrior (65 536 floats), the genus
+// leave counts in the taxonomy tree, and a sparse word-major list of (genus, log conditional probability).  The dense
+// table the kernels use is the same thing with the absent cells spelled out: V[w][g] = fp32(logPrior[w] - logLeave[g])
+// (row A4), overwritten by the listed cells.  A model built this way has no counts: it classifies, it cannot be saved
+// as a .pgm or re-trained.
+
+// one thread per table cell: the absent-cell rule
+__global__ void k_table_default(const float *__restrict__ logPrior, const float *__restrict__ logLeave, int G, size_t total,
+                                float *__restrict__ table)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int lane = (int)(idx & 31), w = (int)((idx >> 5) & (PG_NWORDS - 1)), g = (int)(idx >> 21) * 32 + lane;
+    table[idx] = g < G ? __fsub_rn(logPrior[w], logLeave[g]) : __int_as_float(0xff800000);
+}
+
+// one warp per word: the listed cells
+__global__ void k_table_scatter(const int64_t *__restrict__ idx, const int32_t *__restrict__ genus, const float *__restrict__ logp,
+                                float *__restrict__ table)
+{
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= PG_NWORDS) return;
+    for (int64_t p = idx[w] + (threadIdx.x & 31); p < idx[w + 1]; p += 32) {
+        const int g = genus[p];
+        table[((size_t)(g >> 5) * PG_NWORDS + w) * PG_GENUS_TILE + (g & 31)] = logp[p];
+    }
+}
+
+int pg_model_derive_quantised(pg_model *md);   // pg_certified.cu
+
+// logLeave[g] = (float)ln((float)leaveCount + 1): the expression of k_derive_prior (pg_train.cu), so that a model exported
+// from counts and imported again holds the same bits
+__global__ void k_log_leave(const int32_t *__restrict__ M, int Gpad, float *__restrict__ logLeave)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < Gpad) logLeave[i] = (float)log((double)__fadd_rn((float)M[i], 1.0f));
+}
+
+extern "C" int pg_model_from_tables(pg_ctx *ctx, int G, const float *logPrior, const int32_t *leave_count, const int64_t *idx,
+                                    const int32_t *genus_of_entry, const float *logp_of_entry, pg_model **out)
+{
+    if (!ctx || G <= 0 || !logPrior || !leave_count || !idx || !out || (idx[PG_NWORDS] > 0 && (!genus_of_entry || !logp_of_entry)))
+        return pg_fail(ctx, PG_EINVAL, "pg_model_from_tables: bad arguments");
+    const int64_t nnz = idx[PG_NWORDS];
+    if (idx[0] != 0 || nnz < 0 || nnz > (int64_t)PG_NWORDS * G) return pg_fail(ctx, PG_EFORMAT, "pg_model_from_tables: implausible index");
+    for (int w = 0; w < PG_NWORDS; w++)
+        if (idx[w] > idx[w + 1]) return pg_fail(ctx, PG_EFORMAT, "pg_model_from_tables: index not monotone at word %d", w);
+    for (int64_t p = 0; p < nnz; p++)
+        if (genus_of_entry[p] < 0 || genus_of_entry[p] >= G) return pg_fail(ctx, PG_EFORMAT, "pg_model_from_tables: genus index %d out of range", genus_of_entry[p]);
+    PG_CUDA(ctx, cudaSetDevice(ctx->device));
+    pg_model *md = NULL;
+    PG_TRY(pg_model_create(ctx, G, &md));
+    int64_t *d_idx = NULL;
+    int32_t *d_g = NULL;
+    float *d_p = NULL;
+    int rc = PG_OK;
+    cudaError_t e;
+    if ((e = pg_dev_alloc(ctx, (void **)&d_idx, (PG_NWORDS + 1) * 8)) != cudaSuccess ||
+        (e = pg_dev_alloc(ctx, (void **)&d_g, (size_t)(nnz + 1) * 4)) != cudaSuccess ||
+        (e = pg_dev_alloc(ctx, (void **)&d_p, (size_t)(nnz + 1) * 4)) != cudaSuccess ||
+        (e = pg_copy_sync(ctx, d_idx, idx, (PG_NWORDS + 1) * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (nnz && (e = pg_copy_sync(ctx, d_g, genus_of_entry, (size_t)nnz * 4, cudaMemcpyHostToDevice)) != cudaSuccess) ||
+        (nnz && (e = pg_copy_sync(ctx, d_p, logp_of_entry, (size_t)nnz * 4, cudaMemcpyHostToDevice)) != cudaSuccess) ||
+        (e = pg_copy_sync(ctx, md->d_logPrior, logPrior, PG_NWORDS * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = pg_copy_sync(ctx, md->d_M, leave_count, (size_t)G * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+        rc = pg_fail(ctx, PG_ECUDA, "pg_model_from_tables: upload failed: %s", cudaGetErrorString(e));
+    if (rc == PG_OK) {
+        const size_t cells = (size_t)md->ntile * PG_NWORDS * PG_GENUS_TILE;
+        k_log_leave<<<(md->ntile * 32 + 255) / 256, 256, 0, ctx->stream>>>(md->d_M, md->ntile * 32, md->d_logLeave);
+        ctx->launches++;
+        pg_prior_diff_launch(ctx, md);
+        k_table_default<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(md->d_logPrior, md->d_logLeave, G, cells, md->d_table);
+        ctx->launches++;
+        k_table_scatter<<<PG_NWORDS / 8, 256, 0, ctx->stream>>>(d_idx, d_g, d_p, md->d_table);
+        ctx->launches++;
+        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) rc = pg_fail(ctx, PG_ECUDA, "pg_model_from_tables: %s", cudaGetErrorString(e));
+    }
+    pg_dev_free(ctx, d_idx); pg_dev_free(ctx, d_g); pg_dev_free(ctx, d_p);
+    if (rc == PG_OK) {
+        md->N = 0;
+        md->committed = true;
+        md->tables_only = true;
+        rc = pg_model_derive_quantised(md);
+    }
+    if (rc != PG_OK) { pg_model_free(md); return rc; }
+    *out = md;
     return PG_OK;
 }

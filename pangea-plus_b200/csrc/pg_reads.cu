@@ -70,7 +70,7 @@ __device__ __forceinline__ uint32_t pg_spread8(uint32_t x)
 template <bool ASCII>
 __global__ void __launch_bounds__(256)
 k_extract(const uint32_t *__restrict__ planes, const char *__restrict__ bytes, const int64_t *__restrict__ off, int64_t nreads,
-          const float *__restrict__ logPrior, uint16_t *__restrict__ words,
+          const float *__restrict__ priorDiff, uint16_t *__restrict__ words,
           int32_t *__restrict__ nwords, uint8_t *__restrict__ flags /* [2*nreads]: reversed, status */)
 {
     const int lane = threadIdx.x & 31;
@@ -123,31 +123,26 @@ k_extract(const uint32_t *__restrict__ planes, const char *__restrict__ bytes, c
     }
     __syncwarp();
 
-    // ---- A3: fwd = sum logPrior[w_j], rev = sum logPrior[rc(w_j)], fp32, word order.
-    // Every lane carries the same two running sums; values are fetched 32 at a
-    // time and fed through shuffles so the adds stay in sequence order.
-    // Lanes 0-15 carry the forward chain, lanes 16-31 the reverse-complement chain.  Lane hl of a half gathers
-    // the 16 consecutive terms 16*hl .. 16*hl+15 of a 256-word pass; the running sum hops from lane to lane, each
-    // adding its own 16 terms in order: the adds stay one chain in word order for one shuffle per 16 words.
+    // ---- A3 (upstream TrainingInfo.isSeqReversed): prior = sum over the words, in word order, of
+    // priorDiff[w] = logPrior[w] - logPrior[rc(w)] -- ONE fp32 accumulator; the read is reverse-complemented iff
+    // prior < 0.  priorDiff is a per-model table (k_prior_diff).  Lane l gathers the 16 consecutive terms
+    // 16l .. 16l+15 of a 512-word pass; the running sum hops from lane to lane, each adding its own 16 terms in
+    // order: the adds stay one chain in word order for one shuffle per 16 words.
     float acc = 0.0f;
-    const int half = lane & 16, hl = lane & 15;
-    for (int base = 0; base < n; base += 256) {
+    for (int base = 0; base < n; base += 512) {
         float v[16];
-        const int j0 = base + hl * 16;
+        const int j0 = base + lane * 16;
 #pragma unroll
         for (int u = 0; u < 16; u++) {
             const int j = j0 + u;
             v[u] = 0.0f;
-            if (j < n) {
-                const uint32_t wj = w[j];
-                v[u] = __ldg(logPrior + (half ? pg_revcomp_word(wj) : wj));
-            }
+            if (j < n) v[u] = __ldg(priorDiff + w[j]);
         }
         const int cnt = n - j0;
-        const int hops = (n - base + 15) / 16 < 16 ? (n - base + 15) / 16 : 16;
+        const int hops = (n - base + 15) / 16 < 32 ? (n - base + 15) / 16 : 32;
         for (int h = 0; h < hops; h++) {
-            const float in = __shfl_sync(0xffffffffu, acc, half + (h == 0 ? 15 : h - 1));
-            if (hl == h) {
+            const float in = __shfl_sync(0xffffffffu, acc, h == 0 ? 31 : h - 1);
+            if (lane == h) {
                 float x = (h == 0 && base == 0) ? 0.0f : in;
 #pragma unroll
                 for (int u = 0; u < 16; u++)
@@ -155,10 +150,9 @@ k_extract(const uint32_t *__restrict__ planes, const char *__restrict__ bytes, c
                 acc = x;
             }
         }
-        acc = __shfl_sync(0xffffffffu, acc, half + hops - 1);       // every lane of the half holds the pass result
+        acc = __shfl_sync(0xffffffffu, acc, hops - 1);              // every lane holds the pass result (lane 31 for the next pass)
     }
-    const float fwd = __shfl_sync(0xffffffffu, acc, 0), rev = __shfl_sync(0xffffffffu, acc, 16);
-    const bool reversed = rev > fwd;
+    const bool reversed = n > 0 && acc < 0.0f;
     if (reversed) {
         // word list of the reverse-complemented read = reversed list of rc words
         for (int j = lane; j < n / 2; j += 32) {
@@ -173,6 +167,20 @@ k_extract(const uint32_t *__restrict__ planes, const char *__restrict__ bytes, c
         flags[2 * i] = reversed ? 1 : 0;
         flags[2 * i + 1] = 0;
     }
+}
+
+// A3: priorDiff[w] = fp32(logPrior[w] - logPrior[rc(w)]) (upstream wordPairPriorDiffArr), once per model
+__global__ void k_prior_diff(const float *__restrict__ logPrior, float *__restrict__ priorDiff)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < PG_NWORDS) priorDiff[w] = __fsub_rn(logPrior[w], logPrior[pg_revcomp_word(w)]);
+}
+
+int pg_prior_diff_launch(pg_ctx *ctx, pg_model *md)
+{
+    k_prior_diff<<<PG_NWORDS / 256, 256, 0, ctx->stream>>>(md->d_logPrior, md->d_pdiff);
+    PG_LAUNCHED(ctx);
+    return PG_OK;
 }
 
 // ------------------------------------------------------------------ host side
@@ -222,7 +230,7 @@ int pg_extract_launch(pg_ctx *ctx, const pg_model *md, const uint32_t *d_planes,
     if (count == 0) return PG_OK;
     const int wpb = 8;
     k_extract<false><<<(unsigned)((count + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
-        d_planes, NULL, d_off, count, md->d_logPrior, d_words, d_nwords, d_flags);
+        d_planes, NULL, d_off, count, md->d_pdiff, d_words, d_nwords, d_flags);
     PG_LAUNCHED(ctx);
     return PG_OK;
 }
@@ -234,7 +242,7 @@ int pg_extract_ascii_launch(pg_ctx *ctx, const pg_model *md, const char *d_bytes
     if (count == 0) return PG_OK;
     const int wpb = 8;
     k_extract<true><<<(unsigned)((count + wpb - 1) / wpb), wpb * 32, 0, ctx->stream>>>(
-        NULL, d_bytes, d_off, count, md->d_logPrior, d_words, d_nwords, d_flags);
+        NULL, d_bytes, d_off, count, md->d_pdiff, d_words, d_nwords, d_flags);
     PG_LAUNCHED(ctx);
     return PG_OK;
 }

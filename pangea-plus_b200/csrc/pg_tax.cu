@@ -321,6 +321,28 @@ __global__ void k_hit_lineage(const int32_t *__restrict__ leaf, const int32_t *_
     }
 }
 
+// pass 2 with one WARP per hit: the lineage string of the leaf is copied with coalesced byte loads and stores (the
+// thread-per-hit loop above moves every string through 110 scattered single-byte transactions per lane)
+__global__ void __launch_bounds__(256)
+k_hit_lineage_copy(const int32_t *__restrict__ leaf, const int32_t *__restrict__ gi, int64_t n, int64_t nnodes,
+                   const int64_t *__restrict__ linoff, const char *__restrict__ linpool,
+                   const int64_t *__restrict__ outoff, char *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int t = leaf[i];
+    char *dst = out + outoff[i];
+    if (t >= 1 && t <= nnodes) {
+        const int64_t a = linoff[t - 1];
+        const int len = (int)(linoff[t] - a);
+        const char *src = linpool + a;
+        for (int k = lane; k < len; k += 32) dst[k] = src[k];
+    } else if (lane == 0) {
+        pg_unidentified(gi[i], dst);
+    }
+}
+
 // ------------------------------------------------------------------ load
 
 static int slurp(const std::string &path, std::vector<unsigned char> &buf)
@@ -501,7 +523,7 @@ extern "C" int pg_tax_lineage(pg_ctx *ctx, const pg_tax *t, const int32_t *gi_ho
     if (total == 0) return PG_OK;
     PG_TRY(pg_scratch(ctx, &ctx->s_results, (size_t)total + 16));
     char *d_out = (char *)ctx->s_results.p;
-    k_hit_lineage<<<nb, 256, 0, ctx->stream>>>(d_leaf, d_gi, n, t->nnodes, t->d_linoff, t->d_linpool, d_off, NULL, d_out);
+    k_hit_lineage_copy<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(d_leaf, d_gi, n, t->nnodes, t->d_linoff, t->d_linpool, d_off, d_out);
     PG_LAUNCHED(ctx);
     PG_CUDA(ctx, cudaMemcpyAsync(out_bytes, d_out, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream));
     PG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

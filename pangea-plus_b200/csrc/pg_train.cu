@@ -149,6 +149,7 @@ static int model_alloc(pg_ctx *ctx, int G, pg_model **out)
         (e = cudaMalloc(&md->d_M, (size_t)md->ntile * 32 * 4)) != cudaSuccess ||
         (e = cudaMalloc(&md->d_N, 8)) != cudaSuccess ||
         (e = cudaMalloc(&md->d_logPrior, PG_NWORDS * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&md->d_pdiff, PG_NWORDS * 4)) != cudaSuccess ||
         (e = cudaMalloc(&md->d_Pw, PG_NWORDS * 4)) != cudaSuccess ||
         (e = cudaMalloc(&md->d_logLeave, (size_t)md->ntile * 32 * 4)) != cudaSuccess) {
         (void)cudaGetLastError();
@@ -171,7 +172,7 @@ extern "C" void pg_model_free(pg_model *md)
     cudaSetDevice(md->ctx->device);
     cudaStreamSynchronize(md->ctx->stream);
     cudaFree(md->d_m); cudaFree(md->d_table); cudaFree(md->d_nw); cudaFree(md->d_M);
-    cudaFree(md->d_N); cudaFree(md->d_logPrior); cudaFree(md->d_Pw); cudaFree(md->d_logLeave);
+    cudaFree(md->d_N); cudaFree(md->d_logPrior); cudaFree(md->d_pdiff); cudaFree(md->d_Pw); cudaFree(md->d_logLeave);
     cudaFree(md->d_anc); cudaFree(md->d_qtable); cudaFree(md->d_rowmax);
     cudaFree(md->d_perm); cudaFree(md->d_bmtable); cudaFree(md->d_blockmask); cudaFree(md->d_hmtable); cudaFree(md->d_bm8);
     delete md;
@@ -186,12 +187,14 @@ extern "C" int pg_model_commit(pg_model *md)
 {
     if (!md) return PG_EINVAL;
     pg_ctx *ctx = md->ctx;
+    if (md->tables_only) return pg_fail(ctx, PG_EINVAL, "pg_model_commit: this model was built from tables and has no counts to derive them from");
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     int Gpad = md->ntile * 32;
     int n1 = PG_NWORDS > Gpad ? PG_NWORDS : Gpad;
     k_derive_prior<<<(n1 + 255) / 256, 256, 0, ctx->stream>>>(md->d_nw, md->d_M, md->d_N, Gpad, md->d_Pw,
                                                             md->d_logPrior, md->d_logLeave);
     PG_LAUNCHED(ctx);
+    PG_TRY(pg_prior_diff_launch(ctx, md));
     size_t cells = (size_t)md->ntile * PG_NWORDS * PG_GENUS_TILE;
     k_derive_table<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(
         md->d_m, md->d_M, md->d_Pw, md->d_logPrior, md->d_logLeave, md->G, cells, md->d_table);

@@ -20,13 +20,25 @@
  * or, with --genus-token N, the genus is the N-th blank-separated token of the header (the
  * layout of the reference's validation_dataset/rdp_download_*.fa: N = 2) under a flat Root.
  *
+ * Stock RDP trainset files (layouts per SURVEY.md appendix B, recalled from upstream and
+ * UNVERIFIED against a real RDP 2.5 distribution -- no copy of it is reachable from the build environment):
+ *     rdp_classifier --export-rdp <dir> -t model.pgm      writes rRNAClassifier.properties, bergeyTrainingTree.xml,
+ *                                                          logWordPrior.txt, wordConditionalProbIndexArr.txt,
+ *                                                          genus_wordConditionalProbList.txt
+ *     rdp_classifier -q in.fa -o out.txt -t <dir>/rRNAClassifier.properties        classifies from such files
+ * so that a user with Java can run `java -jar rdp_classifier-2.5.jar -t <dir>/rRNAClassifier.properties` on the same
+ * trainset and diff the two outputs -- the one way to pin Stage A to the jar itself.
+ * -g 16srrna|fungallsu picks the default model when -t is absent ($PANGEA_RDP_MODEL_16SRRNA / _FUNGALLSU).
+ *
  * Output formats:
+ *   db       id TAB trainset-no TAB taxid TAB conf, one line per rank of the assignment (UNVERIFIED layout)
  *   allrank  id TAB [-] (TAB name TAB rank TAB conf)*      the jar's default
  *   fixrank  id TAB [-] then domain, phylum, class, order, family, genus triples
  *   pangea   id, five TABs, then the triples below Root -- the layout that
  *            Consensus_BLAST_SOAP_RDP-1.1.pl:126 actually parses
  */
 #include <getopt.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -51,6 +63,8 @@ typedef struct {
     char **name, **rank;
     int    G, maxdepth;
     int   *genus_node;
+    int   *taxid;          /* NULL: a node's taxid is its index (models trained here) */
+    int    trainset_no;
 } taxonomy;
 
 static const char *DEFAULT_RANKS[] = {"rootrank", "domain", "phylum", "class", "order", "family", "genus"};
@@ -217,6 +231,270 @@ static int do_train(pg_ctx *ctx, const char *fasta_path, const char *model_path,
     pg_model_free(md);
     pg_fasta_free(&fa);
     return 0;
+}
+
+/* ------------------------------------------------------------------ stock RDP trainset files (UNVERIFIED layouts) */
+
+static const char *RDP_VERSION = "RDP Naive Bayesian rRNA Classifier Version 2.5, May 2012";
+
+static void xml_escape(FILE *f, const char *s)
+{
+    for (; *s; s++) {
+        if (*s == '&') fputs("&amp;", f);
+        else if (*s == '<') fputs("&lt;", f);
+        else if (*s == '>') fputs("&gt;", f);
+        else if (*s == '"') fputs("&quot;", f);
+        else fputc(*s, f);
+    }
+}
+
+static void xml_unescape(char *s)
+{
+    char *o = s;
+    while (*s) {
+        if (!strncmp(s, "&amp;", 5)) { *o++ = '&'; s += 5; }
+        else if (!strncmp(s, "&lt;", 4)) { *o++ = '<'; s += 4; }
+        else if (!strncmp(s, "&gt;", 4)) { *o++ = '>'; s += 4; }
+        else if (!strncmp(s, "&quot;", 6)) { *o++ = '"'; s += 6; }
+        else if (!strncmp(s, "&apos;", 6)) { *o++ = '\''; s += 6; }
+        else *o++ = *s++;
+    }
+    *o = 0;
+}
+
+/* model.pgm -> the five files of an RDP trainset directory.  Floats are written with nine significant digits, which
+ * is enough to read every fp32 value back exactly. */
+static int export_rdp(pg_ctx *ctx, const pg_model *md, const taxonomy *t, const char *dir)
+{
+    const int G = t->G;
+    float *lp = (float *)malloc(sizeof(float) * 65536), *ll = (float *)malloc(sizeof(float) * (size_t)G);
+    float *logp = (float *)malloc(sizeof(float) * 65536 * (size_t)G);
+    int32_t *m = (int32_t *)malloc(sizeof(int32_t) * 65536 * (size_t)G), *M = (int32_t *)malloc(sizeof(int32_t) * (size_t)G);
+    if (!lp || !ll || !logp || !m || !M) { fprintf(stderr, "rdp_classifier: out of memory\n"); return 1; }
+    if (pg_model_tables(md, lp, ll, logp) != PG_OK || pg_model_counts(md, m, NULL, M, NULL) != PG_OK) {
+        fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx));
+        return 1;
+    }
+    char path[4096], hdr[256];
+#define RDP_OPEN(name) snprintf(path, sizeof path, "%s/%s", dir, name); f = fopen(path, "w"); \
+    if (!f) { fprintf(stderr, "rdp_classifier: cannot write %s\n", path); return 1; }
+#define RDP_HDR(file) snprintf(hdr, sizeof hdr, "<trainsetNo>%d</trainsetNo><version>pangea_b200</version><modversion>1</modversion><file>%s</file>", t->trainset_no, file)
+    FILE *f;
+    RDP_OPEN("rRNAClassifier.properties")
+    fprintf(f, "# written by pangea_b200 rdp_classifier --export-rdp (layouts per SURVEY.md appendix B, UNVERIFIED)\n"
+               "bergeyTree=bergeyTrainingTree.xml\nprobabilityList=genus_wordConditionalProbList.txt\n"
+               "probabilityIndex=wordConditionalProbIndexArr.txt\nwordPrior=logWordPrior.txt\nclassifierVersion=%s\n", RDP_VERSION);
+    fclose(f);
+    /* the tree: leaveCount = training sequences under the node */
+    long long *leave = (long long *)calloc((size_t)t->nnodes, sizeof(long long));
+    int *gidx = (int *)malloc(sizeof(int) * (size_t)t->nnodes);
+    for (int k = 0; k < t->nnodes; k++) gidx[k] = -1;
+    for (int g = 0; g < G; g++) {
+        gidx[t->genus_node[g]] = g;
+        for (int n = t->genus_node[g]; n >= 0; n = t->parent[n]) leave[n] += M[g];
+    }
+    RDP_OPEN("bergeyTrainingTree.xml")
+    RDP_HDR("bergeyTrainingTree");
+    fprintf(f, "%s\n", hdr);
+    for (int k = 0; k < t->nnodes; k++) {
+        fputs("<TreeNode name=\"", f);
+        xml_escape(f, t->name[k]);
+        fprintf(f, "\" taxid=\"%d\" rank=\"%s\" parentTaxid=\"%d\" leaveCount=\"%lld\" genusIndex=\"%d\"></TreeNode>\n",
+                t->taxid ? t->taxid[k] : k, t->rank[k], t->parent[k] < 0 ? -1 : (t->taxid ? t->taxid[t->parent[k]] : t->parent[k]),
+                leave[k], gidx[k]);
+    }
+    fclose(f);
+    RDP_OPEN("logWordPrior.txt")
+    RDP_HDR("logWordPrior");
+    fprintf(f, "%s\n", hdr);
+    for (int w = 0; w < 65536; w++) fprintf(f, "%d\t%.9g\n", w, (double)lp[w]);
+    fclose(f);
+    RDP_OPEN("wordConditionalProbIndexArr.txt")
+    RDP_HDR("wordConditionalProbIndexArr");
+    fprintf(f, "%s\n", hdr);
+    long long at = 0;
+    for (int w = 0; w < 65536; w++) {
+        fprintf(f, "%d\t%lld\n", w, at);
+        for (int g = 0; g < G; g++) at += m[(size_t)w * G + g] > 0;
+    }
+    fprintf(f, "%d\t%lld\n", 65536, at);
+    fclose(f);
+    RDP_OPEN("genus_wordConditionalProbList.txt")
+    RDP_HDR("genus_wordConditionalProbList");
+    fprintf(f, "%s\n", hdr);
+    for (int w = 0; w < 65536; w++)
+        for (int g = 0; g < G; g++)
+            if (m[(size_t)w * G + g] > 0) fprintf(f, "%d\t%.9g\n", g, (double)logp[(size_t)w * G + g]);
+    fclose(f);
+#undef RDP_OPEN
+#undef RDP_HDR
+    printf("exported %d genera, %d taxa, %lld conditional probabilities -> %s/rRNAClassifier.properties\n", G, t->nnodes, at, dir);
+    free(lp); free(ll); free(logp); free(m); free(M); free(leave); free(gidx);
+    return 0;
+}
+
+static char *xml_attr(const char *line, const char *key, char *buf, size_t cap)
+{
+    char pat[64];
+    snprintf(pat, sizeof pat, " %s=\"", key);
+    const char *p = strstr(line, pat);
+    if (!p) return NULL;
+    p += strlen(pat);
+    const char *e = strchr(p, '"');
+    if (!e || (size_t)(e - p) >= cap) return NULL;
+    memcpy(buf, p, (size_t)(e - p));
+    buf[e - p] = 0;
+    xml_unescape(buf);
+    return buf;
+}
+
+/* pg_lines keeps the newline bytes in place: make every line a C string */
+static int read_lines_z(const char *path, pg_lines *pl)
+{
+    if (pg_lines_read(path, pl)) return -1;
+    for (int64_t i = 0; i < pl->count; i++) {
+        size_t n = pl->len[i];
+        if (n && pl->line[i][n - 1] == '\r') n--;
+        pl->line[i][n] = 0;
+    }
+    return 0;
+}
+
+/* rRNAClassifier.properties -> model on the device + taxonomy.  Paths in the properties file are relative to it. */
+static int import_rdp(pg_ctx *ctx, const char *props, pg_model **out, taxonomy *t)
+{
+    memset(t, 0, sizeof *t);
+    pg_lines pl;
+    if (read_lines_z(props, &pl)) { fprintf(stderr, "rdp_classifier: cannot read %s\n", props); return 1; }
+    char dir[4096], tree[256] = "", plist[256] = "", pindex[256] = "", prior[256] = "";
+    snprintf(dir, sizeof dir, "%s", props);
+    char *slash = strrchr(dir, '/');
+    if (slash) *slash = 0; else strcpy(dir, ".");
+    for (int64_t i = 0; i < pl.count; i++) {
+        char *l = pl.line[i];
+        while (*l == ' ' || *l == '\t') l++;
+        if (*l == '#' || *l == '!') continue;
+        char *eq = strpbrk(l, "=:");
+        if (!eq) continue;
+        *eq = 0;
+        char *v = eq + 1;
+        while (*v == ' ' || *v == '\t') v++;
+        size_t vl = strlen(v);
+        while (vl && (v[vl - 1] == '\r' || v[vl - 1] == ' ' || v[vl - 1] == '\t')) v[--vl] = 0;
+        size_t kl = strlen(l);
+        while (kl && (l[kl - 1] == ' ' || l[kl - 1] == '\t')) l[--kl] = 0;
+        if (!strcmp(l, "bergeyTree")) snprintf(tree, sizeof tree, "%s", v);
+        else if (!strcmp(l, "probabilityList")) snprintf(plist, sizeof plist, "%s", v);
+        else if (!strcmp(l, "probabilityIndex")) snprintf(pindex, sizeof pindex, "%s", v);
+        else if (!strcmp(l, "wordPrior")) snprintf(prior, sizeof prior, "%s", v);
+    }
+    pg_lines_free(&pl);
+    if (!tree[0] || !plist[0] || !pindex[0] || !prior[0]) {
+        fprintf(stderr, "rdp_classifier: %s lacks one of bergeyTree / probabilityList / probabilityIndex / wordPrior\n", props);
+        return 1;
+    }
+    char path[4400];
+    /* ---- the tree */
+    snprintf(path, sizeof path, "%s/%s", dir, tree);
+    if (read_lines_z(path, &pl)) { fprintf(stderr, "rdp_classifier: cannot read %s\n", path); return 1; }
+    int cap = (int)pl.count + 1, maxg = -1;
+    t->parent = (int *)malloc(sizeof(int) * (size_t)cap);
+    t->depth = (int *)malloc(sizeof(int) * (size_t)cap);
+    t->taxid = (int *)malloc(sizeof(int) * (size_t)cap);
+    t->name = (char **)malloc(sizeof(char *) * (size_t)cap);
+    t->rank = (char **)malloc(sizeof(char *) * (size_t)cap);
+    int *ptax = (int *)malloc(sizeof(int) * (size_t)cap), *gidx = (int *)malloc(sizeof(int) * (size_t)cap);
+    long long *leave = (long long *)malloc(sizeof(long long) * (size_t)cap);
+    for (int64_t i = 0; i < pl.count; i++) {
+        const char *l = pl.line[i];
+        char b[1024];
+        if (i == 0) {
+            const char *q = strstr(l, "<trainsetNo>");
+            if (q) t->trainset_no = atoi(q + 12);
+        }
+        const char *tn = strstr(l, "<TreeNode");
+        if (!tn) continue;
+        const int k = t->nnodes++;
+        t->name[k] = strdup(xml_attr(tn, "name", b, sizeof b) ? b : "");
+        t->taxid[k] = xml_attr(tn, "taxid", b, sizeof b) ? atoi(b) : k;
+        t->rank[k] = strdup(xml_attr(tn, "rank", b, sizeof b) ? b : "");
+        ptax[k] = xml_attr(tn, "parentTaxid", b, sizeof b) ? atoi(b) : -1;
+        leave[k] = xml_attr(tn, "leaveCount", b, sizeof b) ? atoll(b) : 0;
+        gidx[k] = xml_attr(tn, "genusIndex", b, sizeof b) ? atoi(b) : -1;
+        if (gidx[k] > maxg) maxg = gidx[k];
+    }
+    pg_lines_free(&pl);
+    if (t->nnodes == 0 || maxg < 0) { fprintf(stderr, "rdp_classifier: %s holds no genus node\n", path); return 1; }
+    for (int k = 0; k < t->nnodes; k++) {                   /* parent taxid -> node index (the root's parent is absent) */
+        t->parent[k] = -1;
+        if (ptax[k] != t->taxid[k])
+            for (int j = 0; j < t->nnodes; j++)
+                if (t->taxid[j] == ptax[k] && j != k) { t->parent[k] = j; break; }
+    }
+    for (int k = 0; k < t->nnodes; k++) {
+        int d = 0;
+        for (int n = t->parent[k]; n >= 0 && d <= t->nnodes; n = t->parent[n]) d++;
+        t->depth[k] = d;
+        if (d + 1 > t->maxdepth) t->maxdepth = d + 1;
+    }
+    if (t->maxdepth > PG_MAX_DEPTH) { fprintf(stderr, "rdp_classifier: the taxonomy of %s is deeper than %d\n", path, PG_MAX_DEPTH); return 1; }
+    const int G = t->G = maxg + 1;
+    t->genus_node = (int *)malloc(sizeof(int) * (size_t)G);
+    int32_t *ll = (int32_t *)malloc(sizeof(int32_t) * (size_t)G);
+    for (int g = 0; g < G; g++) t->genus_node[g] = -1;
+    for (int k = 0; k < t->nnodes; k++)
+        if (gidx[k] >= 0) { t->genus_node[gidx[k]] = k; ll[gidx[k]] = (int32_t)leave[k]; }
+    for (int g = 0; g < G; g++)
+        if (t->genus_node[g] < 0) { fprintf(stderr, "rdp_classifier: genusIndex %d is missing from %s\n", g, path); return 1; }
+    /* ---- word priors */
+    float *lp = (float *)malloc(sizeof(float) * 65536);
+    for (int w = 0; w < 65536; w++) lp[w] = 0.f;
+    snprintf(path, sizeof path, "%s/%s", dir, prior);
+    if (read_lines_z(path, &pl)) { fprintf(stderr, "rdp_classifier: cannot read %s\n", path); return 1; }
+    for (int64_t i = 1; i < pl.count; i++) {
+        char *e;
+        long w = strtol(pl.line[i], &e, 10);
+        if (e == pl.line[i] || w < 0 || w > 65535) continue;
+        lp[w] = strtof(e, NULL);
+    }
+    pg_lines_free(&pl);
+    /* ---- index and list */
+    int64_t *idx = (int64_t *)calloc(65537, sizeof(int64_t));
+    snprintf(path, sizeof path, "%s/%s", dir, pindex);
+    if (read_lines_z(path, &pl)) { fprintf(stderr, "rdp_classifier: cannot read %s\n", path); return 1; }
+    int seen_end = 0;
+    for (int64_t i = 1; i < pl.count; i++) {
+        char *e;
+        long w = strtol(pl.line[i], &e, 10);
+        if (e == pl.line[i] || w < 0 || w > 65536) continue;
+        idx[w] = strtoll(e, NULL, 10);
+        if (w == 65536) seen_end = 1;
+    }
+    pg_lines_free(&pl);
+    snprintf(path, sizeof path, "%s/%s", dir, plist);
+    if (read_lines_z(path, &pl)) { fprintf(stderr, "rdp_classifier: cannot read %s\n", path); return 1; }
+    const int64_t nnz = pl.count > 0 ? pl.count - 1 : 0;
+    if (!seen_end) idx[65536] = nnz;
+    int32_t *eg = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz + 1));
+    float *ep = (float *)malloc(sizeof(float) * (size_t)(nnz + 1));
+    for (int64_t i = 0; i < nnz; i++) {
+        char *e;
+        eg[i] = (int32_t)strtol(pl.line[i + 1], &e, 10);
+        ep[i] = strtof(e, NULL);
+    }
+    pg_lines_free(&pl);
+    if (idx[65536] != nnz) { fprintf(stderr, "rdp_classifier: %s lists %lld entries, the index says %lld\n", path, (long long)nnz, (long long)idx[65536]); return 1; }
+    if (pg_model_from_tables(ctx, G, lp, ll, idx, eg, ep, out) != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx)); return 1; }
+    int32_t *anc = tax_lineage_table(t);
+    if (pg_model_set_lineage(*out, anc, t->maxdepth) != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(ctx)); return 1; }
+    free(anc); free(ptax); free(gidx); free(leave); free(ll); free(lp); free(idx); free(eg); free(ep);
+    return 0;
+}
+
+static int is_properties(const char *path)
+{
+    const size_t n = strlen(path);
+    return n > 11 && strcmp(path + n - 11, ".properties") == 0;
 }
 
 /* ------------------------------------------------------------------ pipeline plumbing */
@@ -469,6 +747,15 @@ static void format_piece(pipeline_t *pl, piece_t *p)
             path[np++] = n;
             need += pl->tpiece_len[n] + 16;               /* "\tname\trank\t" + confidence; fixrank names a longer rank at most */
         }
+        if (ifmt == 3) {                                  /* db: one line per rank of the assignment */
+            for (int j = np - 1; j >= 0; j--) {
+                grow(&p->out, &p->out_cap, on + idlen + 64);
+                OUT_STR(rid, idlen);
+                on += (size_t)sprintf(p->out + on, "\t%d\t%d\t%s\n", t->trainset_no, t->taxid ? t->taxid[path[j]] : path[j],
+                                      pl->conf_tab[r->votes[t->depth[path[j]]]]);
+            }
+            continue;
+        }
         grow(&p->out, &p->out_cap, on + need);
         OUT_STR(rid, idlen);
         if (ifmt == 2) OUT_STR("\t\t\t\t", 4);           /* with the piece's own leading TAB: five */
@@ -600,8 +887,9 @@ int main(int argc, char **argv)
                                  {"strict", no_argument, 0, 'S'}, {"min-boot-words", required_argument, 0, 'M'},
                                  {"gpus", required_argument, 0, 'N'}, {"devices", required_argument, 0, 'D'},
                                  {"contexts-per-gpu", required_argument, 0, 'C'}, {"format-threads", required_argument, 0, 'F'},
-                                 {0, 0, 0, 0}};
-    const char *q = NULL, *o = NULL, *model = NULL, *fmt = "allrank", *train = NULL, *ranks = NULL, *devlist = NULL;
+                                 {"export-rdp", required_argument, 0, 'E'}, {0, 0, 0, 0}};
+    const char *q = NULL, *o = NULL, *model = NULL, *fmt = "allrank", *train = NULL, *ranks = NULL, *devlist = NULL, *export_dir = NULL;
+    const char *gene = "16srrna";
     int device = 0, genus_token = 0, strict = 0, min_boot = 0, ngpu = 1, per_gpu = 2, nformat = 0;
     for (;;) {
         int c = getopt_long(argc, argv, "q:o:t:f:g:", lo, NULL);
@@ -611,7 +899,8 @@ int main(int argc, char **argv)
         case 'o': o = optarg; break;
         case 't': model = optarg; break;
         case 'f': fmt = optarg; break;
-        case 'g': break;                                  /* -g 16srrna|fungallsu: one gene per model file here */
+        case 'g': gene = optarg; break;                   /* -g 16srrna|fungallsu: which default model when -t is absent */
+        case 'E': export_dir = optarg; break;
         case 'T': train = optarg; break;
         case 'R': ranks = optarg; break;
         case 'K': genus_token = atoi(optarg); break;
@@ -625,14 +914,19 @@ int main(int argc, char **argv)
         default: break;
         }
     }
-    if (!model) model = getenv("PANGEA_RDP_MODEL");
-    if (!model) model = "rdp_model.pgm";
-    if (!train && (!q || !o)) {
-        printf("Usage: rdp_classifier -q <query.fa> -o <out.txt> [-t model.pgm] [-f allrank|fixrank|pangea] [--gpus N] [--devices a,b,...]\n"
-               "       rdp_classifier --train <training.fa> -t <model.pgm> [--ranks r0,r1,...] [--genus-token N]\n");
+    if (strcmp(gene, "16srrna") != 0 && strcmp(gene, "fungallsu") != 0) { fprintf(stderr, "rdp_classifier: -g takes 16srrna or fungallsu\n"); return 1; }
+    const int lsu = strcmp(gene, "fungallsu") == 0;
+    if (!model) model = getenv(lsu ? "PANGEA_RDP_MODEL_FUNGALLSU" : "PANGEA_RDP_MODEL_16SRRNA");
+    if (!model && !lsu) model = getenv("PANGEA_RDP_MODEL");
+    if (!model) model = lsu ? "rdp_model_fungallsu.pgm" : "rdp_model.pgm";
+    if (!train && !export_dir && (!q || !o)) {
+        printf("Usage: rdp_classifier -q <query.fa> -o <out.txt> [-t model.pgm | -t rRNAClassifier.properties] [-g 16srrna|fungallsu]\n"
+               "                      [-f allrank|fixrank|db|pangea] [--gpus N] [--devices a,b,...]\n"
+               "       rdp_classifier --train <training.fa> -t <model.pgm> [--ranks r0,r1,...] [--genus-token N]\n"
+               "       rdp_classifier --export-rdp <dir> -t <model.pgm>     (stock RDP trainset files; layouts UNVERIFIED against RDP 2.5)\n");
         return 0;
     }
-    int ifmt = strcmp(fmt, "allrank") == 0 ? 0 : strcmp(fmt, "fixrank") == 0 ? 1 : strcmp(fmt, "pangea") == 0 ? 2 : -1;
+    int ifmt = strcmp(fmt, "allrank") == 0 ? 0 : strcmp(fmt, "fixrank") == 0 ? 1 : strcmp(fmt, "pangea") == 0 ? 2 : strcmp(fmt, "db") == 0 ? 3 : -1;
     if (ifmt < 0) { fprintf(stderr, "rdp_classifier: unknown format %s\n", fmt); return 1; }
     if (ngpu < 1 || ngpu > 16 || per_gpu < 1 || per_gpu > 4) { fprintf(stderr, "rdp_classifier: --gpus 1..16, --contexts-per-gpu 1..4\n"); return 1; }
     int dev[16];
@@ -647,7 +941,7 @@ int main(int argc, char **argv)
     const int timing = getenv("PG_TIMING") != NULL;
     double t0 = now_s(), t1, t_begin = t0;
 #define LAP(what) do { if (timing) { t1 = now_s(); fprintf(stderr, "[timing] %-22s %.3f s\n", what, t1 - t0); t0 = t1; } } while (0)
-    const int nworkers = train ? 1 : ngpu * per_gpu;
+    const int nworkers = (train || export_dir) ? 1 : ngpu * per_gpu;
     pg_ctx **wctx = (pg_ctx **)calloc((size_t)nworkers, sizeof(pg_ctx *));
     for (int w = 0; w < nworkers; w++) {
         wctx[w] = pg_init(dev[w % ngpu]);                /* workers 0..ngpu-1 own the models of their devices */
@@ -664,11 +958,29 @@ int main(int argc, char **argv)
     pg_model **models = (pg_model **)calloc((size_t)ngpu, sizeof(pg_model *));
     void *blob = NULL;
     int64_t blen = 0;
-    if (pg_model_load(wctx[0], model, &models[0], &blob, &blen) != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(wctx[0])); return 1; }
     taxonomy t;
-    if (!blob || tax_from_blob((const char *)blob, blen, &t)) { fprintf(stderr, "rdp_classifier: %s has no taxonomy section\n", model); return 1; }
+    const int from_tables = is_properties(model);
+    if (from_tables) {
+        if (import_rdp(wctx[0], model, &models[0], &t)) return 1;
+    } else {
+        if (pg_model_load(wctx[0], model, &models[0], &blob, &blen) != PG_OK) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(wctx[0])); return 1; }
+        if (!blob || tax_from_blob((const char *)blob, blen, &t)) { fprintf(stderr, "rdp_classifier: %s has no taxonomy section\n", model); return 1; }
+    }
     LAP("model load");
-    if (ngpu > 1) {
+    if (export_dir) {
+        if (from_tables) { fprintf(stderr, "rdp_classifier: --export-rdp needs a .pgm model (counts), not trainset files\n"); return 1; }
+        const int rc = export_rdp(wctx[0], models[0], &t, export_dir);
+        pg_model_free(models[0]);
+        pg_shutdown(wctx[0]);
+        return rc;
+    }
+    if (ngpu > 1 && from_tables) {
+        /* a model given as tables has no counts to broadcast: every device reads the files itself */
+        for (int r = 1; r < ngpu; r++) {
+            taxonomy t2;
+            if (import_rdp(wctx[r], model, &models[r], &t2)) return 1;
+        }
+    } else if (ngpu > 1) {
         int32_t *anc = tax_lineage_table(&t);
         for (int r = 1; r < ngpu; r++) {
             if (pg_model_create(wctx[r], t.G, &models[r]) != PG_OK || pg_model_set_lineage(models[r], anc, t.maxdepth) != PG_OK) {

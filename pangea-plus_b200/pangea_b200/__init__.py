@@ -141,6 +141,7 @@ def load_library() -> C.CDLL:
     lib.pg_free.argtypes = [vp]
     lib.pg_free.restype = None
     lib.pg_model_create.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    lib.pg_model_from_tables.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(vp)]
     lib.pg_model_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.c_int, C.POINTER(C.c_int)]
     lib.pg_model_commit.argtypes = [vp]
     lib.pg_reads_pack.argtypes = [vp, C.POINTER(_SeqBatch), C.POINTER(vp)]
@@ -356,6 +357,19 @@ class Context:
                     out_dev, src_dev=None, read_len: int = 250, gap: int = 189, paired: bool = True) -> None:
         self._chk(self.lib.pg_synth_reads(self.h, seed, _ptr(members_dev), _ptr(member_off_dev), _ptr(member_genus_dev), nmembers,
                                           first, count, read_len, gap, int(paired), _ptr(out_dev), _ptr(src_dev)))
+
+    def model_from_tables(self, log_prior, leave_count, idx, genus_of_entry, logp_of_entry) -> Model:
+        """a model given as RDP-style tables (pg_model_from_tables): logPrior[65536], leaveCount[G], sparse word-major cells"""
+        lp = np.ascontiguousarray(log_prior, np.float32)
+        lc = np.ascontiguousarray(leave_count, np.int32)
+        ix = np.ascontiguousarray(idx, np.int64)
+        eg = np.ascontiguousarray(genus_of_entry, np.int32)
+        ep = np.ascontiguousarray(logp_of_entry, np.float32)
+        assert lp.size == PG_NWORDS and ix.size == PG_NWORDS + 1 and eg.size == ep.size == ix[-1]
+        h = C.c_void_p()
+        self._chk(self.lib.pg_model_from_tables(self.h, lc.size, lp.ctypes.data, lc.ctypes.data, ix.ctypes.data, eg.ctypes.data,
+                                                ep.ctypes.data, C.byref(h)))
+        return Model(self, h.value)
 
     def model_create(self, G: int) -> Model:
         h = C.c_void_p()

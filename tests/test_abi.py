@@ -10,9 +10,11 @@ import pangea_b200 as pg
 
 
 def declared_symbols():
-    text = pg.HEADER.read_text()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(pg_[a-z_0-9]+)\s*\(", text)))
+    syms = set()
+    for h in sorted(pg.HEADER.parent.glob("*.h")):          # pangea_b200.h and pangea_b200_synth.h
+        text = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
+        syms |= set(re.findall(r"\b(pg_[a-z_0-9]+)\s*\(", text))
+    return sorted(syms)
 
 
 @pytest.fixture(scope="module")

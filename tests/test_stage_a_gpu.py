@@ -376,6 +376,17 @@ def baseline_model(ctx):
     gm.free()
 
 
+def test_tables_bit_exact_full_size_model(ctx, baseline_model):
+    """the device's double-precision log() against glibc's on every cell of the 1 219-genus bench model (80 M cells):
+    A6 narrows ln() of a float quotient to fp32, so the two libraries would have to disagree in the last bits of the
+    double AND sit on a rounding boundary of the float to differ; the whole table is compared bit for bit"""
+    tr, om, gm = baseline_model
+    lp, ll, t = gm.tables()
+    rlp, rll, rt = om.tables()
+    assert np.array_equal(bits(lp), bits(rlp)) and np.array_equal(bits(ll), bits(rll))
+    assert np.array_equal(bits(t), bits(np.ascontiguousarray(rt)))
+
+
 def test_config0_real_16s_queries_vs_9178_model(ctx, baseline_model):
     """configs[0]: real full-length 16S queries (subset of rdp_download_373seqs.fa) against the 9178-seq model"""
     from pathlib import Path
@@ -434,6 +445,11 @@ def test_config3_rdp_scale_genera(ctx):
     m, nw, M, N = gm.counts(dense=False)
     rm, rnw, rM, rN = om.counts()
     assert np.array_equal(nw, rnw) and np.array_equal(M, rM) and N == rN
+    lp, ll, t = gm.tables()                                  # 655 M cells: device log() == glibc log() after narrowing
+    rlp, rll, rt = om.tables()
+    assert np.array_equal(bits(lp), bits(rlp)) and np.array_equal(bits(ll), bits(rll))
+    assert np.array_equal(bits(t), bits(np.ascontiguousarray(rt)))
+    del t, rt
     data, off, src = synth.synth_reads(0x3000001, tr, 4096, paired=False)
     reads = [data[off[i]:off[i + 1]].tobytes() for i in range(0, 4096, 32)]
     check_against_oracle(ctx, gm, om, tr["anc"], reads, mode=1)
@@ -564,3 +580,97 @@ def test_large_batches_are_sliced(ctx, small, monkeypatch):
     st1 = ctx.classify_stats()
     assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb)
     assert st1["certified"] + st1["strict"] == 3000 == st0["certified"] + st0["strict"]
+
+
+def test_model_from_tables_round_trip(ctx, small):
+    """a model exported as RDP-style tables (word priors, leave counts, the sparse word-major
+    list of conditional log probabilities of the cells with a count) and built again from them holds the same dense
+    table bit for bit -- the absent cells are fp32(logPrior - logLeave) on both sides -- and classifies to the same
+    records; it has no counts, so it refuses to be saved or committed."""
+    tr, om, gm = small
+    m, nw, M, N = gm.counts()
+    lp, ll, t = gm.tables()
+    present = m > 0
+    idx = np.zeros(65537, np.int64)
+    idx[1:] = np.cumsum(present.sum(axis=1))
+    w_, g_ = np.nonzero(present)                           # row-major: word-major, genus ascending
+    tm = ctx.model_from_tables(lp, M, idx, g_.astype(np.int32), t[w_, g_])
+    lp2, ll2, t2 = tm.tables()
+    assert np.array_equal(bits(lp2), bits(lp)) and np.array_equal(bits(ll2), bits(ll)) and np.array_equal(bits(t2), bits(t))
+    tm.set_lineage(tr["anc"])
+    assert tm.certifiable
+    data, off, src = synth.synth_reads(77, tr, 500, paired=True)
+    for mode in (0, 1):
+        a, ba = ctx.classify(gm, data, off, mode=mode, want_boot=True)
+        b, bb = ctx.classify(tm, data, off, mode=mode, want_boot=True)
+        assert a.tobytes() == b.tobytes() and np.array_equal(ba, bb)
+    with pytest.raises(pg.PangeaError):
+        tm.commit()
+    with pytest.raises(pg.PangeaError):
+        tm.save("/tmp/never.pgm")
+    # malformed input is refused, not scattered
+    bad = idx.copy()
+    bad[100] = bad[101] + 5
+    with pytest.raises(pg.PangeaError):
+        ctx.model_from_tables(lp, M, bad, g_.astype(np.int32), t[w_, g_])
+    gbad = g_.astype(np.int32).copy()
+    gbad[0] = tr["G"]
+    with pytest.raises(pg.PangeaError):
+        ctx.model_from_tables(lp, M, idx, gbad, t[w_, g_])
+    tm.free()
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_ties_without_lineage_and_min_boot_words(ctx, seed):
+    """everything awkward at once: genera that are exact copies of each other (ties in the full sum and in every
+    replicate), a few near-copies, NO lineage (the table keeps the training order, so twins sit in different blocks
+    and the bounds cannot dismiss them), min_boot_words = 5 with reads short enough for it to matter (k = max(n/8, 5)),
+    reads with runs of N, both strands.  Certified (every plan) == strict == oracle."""
+    rng = np.random.default_rng(seed)
+    base = synth.synth16s(seed=40 + seed, seqs=150, genera=150, length=420)
+    seqs, genus = [], []
+    for i in range(150):
+        s = base["data"][base["off"][i]:base["off"][i + 1]]
+        seqs.append(s.tobytes())
+        genus.append(int(base["genus"][i]))
+    G = 150
+    for c in range(60):                                      # exact twins of the first 60 sequences, as new genera
+        seqs.append(seqs[c])
+        genus.append(G)
+        G += 1
+    for c in range(30):                                      # near copies: two substitutions
+        s = np.frombuffer(seqs[c], np.uint8).copy()
+        for p in rng.integers(0, len(s), 2):
+            s[p] = synth.BASES[rng.integers(0, 4)]
+        seqs.append(s.tobytes())
+        genus.append(G)
+        G += 1
+    data, off = pack_sequences(seqs)
+    genus = np.array(genus, np.int32)
+    om = ora.Model(data, off, genus, G)
+    gm = ctx.train(data, off, genus, G)                      # no set_lineage
+    assert gm.certifiable
+    reads = []
+    for i in range(400):
+        s = np.frombuffer(seqs[int(rng.integers(0, len(seqs)))], np.uint8)
+        ln = int(rng.choice([50, 52, 55, 60, 90, 250, len(s)]))
+        a = int(rng.integers(0, len(s) - ln + 1))
+        r = s[a:a + ln].copy()
+        if i % 7 == 0 and ln >= 90:
+            r[20:20 + int(rng.integers(1, 30))] = ord("N")
+        if i % 2:
+            r = synth.revcomp(r)
+        reads.append(r.tobytes())
+    rdata, roff = pack_sequences(reads)
+    ref = om.classify(rdata, roff, 5)
+    want, wb = ctx.classify(gm, rdata, roff, mode=0, min_boot_words=5, want_boot=True)
+    ok = ref["status"] == 0
+    assert np.array_equal(want["genus"], ref["genus"]) and np.array_equal(wb[ok], ref["boot"][ok])
+    assert np.array_equal(bits(want["score"][ok]), bits(ref["score"][ok]))
+    assert (want["votes"][ok][:, 0].astype(int) == (wb[ok] == want["genus"][ok, None]).sum(axis=1)).all()   # one-level lineage {g}
+    assert ((want["n_words"][ok] // 8) < 5).any()            # min_boot_words really decided k for some reads
+    for kw in (dict(), dict(cert_plan=1), dict(cert_plan=2), dict(light_max=3), dict(bound_level=2), dict(bound_level=3)):
+        got, gb = ctx.classify(gm, rdata, roff, mode=1, min_boot_words=5, want_boot=True, **kw)
+        assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb), kw
+    om.free()
+    gm.free()

@@ -329,3 +329,60 @@ def test_rdp_classifier_cli_multi_gpu_equals_single(tmp_path):
         assert cells[0] == f"r{i:07d}:AB" and cells[1] == ("-" if ref[i]["reversed"] else "")
         assert cells[-3] == tr["node_names"][tr["anc"][order[ref[i]["genus"]]][-1]]
     om.free()
+
+
+def test_rdp_classifier_cli_stock_trainset_files(tmp_path):
+    """--export-rdp writes the five files of an RDP trainset directory (layouts per appendix B,
+    unverified against the jar); classifying from rRNAClassifier.properties must give, byte for byte, the lines the
+    .pgm model gives -- in every format -- and -f db carries trainset number, taxid and confidence per rank."""
+    from pangea_b200 import synth
+
+    tr = synth.synth16s(seed=81, seqs=260, genera=70, length=700)
+    write_training_fasta(tmp_path / "train.fa", tr)
+    model = tmp_path / "m.pgm"
+    run([BIN / "rdp_classifier", "--train", tmp_path / "train.fa", "-t", model])
+    ts = tmp_path / "trainset"
+    ts.mkdir()
+    r = run([BIN / "rdp_classifier", "--export-rdp", ts, "-t", model])
+    assert "exported 70 genera" in r.stdout
+    for fn in ("rRNAClassifier.properties", "bergeyTrainingTree.xml", "logWordPrior.txt", "wordConditionalProbIndexArr.txt",
+               "genus_wordConditionalProbList.txt"):
+        assert (ts / fn).stat().st_size > 0
+    tree = (ts / "bergeyTrainingTree.xml").read_text().split("\n")
+    assert tree[0].startswith("<trainsetNo>") and "<file>bergeyTrainingTree</file>" in tree[0]
+    assert tree[1].startswith('<TreeNode name="Root" taxid="0" rank="rootrank" parentTaxid="-1" leaveCount="260" genusIndex="-1">')
+    assert sum('genusIndex="-1"' not in l for l in tree[1:] if l) == 70
+    idx_lines = (ts / "wordConditionalProbIndexArr.txt").read_text().split("\n")
+    assert len([l for l in idx_lines if l]) == 1 + 65537
+    data, off, src = synth.synth_reads(82, tr, 600, paired=True)
+    with open(tmp_path / "q.fa", "w") as f:
+        for i in range(600):
+            f.write(f">q{i:05d}\n{data[off[i]:off[i + 1]].tobytes().decode()}\n")
+        f.write(">tiny\nACGT\n")
+    for fmt in ("allrank", "fixrank", "pangea", "db"):
+        a, b = tmp_path / f"a_{fmt}.txt", tmp_path / f"b_{fmt}.txt"
+        ra = run([BIN / "rdp_classifier", "-q", tmp_path / "q.fa", "-o", a, "-t", model, "-f", fmt])
+        rb = run([BIN / "rdp_classifier", "-q", tmp_path / "q.fa", "-o", b, "-t", ts / "rRNAClassifier.properties", "-f", fmt])
+        assert a.read_bytes() == b.read_bytes() and a.stat().st_size > 0, fmt
+        assert ra.stdout == rb.stdout and "ShortSequenceException" in ra.stdout
+    db = (tmp_path / "a_db.txt").read_text().split("\n")[:-1]
+    allr = (tmp_path / "a_allrank.txt").read_text().split("\n")[:-1]
+    assert len(db) == 7 * 600                                # Root .. genus, one line each
+    cells = allr[0].split("\t")
+    for k in range(7):
+        qid, tset, taxid, conf = db[k].split("\t")
+        assert qid == "q00000" and tset == "0" and conf == cells[4 + 3 * k]
+    # two devices from trainset files: every device reads the files itself (tables carry no counts to broadcast)
+    import torch
+
+    devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    c = tmp_path / "c.txt"
+    run([BIN / "rdp_classifier", "-q", tmp_path / "q.fa", "-o", c, "-t", ts / "rRNAClassifier.properties", "--gpus", "2", "--devices", devs])
+    assert c.read_bytes() == (tmp_path / "a_allrank.txt").read_bytes()
+    # -g picks the default model from the environment when -t is absent
+    env = dict(os.environ, PANGEA_RDP_MODEL_FUNGALLSU=str(model))
+    r = subprocess.run([str(BIN / "rdp_classifier"), "-q", str(tmp_path / "q.fa"), "-o", str(c), "-g", "fungallsu"], capture_output=True,
+                       text=True, env=env, timeout=300)
+    assert r.returncode == 0 and c.read_bytes() == (tmp_path / "a_allrank.txt").read_bytes()
+    r = subprocess.run([str(BIN / "rdp_classifier"), "-q", str(tmp_path / "q.fa"), "-o", str(c), "-g", "18s"], capture_output=True, text=True)
+    assert r.returncode != 0
