@@ -12,6 +12,13 @@
  *
  * One documented deviation: where the script prints "not found:" forever (an RDP id with no
  * BLAST line left), this program stops with a message on stderr and exit status 2.
+ *
+ * --soap-votes (opt-in): the README advertises a BLAST + SOAP + RDP consensus, but script 1.1
+ * opens the -s file and never reads it.  With this flag the SOAP hits DO vote, by a rule defined in terms of the
+ * script itself: the -s file is a class file like the -b file (read id, TAB, lineage, TAB, identity, ... -- SOAP2
+ * hits after the taxcollector step), and the result is exactly what the script prints when every read's SOAP lines
+ * are inserted after the read's last BLAST line in the -b file.  SOAP lines of reads without a BLAST line do not
+ * vote.  tests/test_stage_bc_gpu.py checks the flag against the reference script run on such a merged file.
  */
 #include <getopt.h>
 #include <stdio.h>
@@ -47,11 +54,64 @@ static void buf_add(buf *b, const char *s, size_t n)
     b->n += n;
 }
 
+/* --soap-votes: the SOAP lines of a read go after the read's last BLAST line.  SOAP runs are found by id through a
+ * sorted index (the two files need not list the same reads). */
+typedef struct { const char *id; size_t idn; int64_t first, count; } soap_run;
+static int run_cmp(const void *a, const void *b)
+{
+    const soap_run *x = (const soap_run *)a, *y = (const soap_run *)b;
+    const size_t n = x->idn < y->idn ? x->idn : y->idn;
+    const int c = memcmp(x->id, y->id, n);
+    if (c) return c;
+    if (x->idn != y->idn) return x->idn < y->idn ? -1 : 1;
+    return x->first < y->first ? -1 : (x->first > y->first ? 1 : 0);
+}
+static void merge_soap(pg_lines *B, const pg_lines *S)
+{
+    soap_run *runs = (soap_run *)malloc(sizeof(soap_run) * (size_t)(S->count + 1));
+    int64_t nruns = 0;
+    for (int64_t i = 0; i < S->count; i++) {
+        const char *id;
+        size_t idn;
+        tab_field(S->line[i], S->len[i], 0, &id, &idn);
+        if (nruns && runs[nruns - 1].idn == idn && memcmp(runs[nruns - 1].id, id, idn) == 0 && runs[nruns - 1].first + runs[nruns - 1].count == i)
+            runs[nruns - 1].count++;
+        else { runs[nruns].id = id; runs[nruns].idn = idn; runs[nruns].first = i; runs[nruns].count = 1; nruns++; }
+    }
+    qsort(runs, (size_t)nruns, sizeof(soap_run), run_cmp);
+    char *used = (char *)calloc((size_t)nruns + 1, 1);
+    const int64_t cap = B->count + S->count;
+    char **line = (char **)malloc(sizeof(char *) * (size_t)(cap + 1));
+    size_t *len = (size_t *)malloc(sizeof(size_t) * (size_t)(cap + 1));
+    int64_t n = 0;
+    for (int64_t i = 0; i < B->count; i++) {
+        line[n] = B->line[i]; len[n] = B->len[i]; n++;
+        const char *id, *nid = "";
+        size_t idn, nidn = 0;
+        tab_field(B->line[i], B->len[i], 0, &id, &idn);
+        if (i + 1 < B->count) tab_field(B->line[i + 1], B->len[i + 1], 0, &nid, &nidn);
+        if (i + 1 < B->count && nidn == idn && memcmp(nid, id, idn) == 0) continue;      /* not the read's last BLAST line */
+        /* first unused SOAP run with this id */
+        int64_t lo = 0, hi = nruns;
+        soap_run key = {id, idn, -1, 0};
+        while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (run_cmp(&runs[mid], &key) < 0) lo = mid + 1; else hi = mid; }
+        while (lo < nruns && used[lo] && runs[lo].idn == idn && memcmp(runs[lo].id, id, idn) == 0) lo++;
+        if (lo < nruns && !used[lo] && runs[lo].idn == idn && memcmp(runs[lo].id, id, idn) == 0) {
+            used[lo] = 1;
+            for (int64_t k = 0; k < runs[lo].count; k++) { line[n] = S->line[runs[lo].first + k]; len[n] = S->len[runs[lo].first + k]; n++; }
+        }
+    }
+    free(B->line); free(B->len);
+    B->line = line; B->len = len; B->count = n;
+    free(runs); free(used);
+}
+
 int main(int argc, char **argv)
 {
-    static struct option lo[] = {{"device", required_argument, 0, 'G'}, {"quiet", no_argument, 0, 'Q'}, {0, 0, 0, 0}};
+    static struct option lo[] = {{"device", required_argument, 0, 'G'}, {"quiet", no_argument, 0, 'Q'},
+                                 {"soap-votes", no_argument, 0, 'V'}, {0, 0, 0, 0}};
     const char *pb = NULL, *pr = NULL, *ps = NULL, *po = NULL;
-    int device = 0, quiet = 0;
+    int device = 0, quiet = 0, soap_votes = 0;
     for (;;) {
         int c = getopt_long(argc, argv, "b:r:s:o:", lo, NULL);
         if (c == -1) break;
@@ -61,6 +121,7 @@ int main(int argc, char **argv)
         else if (c == 'o') po = optarg;
         else if (c == 'G') device = atoi(optarg);
         else if (c == 'Q') quiet = 1;
+        else if (c == 'V') soap_votes = 1;
     }
     if (!pb || !pr || !po) {
         printf("Usage: perl Consensus-1.0.pl \n\t-b Classification results (Blast)\n\t-r Classification results (RDP)\n"
@@ -71,11 +132,15 @@ int main(int argc, char **argv)
     pg_lines B, R;
     if (pg_lines_read(pb, &B)) { printf("Error: Unable to open %s file.\n", pb); return 0; }
     if (pg_lines_read(pr, &R)) { printf("Error: Unable to open %s file.\n", pr); return 0; }
+    pg_lines S;
+    memset(&S, 0, sizeof S);
     if (ps) {
-        FILE *fs = fopen(ps, "r");                       /* C7: opened, never read */
+        FILE *fs = fopen(ps, "r");                       /* C7: opened, never read (unless --soap-votes) */
         if (!fs) { printf("Error: Unable to open %s file.\n", ps); return 0; }
         fclose(fs);
+        if (soap_votes && pg_lines_read(ps, &S)) { printf("Error: Unable to open %s file.\n", ps); return 0; }
     }
+    if (soap_votes && S.count > 0) merge_soap(&B, &S);
     printf("%s\n", po);
     FILE *fo = fopen(po, "w");
     if (!fo) { printf("Error: Unable to open output file %s.\n", po); return 0; }

@@ -171,6 +171,50 @@ def test_consensus_vs_oracle_large(tmp_path):
     assert out.read_bytes() == want.read_bytes()
 
 
+def test_consensus_soap_votes_is_the_script_on_the_merged_file(tmp_path):
+    """--soap-votes (opt-in): SOAP hits vote by the rule 'what the reference script prints when every read's SOAP lines
+    are inserted after the read's last BLAST line'.  The hits of a synthetic class file are split into a BLAST file
+    and a SOAP file (some reads keep hits only in one of them, SOAP lists a few reads BLAST does not have, in a
+    different place); the tool with the flag must print what the script's restatement prints for the merged file, and
+    without the flag what it prints for the BLAST file alone."""
+    tx = st.make_taxonomy(65, 1500, 80000)
+    st.write_dumps(tx, str(tmp_path / "d"))
+    d = build_bins(tmp_path / "d", tmp_path / "b")
+    lines, ids, per = st.make_blast_hits(66, tx, 3000, max_hits=12)
+    hits = tmp_path / "hits.txt"
+    hits.write_text("\n".join(lines) + "\n")
+    cls = tmp_path / "class.txt"
+    assert op.oracle_taxcollector(d, hits, cls) == 0
+    ids, by = op.group_lineages(cls)
+    rdp = tmp_path / "rdp.txt"
+    rdp.write_text("\n".join(st.make_rdp_lines(67, ids, by, agree=0.6)) + "\n")
+    rng = np.random.default_rng(68)
+    blast, soap, merged = [], [], []
+    cl = [l for l in cls.read_text().split("\n") if l]
+    runs = {}
+    for l in cl:
+        runs.setdefault(l.split("\t")[0], []).append(l)
+    for k, (rid, ls) in enumerate(runs.items()):
+        to_soap = [l for l in ls if rng.random() < 0.4]
+        to_blast = [l for l in ls if l not in to_soap]
+        if not to_blast:                                  # every read keeps a BLAST line (reads without one do not vote)
+            to_blast, to_soap = ls[:1], ls[1:]
+        blast += to_blast
+        soap += to_soap
+        merged += to_blast + to_soap
+    soap = soap[len(soap) // 2:] + ["ZZ_only_soap\t[0]Bacteria;\t99.00\t250"] + soap[: len(soap) // 2]   # another order, an extra read
+    for name, ls in (("blast.txt", blast), ("soap.txt", soap), ("merged.txt", merged)):
+        (tmp_path / name).write_text("\n".join(ls) + "\n")
+    want = tmp_path / "want.txt"
+    out = tmp_path / "out.txt"
+    assert op.oracle_consensus(tmp_path / "merged.txt", rdp, want) == 0
+    run([BIN / "consensus", "-b", tmp_path / "blast.txt", "-r", rdp, "-s", tmp_path / "soap.txt", "-o", out, "--quiet", "--soap-votes"])
+    assert out.read_bytes() == want.read_bytes()
+    assert op.oracle_consensus(tmp_path / "blast.txt", rdp, want) == 0
+    run([BIN / "consensus", "-b", tmp_path / "blast.txt", "-r", rdp, "-s", tmp_path / "soap.txt", "-o", out, "--quiet"])
+    assert out.read_bytes() == want.read_bytes()            # without the flag the SOAP file is opened and ignored (C7)
+
+
 def test_consensus_stops_where_the_reference_loops_forever(tmp_path):
     b = tmp_path / "b.txt"
     r = tmp_path / "r.txt"
