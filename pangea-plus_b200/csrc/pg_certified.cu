@@ -1794,12 +1794,12 @@ static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, unsigned
 {
     dim3 grid(nreads_b, nblk_y);
     if (nblk_y > 1) {
-        PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA(ctx, pg_smem_unlock(ctx, k_classify_q<BLOCK, MINB, true>));
         k_classify_q<BLOCK, MINB, true><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
                                                               slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->d_blockmask,
                                                               md->vmax, d_champ, d_ncand, d_cand, d_guess);
     } else {
-        PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_q<BLOCK, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PG_CUDA(ctx, pg_smem_unlock(ctx, k_classify_q<BLOCK, MINB, false>));
         k_classify_q<BLOCK, MINB, false><<<grid, BLOCK, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,
                                                               slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->d_blockmask,
                                                               md->vmax, d_champ, d_ncand, d_cand, d_guess);
@@ -1882,7 +1882,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
         const unsigned npair = (nreads_b + PG_PARTS - 1) / PG_PARTS;
 #define PG_LAUNCH_H(B, M)                                                                                               \
     {                                                                                                                   \
-        PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_h<B, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        PG_CUDA(ctx, pg_smem_unlock(ctx, k_classify_h<B, M>)); \
         k_classify_h<B, M><<<npair, B, smem, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_flags, d_order,   \
                                                             (int)nreads_b, slot0, ctx->d_boot_pool, ctx->d_boot_off,    \
                                                             min_boot, md->d_blockmask, md->vmax, cb.champ, cb.ncand,    \
@@ -1909,7 +1909,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     // 46 % more instructions, 28 % slower -- LDS.64 rows of 64 bytes gain nothing from the interleave)
     if (use8) {
         const size_t bsmem = (size_t)(nmax + 1) * pitch_s + (((size_t)nmax * 2 + 15) & ~(size_t)15);
-        PG_CUDA(ctx, cudaFuncSetAttribute(k_bound8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+        PG_CUDA(ctx, pg_smem_unlock(ctx, k_bound8));
         k_bound8<<<dim3(nreads_b, (unsigned)nchunk8), block8, bsmem, ctx->stream>>>(
             md->d_bm8, md->bm8_pitch, nsegc, pitch_s, md->d_bmtable, md->d_hmtable, d_words, d_off, d_nwords, d_flags, d_order,
             slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->ntile64, md->sib0, md->vmax, cb.champ, d_guess, cb.items,
@@ -1921,13 +1921,13 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     if (env_part == -2) { const char *e = getenv("PG_BOUND_PART"); env_part = e ? atoi(e) : -1; }
     const bool part_cols = version == 3 && (env_part >= 0 ? env_part != 0 : (blevel == 3 || (blevel == 0 && (cb.force_part >= 0 ? cb.force_part != 0 : md->part_bounds))));
     if (part_cols) {
-        PG_CUDA(ctx, cudaFuncSetAttribute(k_bound<160, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+        PG_CUDA(ctx, pg_smem_unlock(ctx, k_bound<160, true>));
         k_bound<160, true><<<dim3(nreads_b, (unsigned)md->ngroup_h), 160, bsmem, ctx->stream>>>(
             md->d_hmtable, d_words, d_off, d_nwords, d_flags, d_order, slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot,
             md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.counters + 2, cb.item_cap, cb.heavy,
             (unsigned int)light_max, md->d_hmtable);
     } else {
-    PG_CUDA(ctx, cudaFuncSetAttribute(k_bound<160, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+    PG_CUDA(ctx, pg_smem_unlock(ctx, k_bound<160, false>));
     k_bound<160, false><<<dim3(nreads_b, (unsigned)md->ngroup), 160, bsmem, ctx->stream>>>(
         md->d_bmtable, d_words, d_off, d_nwords, d_flags, d_order, slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot,
         md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.counters + 2, cb.item_cap, cb.heavy,
@@ -1957,7 +1957,7 @@ int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int 
     constexpr int WARPS = 4;
     const size_t per_warp = (((size_t)nmax * 2 + 15) & ~(size_t)15) + (PG_NUM_BOOT + 1) * 4 + 16;
     const size_t smem = per_warp * WARPS;
-    PG_CUDA(ctx, cudaFuncSetAttribute(k_resolve<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PG_CUDA(ctx, pg_smem_unlock(ctx, k_resolve<WARPS>));
     k_resolve<WARPS><<<(nreads_b + WARPS - 1) / WARPS, 32 * WARPS, smem, ctx->stream>>>(
         md->d_table, d_words, d_off, d_nwords, d_flags, d_order, (int)nreads_b, slot0, nmax, ctx->d_boot_pool,
         ctx->d_boot_off, min_boot, md->G, md->vmax, cb.champ, cb.ncand, cb.cand, md->d_anc, md->depth, d_results,

@@ -242,8 +242,7 @@ static int launch_strict(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, uns
                          const int32_t *d_order, int64_t slot0, int min_boot, unsigned long long *d_best)
 {
     // per device, so set it on every launch (a few microseconds)
-    PG_CUDA(ctx, cudaFuncSetAttribute(k_classify_strict<LPR, BLOCK>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PG_CUDA(ctx, pg_smem_unlock(ctx, k_classify_strict<LPR, BLOCK>));
     dim3 grid(nreads_b, nblocks_g);
     k_classify_strict<LPR, BLOCK><<<grid, BLOCK, smem, ctx->stream>>>(
         md->d_table, d_words, d_off, d_nwords, d_order, slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, d_best);

@@ -44,6 +44,7 @@ extern "C" pg_ctx *pg_init(int device)
     pg_ctx *ctx = new pg_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     ctx->err[0] = 0;
     ctx->launches = 0;
     ctx->d_boot_pool = NULL;

@@ -16,6 +16,10 @@
 struct pg_ctx {
     int          device;
     int          sm_count;
+    // opt-in maximum of dynamic shared memory per block.  Every kernel that needs more than 48 KB is given THIS limit,
+    // not the size of the launch at hand: the attribute is per function and device, and two host threads that share a
+    // device (rdp_classifier runs two contexts per GPU) would otherwise lower it under each other's launches
+    int          smem_optin;
     cudaStream_t stream;
     cudaStream_t own_stream;
     cudaStream_t copy_stream, down_stream;    // uploads / downloads of pg_classify(), created on first use
@@ -135,6 +139,17 @@ static inline cudaError_t pg_dev_alloc(const pg_ctx *ctx, void **p, size_t bytes
 static inline void pg_dev_free(const pg_ctx *ctx, void *p)
 {
     if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+// every launch of a kernel with more than 48 KB of dynamic shared memory is preceded by this: the function's limit is
+// raised to ALL the device allows beside its static shared memory -- the same value from every thread, see smem_optin
+template <typename K>
+static inline cudaError_t pg_smem_unlock(const pg_ctx *ctx, K kernel)
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - (int)a.sharedSizeBytes);
 }
 
 #define PG_CUDA(ctx, call)                                                              \
