@@ -664,6 +664,7 @@ def main():
 
     for i in range(args.warmup):
         step_resident(i)
+    gather_once()                                            # warm-up: NCCL sets its channels up on the first collective
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

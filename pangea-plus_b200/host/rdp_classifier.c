@@ -862,7 +862,14 @@ static int replicate_counts(int ndev, const int *dev, pg_model **models, char *e
     }
     ncclComm_t comms[16];
     cudaStream_t streams[16];
+    /* stdout belongs to the tool's contract (the ShortSequenceException lines): whatever NCCL has to say (its version
+     * banner under NCCL_DEBUG=VERSION is a plain printf) goes to stderr -- file descriptor 1 points at 2 while it starts */
+    fflush(stdout);
+    const int saved_out = dup(1);
+    dup2(2, 1);
     ncclResult_t nr = ncclCommInitAll(comms, ndev, dev);
+    fflush(stdout);
+    if (saved_out >= 0) { dup2(saved_out, 1); close(saved_out); }
     if (nr != ncclSuccess) { snprintf(err, errlen, "ncclCommInitAll: %s", ncclGetErrorString(nr)); return 1; }
     for (int r = 0; r < ndev; r++) { cudaSetDevice(dev[r]); cudaStreamCreateWithFlags(&streams[r], cudaStreamNonBlocking); }
     for (int b = 0; b < nbuf && nr == ncclSuccess; b++) {
