@@ -873,6 +873,8 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     extern __shared__ uint4 sB[];                   // (n+1) rows x 4 uint4 (32 blocks x 16 bit); row n is zero
     __shared__ uint32_t s_list[PG_LIGHT_MAX];
     __shared__ uint32_t s_full[32];
+    __shared__ uint32_t s_thr[PG_NUM_BOOT];         // champion + margin of the 100 replicates, staged once (a dependent global
+                                                    // load at the head of every task was 8 % of the kernel's stall samples)
     __shared__ unsigned int s_cnt, s_base;
 
     const int tid = threadIdx.x;
@@ -903,6 +905,16 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     if (tid < 4) sB[n * 4 + tid] = make_uint4(0u, 0u, 0u, 0u);
     if (tid < 32) s_full[tid] = 0u;
     if (tid == 0) s_cnt = 0u;
+    {
+        int k0 = n >> 3;
+        if (k0 < min_boot) k0 = min_boot;
+        const uint32_t margin0 = pg_margin(k0, vmax);
+        for (int t = tid; t < PG_NUM_BOOT; t += BLOCK) {
+            const unsigned long long cv = __ldg(champ + rc * (PG_NUM_BOOT + 1) + 1 + t);
+            // sums stay below 2^26: the threshold is kept in 32 bits (an empty slot = no threshold)
+            s_thr[t] = (cv == PG_CHAMP_INIT) ? 0xFFFFFFFFu : (uint32_t)(cv >> 32) + margin0;
+        }
+    }
     pg_cp_async_wait_all();
     __syncthreads();
     if (sib_here) {
@@ -968,12 +980,9 @@ k_bound(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, con
     const int nb = (k + 3) >> 2;
     if (nb > 0) {
         const uint4 *lists = reinterpret_cast<const uint4 *>(boot_pool + boot_off[n]);
-        const uint32_t margin = pg_margin(k, vmax);
         for (int t = unit; t < PG_NUM_BOOT; t += NUNIT) {
-            const unsigned long long cv = __ldg(mychamp + 1 + t);
             const uint4 *lp = lists + (size_t)(t >> 2) * nb * 4 + (t & 3);
-            // sums stay below 2^26: the threshold is kept in 32 bits (an empty slot = no threshold)
-            const uint32_t thr = (cv == PG_CHAMP_INIT) ? 0xFFFFFFFFu : (uint32_t)(cv >> 32) + margin;
+            const uint32_t thr = s_thr[t];
             uint32_t s[4] = {0u, 0u, 0u, 0u}, cx = 0u, cy = 0u;
             bool lane_open = true;                  // some block of this lane may still be within the threshold
             // The four units of a warp walk in lockstep.  Partial sums only grow, so a lane whose four blocks are
