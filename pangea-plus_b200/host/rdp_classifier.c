@@ -8,9 +8,9 @@
  * --gpus N [--devices a,b,..]: the reads shard across N GPUs.  Device 0 loads the model file, its
  * integer training counts are replicated once with ncclBroadcast (peer copies when a device is listed twice), every
  * device derives its tables locally, and the query file is cut into record-aligned pieces that the devices take in
- * turn; lines are written in input order.  The run is a pipeline: one thread reads pieces into pinned buffers, two
- * contexts per device ingest + classify them (the copies of one overlap the kernels of the other), formatter threads
- * turn records into text, and one thread writes the pieces in order.
+ * turn; lines are written in input order.  The run is a pipeline: reader threads pread() pieces into pinned buffers,
+ * per device an ingest context (highest stream priority) uploads and parses them while a classify context works on the
+ * piece before, formatter threads turn records into text, and an in-order thread hands file offsets to a pwrite pool.
  *
  * The jar carries its training data inside; this tool cannot ship RDP's trainset, so the
  * model is a file: `-t model.pgm` (default: $PANGEA_RDP_MODEL, else ./rdp_model.pgm), made by
@@ -507,7 +507,9 @@ typedef struct {
     int64_t   *hdr_off;
     int32_t   *id_len;
     pg_result *res;                 /* pinned */
+    pg_reads  *reads;               /* packed reads of the piece, between the ingest and the classify stage */
     int64_t    rescap;
+    int64_t    out_at;              /* where the piece's lines go in the output file (set by the in-order writer) */
     char      *out, *msg;           /* formatted lines / stdout messages */
     size_t     out_len, out_cap, msg_len, msg_cap;
 } piece_t;
@@ -564,7 +566,11 @@ typedef struct {
     int64_t         piece_bytes;
     FILE           *fq, *fo;
     /* queues */
-    queue_t         q_free, q_gpu, q_fmt, q_out;
+    queue_t         q_free, q_gpu, q_fmt, q_out, q_write;
+    queue_t        *q_mid;          /* per GPU: ingested pieces waiting for the classify context (split mode) */
+    int             ngpu, split, ingest_alive;
+    pg_ctx        **ictx;           /* per GPU: the ingest context (its stream has the highest priority) */
+    int             out_fd, nwriters, write_alive;
     int             npieces;
     /* workers */
     int             nworkers, nformat;
@@ -660,7 +666,41 @@ static void *reader_main(void *arg)
 
 typedef struct { pipeline_t *pl; int idx; } worker_arg;
 
-/* GPU worker: FASTA ingest + classification of one piece at a time on its own context */
+/* FASTA ingest of one piece (text -> records, ids, packed reads on the device) */
+static int ingest_piece(pg_ctx *ctx, piece_t *p)
+{
+    if (p->cap == 0) p->cap = p->len / 32 + 1024;
+    p->reads = NULL;
+    for (;;) {
+        if (!p->hdr_off) {
+            p->hdr_off = (int64_t *)malloc(sizeof(int64_t) * (size_t)p->cap);
+            p->id_len = (int32_t *)malloc(sizeof(int32_t) * (size_t)p->cap);
+        }
+        const int rc = pg_fasta_ingest(ctx, p->text, p->len, p->cap, &p->nrec, p->hdr_off, p->id_len, NULL, &p->reads);
+        if (rc == PG_ERANGE && p->nrec > p->cap) {
+            p->cap = p->nrec;
+            free(p->hdr_off); free(p->id_len);
+            p->hdr_off = NULL; p->id_len = NULL;
+            continue;
+        }
+        return rc;
+    }
+}
+
+static int classify_piece(pipeline_t *pl, pg_ctx *ctx, const pg_model *md, piece_t *p)
+{
+    int rc = PG_OK;
+    if (p->nrec + 1 > p->rescap) {
+        if (p->res) cudaFreeHost(p->res);
+        p->rescap = p->nrec + p->nrec / 8 + 1024;
+        p->res = (pg_result *)pinned_alloc(sizeof(pg_result) * (size_t)p->rescap);
+        if (!p->res) { pl_fail(pl, "pinned allocation failed"); return PG_ENOMEM; }
+    }
+    if (p->nrec > 0) rc = pg_classify_packed_host(ctx, md, p->reads, &pl->opts, p->res, NULL);
+    return rc;
+}
+
+/* GPU worker, one context for both stages (--contexts-per-gpu 1): FASTA ingest, then classification, one piece at a time */
 static void *gpu_main(void *arg)
 {
     worker_arg *wa = (worker_arg *)arg;
@@ -672,36 +712,70 @@ static void *gpu_main(void *arg)
         if (!p) break;
         if (pl->failed || p->len == 0) { p->nrec = 0; q_push(&pl->q_fmt, p); continue; }
         double t0 = now_s();
-        pg_reads *reads = NULL;
-        if (p->cap == 0) p->cap = p->len / 32 + 1024;
-        int rc;
-        for (;;) {
-            if (!p->hdr_off) {
-                p->hdr_off = (int64_t *)malloc(sizeof(int64_t) * (size_t)p->cap);
-                p->id_len = (int32_t *)malloc(sizeof(int32_t) * (size_t)p->cap);
-            }
-            rc = pg_fasta_ingest(ctx, p->text, p->len, p->cap, &p->nrec, p->hdr_off, p->id_len, NULL, &reads);
-            if (rc == PG_ERANGE && p->nrec > p->cap) {
-                p->cap = p->nrec;
-                free(p->hdr_off); free(p->id_len);
-                p->hdr_off = NULL; p->id_len = NULL;
-                continue;
-            }
-            break;
-        }
+        int rc = ingest_piece(ctx, p);
         const double t_ing = now_s() - t0;
-        if (rc == PG_OK && p->nrec + 1 > p->rescap) {
-            if (p->res) cudaFreeHost(p->res);
-            p->rescap = p->nrec + p->nrec / 8 + 1024;
-            p->res = (pg_result *)pinned_alloc(sizeof(pg_result) * (size_t)p->rescap);
-            if (!p->res) { rc = PG_ENOMEM; pl_fail(pl, "pinned allocation failed"); }
-        }
-        if (rc == PG_OK && p->nrec > 0) rc = pg_classify_packed_host(ctx, md, reads, &pl->opts, p->res, NULL);
-        if (reads) pg_reads_free(reads);
+        if (rc == PG_OK) rc = classify_piece(pl, ctx, md, p);
+        if (p->reads) { pg_reads_free(p->reads); p->reads = NULL; }
         if (rc != PG_OK) { pl_fail(pl, pg_last_error(ctx)); p->nrec = 0; }
         pthread_mutex_lock(&pl->mu);
         pl->busy_gpu += now_s() - t0;
         pl->busy_ingest += t_ing;
+        pl->reads_total += p->nrec;
+        pthread_mutex_unlock(&pl->mu);
+        q_push(&pl->q_fmt, p);
+    }
+    pthread_mutex_lock(&pl->mu);
+    int last = --pl->gpu_alive == 0;
+    pthread_mutex_unlock(&pl->mu);
+    if (last) q_close(&pl->q_fmt);
+    return NULL;
+}
+
+/* Split mode (the default): two threads and two contexts per GPU.  The ingest context runs on a stream of the highest
+ * priority, so its short kernels and copies slip in between the thread blocks of the classify context's long kernels:
+ * the upload and parsing of piece i+1 hide under the classification of piece i, and neither stage waits behind the
+ * other's queue (two equal contexts that each do both stages were measured: 3-11 M reads/s, depending on how their
+ * synchronisation points happened to interleave). */
+static void *ingest_main(void *arg)
+{
+    worker_arg *wa = (worker_arg *)arg;
+    pipeline_t *pl = wa->pl;
+    const int g = wa->idx;
+    pg_ctx *ctx = pl->ictx[g];
+    for (;;) {
+        piece_t *p = q_pop(&pl->q_gpu);
+        if (!p) break;
+        if (pl->failed || p->len == 0) { p->nrec = 0; p->reads = NULL; q_push(&pl->q_mid[g], p); continue; }
+        const double t0 = now_s();
+        const int rc = ingest_piece(ctx, p);
+        if (rc != PG_OK) { pl_fail(pl, pg_last_error(ctx)); p->nrec = 0; }
+        pthread_mutex_lock(&pl->mu);
+        pl->busy_ingest += now_s() - t0;
+        pthread_mutex_unlock(&pl->mu);
+        q_push(&pl->q_mid[g], p);
+    }
+    q_close(&pl->q_mid[g]);
+    return NULL;
+}
+
+static void *classify_main(void *arg)
+{
+    worker_arg *wa = (worker_arg *)arg;
+    pipeline_t *pl = wa->pl;
+    const int g = wa->idx;
+    pg_ctx *ctx = pl->wctx[g];
+    const pg_model *md = pl->wmodel[g];
+    for (;;) {
+        piece_t *p = q_pop(&pl->q_mid[g]);
+        if (!p) break;
+        const double t0 = now_s();
+        if (!pl->failed && p->nrec > 0) {
+            const int rc = classify_piece(pl, ctx, md, p);
+            if (rc != PG_OK) { pl_fail(pl, pg_last_error(ctx)); p->nrec = 0; }
+        }
+        if (p->reads) { pg_reads_free(p->reads); p->reads = NULL; }
+        pthread_mutex_lock(&pl->mu);
+        pl->busy_gpu += now_s() - t0;
         pl->reads_total += p->nrec;
         pthread_mutex_unlock(&pl->mu);
         q_push(&pl->q_fmt, p);
@@ -813,12 +887,14 @@ static void *fmt_main(void *arg)
     return NULL;
 }
 
-/* writer: pieces leave in file order whatever order they were finished in */
+/* writer: pieces leave in file order whatever order they were finished in.  The in-order thread only prints the
+ * stdout messages and hands out file offsets (a running sum of the pieces' sizes); a small pool of threads does the
+ * pwrite()s, so the copy into the page cache is not one thread's job */
 static void *writer_main(void *arg)
 {
     pipeline_t *pl = (pipeline_t *)arg;
     piece_t **done = (piece_t **)calloc((size_t)pl->npieces, sizeof(piece_t *));
-    int64_t next = 0;
+    int64_t next = 0, at = 0;
     for (;;) {
         piece_t *p = q_pop(&pl->q_out);
         if (!p) break;
@@ -826,17 +902,36 @@ static void *writer_main(void *arg)
         while (done[next % pl->npieces] && done[next % pl->npieces]->seq == next) {
             piece_t *w = done[next % pl->npieces];
             done[next % pl->npieces] = NULL;
-            double t0 = now_s();
-            if (!pl->failed) {
-                if (w->msg_len) fwrite(w->msg, 1, w->msg_len, stdout);
-                if (w->out_len && fwrite(w->out, 1, w->out_len, pl->fo) != w->out_len) pl_fail(pl, "write failed");
-            }
-            pl->busy_write += now_s() - t0;
+            if (!pl->failed && w->msg_len) fwrite(w->msg, 1, w->msg_len, stdout);
+            w->out_at = at;
+            at += (int64_t)w->out_len;
             next++;
-            q_push(&pl->q_free, w);
+            q_push(&pl->q_write, w);
         }
     }
     free(done);
+    q_close(&pl->q_write);
+    return NULL;
+}
+
+static void *pwrite_main(void *arg)
+{
+    pipeline_t *pl = (pipeline_t *)arg;
+    for (;;) {
+        piece_t *w = q_pop(&pl->q_write);
+        if (!w) break;
+        const double t0 = now_s();
+        size_t off = 0;
+        while (!pl->failed && off < w->out_len) {
+            const ssize_t got = pwrite(pl->out_fd, w->out + off, w->out_len - off, (off_t)(w->out_at + (int64_t)off));
+            if (got <= 0) { pl_fail(pl, "write failed"); break; }
+            off += (size_t)got;
+        }
+        pthread_mutex_lock(&pl->mu);
+        pl->busy_write += now_s() - t0;
+        pthread_mutex_unlock(&pl->mu);
+        q_push(&pl->q_free, w);
+    }
     return NULL;
 }
 
@@ -935,7 +1030,7 @@ int main(int argc, char **argv)
     }
     int ifmt = strcmp(fmt, "allrank") == 0 ? 0 : strcmp(fmt, "fixrank") == 0 ? 1 : strcmp(fmt, "pangea") == 0 ? 2 : strcmp(fmt, "db") == 0 ? 3 : -1;
     if (ifmt < 0) { fprintf(stderr, "rdp_classifier: unknown format %s\n", fmt); return 1; }
-    if (ngpu < 1 || ngpu > 16 || per_gpu < 1 || per_gpu > 4) { fprintf(stderr, "rdp_classifier: --gpus 1..16, --contexts-per-gpu 1..4\n"); return 1; }
+    if (ngpu < 1 || ngpu > 16 || per_gpu < 1 || per_gpu > 2) { fprintf(stderr, "rdp_classifier: --gpus 1..16, --contexts-per-gpu 1 or 2\n"); return 1; }
     int dev[16];
     for (int r = 0; r < ngpu; r++) dev[r] = device + r;
     if (devlist) {
@@ -948,7 +1043,8 @@ int main(int argc, char **argv)
     const int timing = getenv("PG_TIMING") != NULL;
     double t0 = now_s(), t1, t_begin = t0;
 #define LAP(what) do { if (timing) { t1 = now_s(); fprintf(stderr, "[timing] %-22s %.3f s\n", what, t1 - t0); t0 = t1; } } while (0)
-    const int nworkers = (train || export_dir) ? 1 : ngpu * per_gpu;
+    const int split = !(train || export_dir) && per_gpu >= 2;          /* ingest and classify contexts per GPU */
+    const int nworkers = (train || export_dir) ? 1 : ngpu;
     pg_ctx **wctx = (pg_ctx **)calloc((size_t)nworkers, sizeof(pg_ctx *));
     for (int w = 0; w < nworkers; w++) {
         wctx[w] = pg_init(dev[w % ngpu]);                /* workers 0..ngpu-1 own the models of their devices */
@@ -1027,6 +1123,22 @@ int main(int argc, char **argv)
     }
     pl.nworkers = nworkers;
     pl.nformat = nformat;
+    pl.ngpu = ngpu;
+    pl.split = split;
+    if (split) {
+        pl.ictx = (pg_ctx **)calloc((size_t)ngpu, sizeof(pg_ctx *));
+        pl.q_mid = (queue_t *)calloc((size_t)ngpu, sizeof(queue_t));
+        for (int g = 0; g < ngpu; g++) {
+            pl.ictx[g] = pg_init(dev[g]);
+            if (!pl.ictx[g]) { fprintf(stderr, "rdp_classifier: %s\n", pg_last_error(NULL)); return 1; }
+            int lo_p = 0, hi_p = 0;
+            cudaStream_t hs = NULL;
+            cudaSetDevice(dev[g]);
+            if (cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p) == cudaSuccess &&
+                cudaStreamCreateWithPriority(&hs, cudaStreamNonBlocking, hi_p) == cudaSuccess)
+                pg_set_stream(pl.ictx[g], (void *)hs);
+        }
+    }
     pl.wctx = wctx;
     pl.wmodel = (pg_model **)calloc((size_t)nworkers, sizeof(pg_model *));
     for (int w = 0; w < nworkers; w++) pl.wmodel[w] = models[w % ngpu];
@@ -1049,14 +1161,18 @@ int main(int argc, char **argv)
      * is all there is -- size the buffers by the file */
     pl.textcap0 = pl.piece_bytes + pl.piece_bytes / 16 + 65536;
     if (pl.fsize + 4096 < pl.textcap0) pl.textcap0 = pl.fsize + 4096;
-    const int nreaders = pl.total_pieces > 2 ? 3 : 1;
+    const int nreaders = pl.total_pieces > 2 ? (ngpu + 2 > 8 ? 8 : ngpu + 2) : 1;
+    pl.nwriters = pl.total_pieces > 2 ? (ngpu > 3 ? 4 : 2) : 1;
+    pl.out_fd = fileno(pl.fo);
     pl.read_alive = nreaders;
-    pl.npieces = nworkers + nformat + nreaders + 1;
+    pl.npieces = nworkers * (split ? 3 : 1) + nformat + nreaders + pl.nwriters + 1;
     if (pl.total_pieces < pl.npieces) pl.npieces = (int)(pl.total_pieces > 0 ? pl.total_pieces : 1);
     q_init(&pl.q_free, pl.npieces + 1);
     q_init(&pl.q_gpu, pl.npieces + 1);
     q_init(&pl.q_fmt, pl.npieces + 1);
     q_init(&pl.q_out, pl.npieces + 1);
+    q_init(&pl.q_write, pl.npieces + 1);
+    if (split) for (int g = 0; g < ngpu; g++) q_init(&pl.q_mid[g], pl.npieces + 1);
     piece_t *pieces = (piece_t *)calloc((size_t)pl.npieces, sizeof(piece_t));
     cudaSetDevice(dev[0]);
     for (int i = 0; i < pl.npieces; i++) {
@@ -1070,18 +1186,26 @@ int main(int argc, char **argv)
     }
     LAP("buffers");
 
-    pthread_t th_reader[4], th_writer, *th_gpu = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nworkers),
+    pthread_t th_reader[8], th_pwrite[4], th_writer, *th_gpu = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nworkers),
               *th_fmt = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nformat);
     worker_arg *wa = (worker_arg *)malloc(sizeof(worker_arg) * (size_t)nworkers);
     const double t_pipe = now_s();
     pthread_create(&th_writer, NULL, writer_main, &pl);
+    for (int w = 0; w < pl.nwriters; w++) pthread_create(&th_pwrite[w], NULL, pwrite_main, &pl);
     for (int f = 0; f < nformat; f++) pthread_create(&th_fmt[f], NULL, fmt_main, &pl);
-    for (int w = 0; w < nworkers; w++) { wa[w].pl = &pl; wa[w].idx = w; pthread_create(&th_gpu[w], NULL, gpu_main, &wa[w]); }
+    pthread_t *th_ing = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nworkers);
+    for (int w = 0; w < nworkers; w++) {
+        wa[w].pl = &pl; wa[w].idx = w;
+        pthread_create(&th_gpu[w], NULL, split ? classify_main : gpu_main, &wa[w]);
+        if (split) pthread_create(&th_ing[w], NULL, ingest_main, &wa[w]);
+    }
     for (int r = 0; r < nreaders; r++) pthread_create(&th_reader[r], NULL, reader_main, &pl);
     for (int r = 0; r < nreaders; r++) pthread_join(th_reader[r], NULL);
+    if (split) for (int w = 0; w < nworkers; w++) pthread_join(th_ing[w], NULL);
     for (int w = 0; w < nworkers; w++) pthread_join(th_gpu[w], NULL);
     for (int f = 0; f < nformat; f++) pthread_join(th_fmt[f], NULL);
     pthread_join(th_writer, NULL);
+    for (int w = 0; w < pl.nwriters; w++) pthread_join(th_pwrite[w], NULL);
     q_close(&pl.q_free);
     const double dt = now_s() - t_pipe;
     fclose(pl.fq);
@@ -1100,5 +1224,6 @@ int main(int argc, char **argv)
     pg_free(blob);
     for (int r = 0; r < ngpu; r++) pg_model_free(models[r]);
     for (int w = 0; w < nworkers; w++) pg_shutdown(wctx[w]);
+    if (split) for (int g = 0; g < ngpu; g++) pg_shutdown(pl.ictx[g]);
     return 0;
 }
