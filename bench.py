@@ -166,6 +166,11 @@ def workload_config(paired, reads_per_step, L, G, l2_note):
     }
 
 
+def l2_note(reads, L, n_words):
+    return (f"inputs per step ({reads * L / 1e6:.0f} MB ASCII, {reads * n_words * 2 / 1e6:.0f} MB word ids) exceed the 126 MB L2; "
+            "batches alternate")
+
+
 def run_reference(args, rank: int, world: int):
     """the reference arm: the CPU restatement on every host core, a bounded sample of the SAME workload per step
     (config is the GPU arm's config; the sample size lives in cpu_baseline.sample)"""
@@ -193,7 +198,8 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(paired, args.reads, L, tr["G"], "host cores only (the config is the GPU arm's; the CPU arm times a bounded sample of it, see cpu_baseline.sample)"),
+        # the GPU arm's config, key for key (the CPU arm times a bounded sample of it: cpu_baseline.sample)
+        "config": workload_config(paired, args.reads, L, tr["G"], l2_note(args.reads, L, 486 if paired else 243)),
         "cpu_baseline": {"value": rate, "unit": "reads/s", "cores": threads, "per_core": rate / threads, "kind": "port",
                          "sample": f"{n} reads per step x {args.steps} steps of the same synthetic workload; "
                                    "oracle/rdp_ref.c (C restatement of RDP 2.5; the jar is not vendored and no JVM exists)"},
@@ -721,9 +727,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(paired, per_gpu, L, G,
-                                           f"inputs per step ({per_gpu * L / 1e6:.0f} MB ASCII, "
-                                           f"{per_gpu * n_words * 2 / 1e6:.0f} MB word ids) exceed the 126 MB L2; batches alternate"),
+            "config": dict(workload_config(paired, per_gpu, L, G, l2_note(per_gpu, L, n_words)),
                            mode="strict" if args.mode == 0 else "certified", parallelism=f"reads sharded x{world}",
                            median_words=n_words, routing_last_step=route,
                            results="records stay on their rank; one rank-ordered gather after the last step, inside the timed region"),
