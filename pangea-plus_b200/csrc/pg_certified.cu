@@ -31,13 +31,9 @@
 //   atomicMin and near-ties are appended to a short per-read list.
 // Phase 2 (k_resolve): one warp per read; strict re-check of survivors, then the A9 vote.
 // Reads whose list overflows are handed back to the strict kernels.
-#include "pg_classify_common.cuh"
+#include "pg_certified.cuh"
 #include <algorithm>
 
-#define PG_Q_SCALE 128.0            // units per nat
-#define PG_Q_MAX   4095             // 12-bit field: 16 rows x 4095 < 65536
-#define PG_CANDCAP 128              // near-tie entries kept per read
-#define PG_CHAMP_INIT 0xFFFFFFFFFFFFFFFFULL
 
 // ------------------------------------------------------------------ derive
 
@@ -110,9 +106,6 @@ __global__ void k_quantise(const float *__restrict__ table, const float *__restr
 // PG_Q_MAX and never wins).  A group is PG_GB = 28 blocks: bm[group][w][slot], the last PG_PARTS slots of
 // every 64-byte row are spare -- k_bound puts the part minima of the best block there with one 8-byte store
 // per row (plan 3).
-#define PG_PARTS 4                       // plan 3 evaluates one part (64 / PG_PARTS positions) of the best block
-#define PG_PART_POS (64 / PG_PARTS)
-#define PG_GB (32 - PG_PARTS)
 __global__ void k_blockmin(const uint16_t *__restrict__ q, int ntile64, int ngroup, uint16_t *__restrict__ bm)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,6 +263,8 @@ int pg_model_layout_from_lineage(pg_model *md, const int32_t *anc, int depth)
     return pg_model_set_layout(md, pos.data(), (int)pos.size());
 }
 
+int pg_mma_build_tables(pg_model *md);               // pg_mma.cu
+
 int pg_model_derive_quantised(pg_model *md)
 {
     pg_ctx *ctx = md->ctx;
@@ -320,6 +315,7 @@ int pg_model_derive_quantised(pg_model *md)
     memcpy(&vm, &stat[0], 4);
     md->vmax = (double)vm;
     md->q_ok = stat[1] <= PG_Q_MAX;      // no entry was clamped: upper bounds hold for every genus
+    if (md->q_ok) PG_TRY(pg_mma_build_tables(md));      // byte planes of plan 4 (pg_mma.cu)
     // field widths of the certified bookkeeping: part ids in 12 bits (k_guess_bm), block ids in 13 (items)
     if (PG_PARTS * md->ntile64 >= 4096) md->q_ok = false;       // > ~50 000 genera: mode 1 runs the strict kernels
     return PG_OK;
@@ -327,23 +323,6 @@ int pg_model_derive_quantised(pg_model *md)
 
 // ------------------------------------------------------------------ shared device pieces
 
-// margin in quantisation units: terms (floor error) + 2E*128 (fp32 order error) + 1
-__device__ __forceinline__ uint32_t pg_margin(int terms, double vmax)
-{
-    if (terms <= 1) return (uint32_t)terms + 1u;
-    const double u = 5.9604644775390625e-08;                 // 2^-24
-    const double m = (double)(terms - 1) * u;
-    const double E = m / (1.0 - m) * (double)terms * vmax * 1.0001;
-    return (uint32_t)terms + (uint32_t)ceil(2.0 * E * PG_Q_SCALE) + 1u;
-}
-
-__device__ __forceinline__ void pg_emit(unsigned int *ncand, unsigned long long *cand, int task, uint32_t genus,
-                                        uint32_t sum)
-{
-    const unsigned int slot = atomicAdd(ncand, 1u);
-    if (slot < PG_CANDCAP)
-        cand[slot] = ((unsigned long long)task << 56) | ((unsigned long long)genus << 32) | sum;
-}
 
 // Task epilogue, split in two so the returning atomic's latency hides behind the
 // next replicate's main loop.
@@ -821,8 +800,6 @@ k_guess_block(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ 
 //   k_light      group of 8 lanes per item: exact sums of the item's block, champion update
 //   k_resolve    as before; reads flagged heavy (too many items) are redone by the all-block kernel.
 
-#define PG_LIGHT_MAX 768            // items per (read, group) above which the read is "heavy"
-#define PG_ITEM_NULL 0xFFFFu
 
 __global__ void __launch_bounds__(256)
 k_guess_bm(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
@@ -1819,6 +1796,12 @@ static int launch_q(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, unsigned
 
 // phase 1 for one bucket (timed by the caller).  version 2 = best block + lower bounds + items
 // (reads with too many items are flagged in cb.heavy); version 1 = every block, partial-sum pruning.
+bool pg_mma_usable(const pg_model *md, int nmax);                                    // pg_mma.cu
+int pg_mma_build_tables(pg_model *md);
+int pg_mma_launch(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, const uint16_t *d_words, const int64_t *d_off,
+                  const int32_t *d_nwords, const uint8_t *d_flags, const int32_t *d_order, int64_t slot0, int min_boot,
+                  const PgCertBufs &cb, const int32_t *d_guess, unsigned int light_max);
+
 int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsigned nreads_b, int nmax,
                         const uint16_t *d_words, const int64_t *d_off, const int32_t *d_nwords,
                         const uint8_t *d_flags, const int32_t *d_order, int64_t slot0, int min_boot,
@@ -1829,6 +1812,10 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     if (noprune < 0) { const char *e = getenv("PG_NO_PRUNE"); noprune = (e && atoi(e)) ? 1 : 0; }
     int32_t *d_guess = cb.guess;
     if (noprune || md->ntile64 < 2) { d_guess = NULL; version = 1; }
+    // version 4 = plan 4 (pg_mma.cu): plan 3's best part and bounds as one tensor-core product per read; reads it
+    // cannot take (more than 640 words, a model without the byte tables, an explicit bound_level) go through plan 3
+    const bool use_mma = d_guess && version == 4 && cb.bound_level == 0 && cb.force_part < 0 && pg_mma_usable(md, nmax);
+    if (version == 4) version = 3;
     // version 3 = plan 3 (best part of the best block, PG_PARTS reads per CTA, the default); 2 = plan 2 (whole best block);
     // 1 = plan 1 (every block, partial-sum pruning)
     unsigned nblk_y = (unsigned)md->ntile64;
@@ -1887,7 +1874,11 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     static int qblock = -1;                             // PG_Q_BLOCK=448: experiment switch for the first bucket
     if (qblock < 0) { const char *e = getenv("PG_Q_BLOCK"); qblock = e ? atoi(e) : 0; }
     int rc = PG_OK;
-    if (d_guess && version == 3) {
+    if (use_mma) {
+        PG_CUDA(ctx, cudaMemsetAsync(cb.counters + 2, 0, 4, ctx->stream));
+        const unsigned int lm = cb.light_max == 0 ? 0xFFFFFFFFu : (cb.light_max < 0 ? 0u : (unsigned int)cb.light_max);
+        PG_TRY(pg_mma_launch(ctx, md, nreads_b, nmax, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb, d_guess, lm));
+    } else if (d_guess && version == 3) {
         const unsigned npair = (nreads_b + PG_PARTS - 1) / PG_PARTS;
 #define PG_LAUNCH_H(B, M)                                                                                               \
     {                                                                                                                   \
@@ -1913,10 +1904,12 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
 
     int light_max = cb.light_max == 0 ? PG_LIGHT_MAX : (cb.light_max < 0 ? 0 : cb.light_max);
     if (light_max > PG_LIGHT_MAX) light_max = PG_LIGHT_MAX;
-    PG_CUDA(ctx, cudaMemsetAsync(cb.counters + 2, 0, 4, ctx->stream));
+    if (!use_mma) PG_CUDA(ctx, cudaMemsetAsync(cb.counters + 2, 0, 4, ctx->stream));
     // (a two-reads-per-CTA k_bound with interleaved rows, like k_classify_h, was measured: same wavefronts,
     // 46 % more instructions, 28 % slower -- LDS.64 rows of 64 bytes gain nothing from the interleave)
-    if (use8) {
+    if (use_mma) {
+        // best part and bounds are done (pg_mma_launch above)
+    } else if (use8) {
         const size_t bsmem = (size_t)(nmax + 1) * pitch_s + (((size_t)nmax * 2 + 15) & ~(size_t)15);
         PG_CUDA(ctx, pg_smem_unlock(ctx, k_bound8));
         k_bound8<<<dim3(nreads_b, (unsigned)nchunk8), block8, bsmem, ctx->stream>>>(

@@ -258,6 +258,7 @@ int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int 
                         const int64_t *d_off, const int32_t *d_nwords, const uint8_t *d_flags,
                         const int32_t *d_order, int64_t slot0, int min_boot, const PgCertBufs &cb, bool use_heavy,
                         pg_result *d_results, int32_t *d_boot_winners);
+int pg_mma_ensure_images(pg_ctx *ctx, const std::vector<int> &need_n, int min_boot);          // pg_mma.cu
 int pg_certified_reset(pg_ctx *ctx, const int32_t *d_list, int cnt, int64_t slot0, const PgCertBufs &cb);   // pg_certified.cu
 #define PG_CANDCAP 128
 
@@ -378,12 +379,15 @@ struct ClassifyJob {
         nkeys = PG_NUM_BOOT + 1;
         if (min_boot < 0 || min_boot > 64) return pg_fail(ctx, PG_EINVAL, "min_boot_words out of range");
         if (mode != 0 && mode != 1) return pg_fail(ctx, PG_EINVAL, "unknown classify mode %d", mode);
-        if (opts && (opts->cert_plan < 0 || opts->cert_plan > 2)) return pg_fail(ctx, PG_EINVAL, "unknown cert_plan %d", opts->cert_plan);
+        if (opts && (opts->cert_plan < 0 || opts->cert_plan > 3)) return pg_fail(ctx, PG_EINVAL, "unknown cert_plan %d", opts->cert_plan);
         if (count > 0x7fffffffLL) return pg_fail(ctx, PG_ERANGE, "more than 2^31-1 reads in one batch");
         certified = (mode == 1) && md->q_ok;
         static int env_v1 = -1;                         // PG_CERT_V1=1: the all-block kernel for every read (A/B switch)
         if (env_v1 < 0) { const char *e = getenv("PG_CERT_V1"); env_v1 = (e && atoi(e)) ? 1 : 0; }
-        cert_version = (env_v1 || (opts && opts->cert_plan == 1)) ? 1 : ((opts && opts->cert_plan == 2) ? 2 : 3);
+        // 4 = plan 4, the default: plan 3's best part and bounds on the tensor cores (pg_mma.cu); an explicit
+        // bound_level or cert_plan 3 asks for plan 3's own kernels
+        cert_version = (env_v1 || (opts && opts->cert_plan == 1)) ? 1 : ((opts && opts->cert_plan == 2) ? 2 :
+                       ((opts && (opts->cert_plan == 3 || opts->bound_level != 0)) ? 3 : 4));
         ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
         ctx->st_heavy = ctx->st_items = 0;
         // Chunk of reads per pass.  Plan 1 walks every genus block of a chunk (tile-major grid) and wants the
@@ -641,6 +645,7 @@ struct ClassifyJob {
             }
         }
         if (!need.empty()) PG_TRY(ensure_boot_lists(ctx, need, min_boot));
+        if (!need.empty() && certified && cert_version == 4) PG_TRY(pg_mma_ensure_images(ctx, need, min_boot));
         // pageable source: staged before the call returns, so hstart may be rewritten for the next range
         PG_CUDA(ctx, cudaMemcpyAsync(d_start, hstart.data(), PG_HB * 4, cudaMemcpyHostToDevice, ctx->stream));
         PG_CUDA(ctx, cudaMemsetAsync(d_cursor, 0, PG_HB * 4, ctx->stream));

@@ -87,6 +87,7 @@ extern "C" void pg_shutdown(pg_ctx *ctx)
     for (int i = 0; i < pg_ctx::kNumScratch; i++) cudaFree(s[i].p);
     cudaFree(ctx->d_boot_pool);
     cudaFree(ctx->d_boot_off);
+    cudaFree(ctx->d_cnt_img);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (auto &p : ctx->ev_pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto &ev : ctx->ev_free) cudaEventDestroy(ev);

@@ -34,6 +34,11 @@ struct pg_ctx {
     std::vector<int32_t> h_boot_off;
     int                  boot_min_words;
 
+    // plan 4 (pg_mma.cu): draw-count images of the replicates, one slot per word count n <= 640
+    uint8_t             *d_cnt_img;
+    std::vector<char>    cnt_built;
+    int                  cnt_min_words;
+
     // classify-kernel timing (CUDA events on the launching stream)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending;
     std::vector<cudaEvent_t>                         ev_free;
@@ -87,6 +92,12 @@ struct pg_model {
     // bound the table's 16-position parts instead of its 64-position blocks (k_bound<.., true>)?  Decided once per model
     // by timing both on the first chunk of reads it classifies (results do not depend on it); mutable for that reason
     mutable bool part_bounds, bounds_tuned;
+    // plan 4 (pg_mma.cu): byte planes the tensor-core kernel gathers its B operand from
+    uint8_t  *d_qx;             // [ntile64 * 4][65536][32]  low bytes | high bytes of a part's 16 deficits
+    uint8_t  *d_bm8x;           // [65536][pitch8]           min(bm >> 2, 255) per block
+    uint8_t  *d_hm8x;           // [65536][hpitch]           min(hm >> 2, 255) per part (4 * block + part)
+    int      pitch8, hpitch;
+    int      x8_blocks;         // ntile64 the three tables were built for (0: none)
     int      ngroup;            // ceil(ntile64 / 31): slot 31 of a bm row is spare (k_bound, plan 3)
     int      ngroup_h;          // ceil(2*ntile64 / 32)
     double   vmax;              // max |table entry| over real genera (fp32 error bound)

@@ -175,6 +175,7 @@ extern "C" void pg_model_free(pg_model *md)
     cudaFree(md->d_N); cudaFree(md->d_logPrior); cudaFree(md->d_pdiff); cudaFree(md->d_Pw); cudaFree(md->d_logLeave);
     cudaFree(md->d_anc); cudaFree(md->d_qtable); cudaFree(md->d_rowmax);
     cudaFree(md->d_perm); cudaFree(md->d_bmtable); cudaFree(md->d_blockmask); cudaFree(md->d_hmtable); cudaFree(md->d_bm8);
+    cudaFree(md->d_qx); cudaFree(md->d_bm8x); cudaFree(md->d_hm8x);
     delete md;
 }
 
