@@ -1433,7 +1433,7 @@ k_light(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ words,
     const unsigned int ngroups = gridDim.x * (blockDim.x >> 3);
     unsigned int cnt = *item_count;
     if (cnt > item_cap) cnt = item_cap;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(items_total, cnt);
+    if (items_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(items_total, cnt);   // NULL: the list holds blanks, its writer counted
     for (unsigned int it = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); it < cnt; it += ngroups) {
         const unsigned long long e = items[it];
         const int task = (int)((e >> 16) & 0xFFFFu);
@@ -1876,7 +1876,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     int rc = PG_OK;
     if (use_mma) {
         PG_CUDA(ctx, cudaMemsetAsync(cb.counters + 2, 0, 4, ctx->stream));
-        const unsigned int lm = cb.light_max == 0 ? 0xFFFFFFFFu : (cb.light_max < 0 ? 0u : (unsigned int)cb.light_max);
+        const unsigned int lm = cb.light_max == 0 ? 2048u : (cb.light_max < 0 ? 0u : (unsigned int)cb.light_max);
         PG_TRY(pg_mma_launch(ctx, md, nreads_b, nmax, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb, d_guess, lm));
     } else if (d_guess && version == 3) {
         const unsigned npair = (nreads_b + PG_PARTS - 1) / PG_PARTS;
@@ -1943,7 +1943,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     }
     k_light<<<ctx->sm_count * light_ctas, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_order - slot0, ctx->d_boot_pool,
                                                         ctx->d_boot_off, min_boot, md->d_blockmask, md->vmax, cb.items,
-                                                        cb.counters + 2, cb.item_cap, cb.champ, cb.ncand, cb.cand, cb.counters + 3,
+                                                        cb.counters + 2, cb.item_cap, cb.champ, cb.ncand, cb.cand, use_mma ? NULL : cb.counters + 3,
                                                         version == 3 ? md->d_hmtable : NULL);
     PG_LAUNCHED(ctx);
     return PG_OK;

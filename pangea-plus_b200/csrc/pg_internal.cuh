@@ -51,8 +51,8 @@ struct pg_ctx {
         void  *p;
         size_t cap;
     } s_words, s_nwords, s_flags, s_best, s_order, s_results, s_boot, s_bytes, s_off, s_cand,
-      s_champ, s_ncand, s_candl, s_fb, s_guess, s_items, s_heavy, s_hist;
-    static const int kNumScratch = 18;
+      s_champ, s_ncand, s_candl, s_fb, s_guess, s_items, s_heavy, s_hist, s_meta;
+    static const int kNumScratch = 19;
     int64_t st_heavy, st_items;                        // certified v2: reads redone by the all-block kernel, light items
     // pinned host staging
     void  *h_pin;

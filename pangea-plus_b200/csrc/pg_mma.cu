@@ -27,12 +27,13 @@
 
 #define PG_MMA_MAXN   640                   // reads with more good words go through plan 3
 #define PG_MMA_KC     128                   // words per ring stage
-#define PG_MMA_STAGES 4
+#define PG_MMA_MAXSTAGES 8                // ring depth: as many stages as shared memory holds, at least 3
 #define PG_MMA_IMG    (128 * PG_MMA_MAXN)   // bytes of one count image slot
 #define PG_MMA_NPROD  256                   // producer threads
 #define PG_MMA_THREADS (128 + 32 + PG_MMA_NPROD)
-#define PG_MMA_LIST   2048                  // open pairs per read kept in shared memory (more: the read is "heavy")
+#define PG_MMA_LIST   2048                  // open pairs per read above which the read is "heavy" (default)
 #define PG_X8_SHIFT   2
+#define PG_MMA_RESERVE 128                  // entries of the global item list an epilogue warp reserves at a time
 
 // ------------------------------------------------------------------ tables
 
@@ -166,8 +167,13 @@ int pg_mma_ensure_images(pg_ctx *ctx, const std::vector<int> &need_n, int min_bo
 __device__ __forceinline__ uint32_t pgm_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void pgm_cp16(uint32_t s, const void *g)
 {
+#ifdef PG_MMA_CA
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(g) : "memory");
+#endif
 }
+#define PGM_CP16 pgm_cp16
 __device__ __forceinline__ void pgm_mbar_init(uint32_t bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
@@ -199,6 +205,13 @@ __device__ __forceinline__ void pgm_mma_i8(uint32_t d_tmem, uint64_t adesc, uint
                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
                  : "memory");
 }
+// one lane of the (converged) warp
+__device__ __forceinline__ bool pgm_elect()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0u;
+}
 __device__ __forceinline__ void pgm_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -215,6 +228,7 @@ __device__ __forceinline__ void pgm_commit(uint32_t bar)
 struct PgMmaArgs {
     const uint8_t *qx, *bm8x, *hm8x, *images;
     int pitch8, hpitch, ntile64, kmax;               // kmax: words of the longest read of the launch, rounded up to 32
+    unsigned nstage;                                 // ring depth of this launch
     const uint16_t *words;
     const int64_t *off;
     const int32_t *nwords;
@@ -230,39 +244,85 @@ struct PgMmaArgs {
     unsigned long long *cand;
     const int32_t *guess;
     unsigned long long *items;
-    unsigned int *item_count;
+    unsigned int *item_count, *items_total;        // list cursor (reservations incl. blanks); pairs written, for the statistics
     unsigned int item_cap;
     uint8_t *heavy;
     unsigned int light_max;
+    const int4 *meta;                                 // [nreads_b + gridDim.x][2], k_mma_meta
+    long long *prof;                                  // PG_MMA_PROF=1: per CTA 8 cycle counters, else NULL
 };
 
-// the reads of one CTA, in the order every role walks them
+// What the roles need to know about the read in slot s, gathered once by k_mma_meta so that the persistent kernel finds
+// it with ONE 16-byte load, issued a whole read ahead (order -> flags / nwords / off -> guess -> blockmask is a chain of
+// four dependent loads: ~2 000 cycles per read when every role walks it on its own).
+//   x = n (0: the read is skipped -- short, or no word), y = part id | validity bits of the part's 16 positions << 16,
+//   z, w = offset of the read's word ids; second entry: x, y = certified margins of the full sum and of a replicate
+__global__ void k_mma_meta(const int64_t *__restrict__ off, const int32_t *__restrict__ nwords, const uint8_t *__restrict__ flags,
+                           const int32_t *__restrict__ order, int nreads_b, int64_t slot0, const int32_t *__restrict__ guess,
+                           const unsigned long long *__restrict__ blockmask, int min_boot, double vmax, int4 *__restrict__ meta,
+                           int nmeta)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nmeta) return;
+    int4 m = make_int4(0, 0, 0, 0), m2 = make_int4(0, 0, 0, 0);
+    if (s < nreads_b) {
+        const int64_t read = order[s];
+        if (!flags[2 * read + 1]) {
+            const int gs = guess[(size_t)slot0 + s];
+            const uint32_t vb16 = (uint32_t)(blockmask[gs / PG_PARTS] >> ((gs % PG_PARTS) * PG_PART_POS)) & 0xFFFFu;
+            const int64_t wo = off[read];
+            const int n = nwords[read];
+            int k = n >> 3;
+            if (k < min_boot) k = min_boot;
+            m = make_int4(n, (int)((uint32_t)gs | (vb16 << 16)), (int)(uint32_t)wo, (int)(uint32_t)((unsigned long long)wo >> 32));
+            m2 = make_int4((int)pg_margin(n, vmax), (int)pg_margin(k, vmax), 0, 0);     // double-precision work kept out of the epilogue
+        }
+    }
+    meta[2 * s] = m;
+    meta[2 * s + 1] = m2;
+}
+
 struct PgMmaRead {
     int slot, n, gs;
-    int64_t read;
+    uint32_t vb16, margin_full, margin_rep;
+    int64_t woff;
 };
-__device__ __forceinline__ bool pgm_next_read(const PgMmaArgs &a, int &slot, PgMmaRead &r)
-{
-    for (; slot < a.nreads_b; slot += (int)gridDim.x) {
-        const int64_t read = a.order[slot];
-        if (a.flags[2 * read + 1]) continue;            // short read (A2)
-        const int n = a.nwords[read];
-        if (n == 0) continue;                           // no word: phase 2 writes genus 0 directly
-        r.slot = slot; r.n = n; r.read = read; r.gs = a.guess[(size_t)a.slot0 + slot];
-        slot += (int)gridDim.x;
-        return true;
+// A role's cursor over the slots of its CTA (blockIdx.x, + gridDim.x, ...).  The metadata of the NEXT slot is always in
+// flight; meta[] is padded with empty slots past the end, so the look-ahead never needs a bound check.
+struct PgMmaCursor {
+    int slot;
+    int4 ahead, ahead2;
+    __device__ __forceinline__ void start(const PgMmaArgs &a)
+    {
+        slot = (int)blockIdx.x;
+        ahead = __ldg(a.meta + 2 * slot);
+        ahead2 = __ldg(a.meta + 2 * slot + 1);
     }
-    return false;
-}
+    __device__ __forceinline__ bool next(const PgMmaArgs &a, PgMmaRead &r)
+    {
+        while (slot < a.nreads_b) {
+            const int4 m = ahead, m2 = ahead2;
+            const int s = slot;
+            slot += (int)gridDim.x;
+            ahead = __ldg(a.meta + 2 * slot);
+            ahead2 = __ldg(a.meta + 2 * slot + 1);
+            if (m.x == 0) continue;
+            r.slot = s; r.n = m.x; r.gs = m.y & 0xFFFF; r.vb16 = (uint32_t)m.y >> 16;
+            r.margin_full = (uint32_t)m2.x; r.margin_rep = (uint32_t)m2.y;
+            r.woff = (int64_t)(((unsigned long long)(uint32_t)m.w << 32) | (uint32_t)m.z);
+            return true;
+        }
+        return false;
+    }
+};
 
 __global__ void __launch_bounds__(PG_MMA_THREADS, 1)
 k_mma_bound(const __grid_constant__ PgMmaArgs a)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t s_full[PG_MMA_STAGES], s_empty[PG_MMA_STAGES], s_dfull[2], s_dempty[2];
+    __shared__ __align__(8) uint64_t s_full[PG_MMA_MAXSTAGES], s_empty[PG_MMA_MAXSTAGES], s_dfull[2], s_dempty[2];
     __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_list[2][PG_MMA_LIST];
-    __shared__ unsigned int s_cnt[2], s_base;
+    __shared__ unsigned int s_cnt[2], s_ntie[2], s_wdone[2];   // per accumulator buffer: open pairs, near-ties, epilogue warps done
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nch = 3 + a.pitch8 / 16;                   // 16-column chunks of B
@@ -276,10 +336,12 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     if (tid == 32) {
-        for (int s = 0; s < PG_MMA_STAGES; s++) { pgm_mbar_init(pgm_smem(&s_full[s]), PG_MMA_NPROD); pgm_mbar_init(pgm_smem(&s_empty[s]), 1); }
+        for (int s = 0; s < PG_MMA_MAXSTAGES; s++) { pgm_mbar_init(pgm_smem(&s_full[s]), PG_MMA_NPROD); pgm_mbar_init(pgm_smem(&s_empty[s]), 1); }
         for (int i = 0; i < 2; i++) { pgm_mbar_init(pgm_smem(&s_dfull[i]), 1); pgm_mbar_init(pgm_smem(&s_dempty[i]), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         s_cnt[0] = s_cnt[1] = 0u;
+        s_ntie[0] = s_ntie[1] = 0u;
+        s_wdone[0] = s_wdone[1] = 0u;
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
@@ -288,107 +350,151 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
 
     if (warp >= 5) {
         // ================================================================ producers
-        const int p = tid - 160, jr = p & (PG_MMA_KC - 1), c0 = p >> 7;      // this thread's row of a stage; its chunks: c0, c0 + 2, ...
-        int slot = (int)blockIdx.x, cur_n = -1;
-        unsigned it = 0;
-        bool owe = false;                                // the previous stage is issued but not yet signalled
-        PgMmaRead r;
-        bool have = pgm_next_read(a, slot, r);
-        int kc = 0;
-        uint32_t wid = 0u;
-        if (have && jr < r.n) wid = a.words[a.off[r.read] + jr];
+        // Thread p gathers row jr = p / 2 of every stage; lanes 2i and 2i + 1 fetch the two 16-byte halves of the same
+        // 32-byte sector in one instruction (qx: low | high bytes; bm8x: two chunks of 16 blocks).
+        const int p = tid - 160, jr = p >> 1, sub = p & 1;
+        constexpr int MAXST = PG_MMA_MAXN / PG_MMA_KC;                       // stages of the longest read
+        int cur_n = -1;
+        unsigned s = 0, ph = 1u, sprev = 0, phprev = 0;  // ring slot of the next stage and the parity of its "free" phase
+        bool first = true;
+        PgMmaCursor cur;
+        cur.start(a);
+        PgMmaRead r, rn, rnn;
+        bool have = cur.next(a, r);
+        bool have_n = have && cur.next(a, rn);
+        // This thread's word id in every stage of a read is fetched TWO reads ahead (the ids stream from DRAM), so that
+        // one read ahead the rows of the exact table -- 235 MB and more, mostly not in L2 -- can be prefetched into L2:
+        // the gather is bound by requests in flight x their latency, and a DRAM round trip is twice an L2 hit.
+        uint32_t w[MAXST], wn[MAXST], wnn[MAXST];
+#pragma unroll
+        for (int i = 0; i < MAXST; i++) {
+            w[i] = (have && i * PG_MMA_KC + jr < r.n) ? (uint32_t)a.words[r.woff + i * PG_MMA_KC + jr] : 0u;
+            wn[i] = (have_n && i * PG_MMA_KC + jr < rn.n) ? (uint32_t)a.words[rn.woff + i * PG_MMA_KC + jr] : 0u;
+        }
+        long long t_wait = 0, t_all = clock64();
+        unsigned nst_total = 0;
+        const int nb8 = a.pitch8 / 16;                   // chunks of block columns: chunk 2 + i
         while (have) {
-            // the stage after this one: its word id is fetched now and used a whole stage later
-            PgMmaRead rn = r;
-            int kcn = kc + 1;
-            bool have_n = true;
-            if (kcn * PG_MMA_KC >= r.n) { kcn = 0; have_n = pgm_next_read(a, slot, rn); }
-            uint32_t wid_n = 0u;
-            if (have_n && kcn * PG_MMA_KC + jr < rn.n) wid_n = a.words[a.off[rn.read] + kcn * PG_MMA_KC + jr];
-
-            const unsigned s = it % PG_MMA_STAGES;
-            if (kc == 0 && r.n != cur_n) {
-                // a new count image: every product that reads the old one must be done.  Signal the stage we owe first
-                // (its products cannot start before), then wait for the products of the last stage issued.
-                if (owe) {
-                    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                    pgm_mbar_arrive(pgm_smem(&s_full[(it - 1) % PG_MMA_STAGES]));
-                    owe = false;
-                }
-                if (it > 0) pgm_mbar_wait(pgm_smem(&s_empty[(it - 1) % PG_MMA_STAGES]), ((it - 1) / PG_MMA_STAGES) & 1u);
+            const bool have_nn = have_n && cur.next(a, rnn);
+#pragma unroll
+            for (int i = 0; i < MAXST; i++) wnn[i] = (have_nn && i * PG_MMA_KC + jr < rnn.n) ? (uint32_t)a.words[rnn.woff + i * PG_MMA_KC + jr] : 0u;
+            if (have_n && sub == 0) {
+                const uint8_t *qn = a.qx + (size_t)rn.gs * PG_NWORDS * 32;
+#pragma unroll
+                for (int i = 0; i < MAXST; i++)
+                    if (i * PG_MMA_KC + jr < rn.n) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(qn + (size_t)wn[i] * 32));
+            }
+            if (r.n != cur_n) {
+                // a new count image: every product that reads the old one must be done, i.e. those of the last stage issued
+                if (!first && lane == 0) pgm_mbar_wait(pgm_smem(&s_empty[sprev]), phprev);
+                __syncwarp();
                 const uint8_t *img = a.images + (size_t)r.n * PG_MMA_IMG;
                 const int pieces = 128 * ((r.n + 31) & ~31) / 16;
-                for (int i = p; i < pieces; i += PG_MMA_NPROD) pgm_cp16(pgm_smem(sA) + (uint32_t)i * 16u, img + (size_t)i * 16);
+                for (int i = p; i < pieces; i += PG_MMA_NPROD) PGM_CP16(pgm_smem(sA) + (uint32_t)i * 16u, img + (size_t)i * 16);
                 cur_n = r.n;
             }
-            pgm_mbar_wait(pgm_smem(&s_empty[s]), ((it / PG_MMA_STAGES) & 1u) ^ 1u);   // the ring slot is free
-            if (kc * PG_MMA_KC + jr < r.n) {
-                const int blk = r.gs / PG_PARTS;
-                const uint32_t dst0 = pgm_smem(ring) + s * stage_bytes + (uint32_t)jr * 16u;
-                for (int c = c0; c < nch; c += PG_MMA_NPROD / PG_MMA_KC) {
-                    const uint8_t *src;
-                    if (c < 2) src = a.qx + ((size_t)r.gs * PG_NWORDS + wid) * 32 + c * 16;
-                    else if (c < nch - 1) src = a.bm8x + (size_t)wid * a.pitch8 + (c - 2) * 16;
-                    else src = a.hm8x + (size_t)wid * a.hpitch + (blk >> 2) * 16;
-                    pgm_cp16(dst0 + (uint32_t)c * (PG_MMA_KC * 16u), src);
-                }
-            }
-            asm volatile("cp.async.commit_group;\n" ::: "memory");
-            if (owe) {
-                asm volatile("cp.async.wait_group 1;\n" ::: "memory");               // everything but the stage just issued has landed
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");       // generic-proxy writes -> the tensor core's reads
-                pgm_mbar_arrive(pgm_smem(&s_full[(it - 1) % PG_MMA_STAGES]));
-            }
-            owe = true;
-            it++;
-            r = rn; kc = kcn; have = have_n; wid = wid_n;
-        }
-        if (owe) {
-            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-            pgm_mbar_arrive(pgm_smem(&s_full[(it - 1) % PG_MMA_STAGES]));
-        }
-    } else if (warp == 4) {
-        // ================================================================ the issuing thread
-        if (lane == 0) {
-            const uint32_t idesc = (2u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | (8u << 24);   // u8 x u8 -> s32, B MN-major, M = 128
-            const uint64_t adesc0 = pgm_desc(pgm_smem(sA), 2048u, 128u);             // K chunks 2 048 B apart, row groups 128 B
-            int slot = (int)blockIdx.x;
-            unsigned it = 0, rd = 0;
-            PgMmaRead r;
-            while (pgm_next_read(a, slot, r)) {
-                const unsigned acc = rd & 1u;
-                pgm_mbar_wait(pgm_smem(&s_dempty[acc]), ((rd >> 1) & 1u) ^ 1u);       // the epilogue has drained this buffer
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                const uint32_t dcol = tmem + acc * 256u;
-                const int nks = (r.n + 31) >> 5;
-                for (int ks0 = 0; ks0 < nks; ks0 += PG_MMA_KC / 32) {
-                    const unsigned s = it % PG_MMA_STAGES;
-                    pgm_mbar_wait(pgm_smem(&s_full[s]), (it / PG_MMA_STAGES) & 1u);
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    // words 8 apart 128 B apart (leading), 16-column chunks PG_MMA_KC * 16 B apart (stride)
-                    const uint64_t bdesc0 = pgm_desc(pgm_smem(ring) + s * stage_bytes, 128u, PG_MMA_KC * 16u);
+            const uint8_t *qrow = a.qx + (size_t)r.gs * PG_NWORDS * 32 + sub * 16;
+            const int sibc = ((r.gs / PG_PARTS) >> 2) * 16;
 #pragma unroll
-                    for (int u = 0; u < PG_MMA_KC / 32; u++) {
-                        const int ks = ks0 + u;
-                        if (ks < nks)
-                            pgm_mma_i8(dcol, adesc0 + (uint64_t)(ks * (4096 >> 4)), bdesc0 + (uint64_t)(u * (512 >> 4)), idesc, ks > 0 ? 1u : 0u);
-                    }
-                    pgm_commit(pgm_smem(&s_empty[s]));                                // the slot is free once these products are done
-                    it++;
+            for (int kc = 0; kc < MAXST; kc++) {
+                if (kc * PG_MMA_KC >= r.n) break;
+                const long long tw0 = a.prof ? clock64() : 0;
+                if (lane == 0) pgm_mbar_wait(pgm_smem(&s_empty[s]), ph);             // the ring slot is free
+                __syncwarp();
+                if (a.prof) t_wait += clock64() - tw0;
+                if (kc * PG_MMA_KC + jr < r.n) {
+                    const uint32_t wid = w[kc];
+                    const uint32_t dst0 = pgm_smem(ring) + s * stage_bytes + (uint32_t)jr * 16u;
+                    PGM_CP16(dst0 + (uint32_t)sub * (PG_MMA_KC * 16u), qrow + (size_t)wid * 32);
+                    const uint8_t *brow = a.bm8x + (size_t)wid * a.pitch8;
+                    for (int c = sub; c < nb8; c += 2) PGM_CP16(dst0 + (uint32_t)(2 + c) * (PG_MMA_KC * 16u), brow + c * 16);
+                    if (sub == (nb8 & 1)) PGM_CP16(dst0 + (uint32_t)(2 + nb8) * (PG_MMA_KC * 16u), a.hm8x + (size_t)wid * a.hpitch + sibc);
                 }
-                pgm_commit(pgm_smem(&s_dfull[acc]));
-                rd++;
+                // This thread's arrival fires when its copies have landed; the thread itself never waits for data, so a
+                // whole ring of stages is in flight.  (Waiting per stage -- cp.async.wait_group, then fence.proxy.async --
+                // cost 1 700 cycles a stage: the fence waits for every copy in flight, not just the stage being signalled.)
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(pgm_smem(&s_full[s])) : "memory");
+                sprev = s; phprev = ph ^ 1u; first = false;
+                if (++s == a.nstage) { s = 0; ph ^= 1u; }
+                nst_total++;
             }
+            r = rn; rn = rnn; have = have_n; have_n = have_nn;
+#pragma unroll
+            for (int i = 0; i < MAXST; i++) { w[i] = wn[i]; wn[i] = wnn[i]; }
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        if (a.prof && p == 0) { a.prof[blockIdx.x * 16 + 0] = clock64() - t_all; a.prof[blockIdx.x * 16 + 1] = t_wait; a.prof[blockIdx.x * 16 + 7] = nst_total; }
+    } else if (warp == 4) {
+        // ================================================================ the issuing warp
+        // The whole warp walks the loop (so every operand of tcgen05.mma is warp-uniform and lives in uniform
+        // registers); one elected lane issues.  With a single lane inside `if (lane == 0)` the compiler wrapped every
+        // product in a divergence loop and ~12 register-to-uniform moves: 150 cycles per instruction.
+        const uint32_t idesc = (2u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | (8u << 24);   // u8 x u8 -> s32, B MN-major, M = 128
+        const uint32_t a_lo = ((pgm_smem(sA) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);               // K chunks 2 048 B apart (leading)
+        const uint32_t a_hi = (128u >> 4) | (1u << 14);                                            // row groups 128 B apart (stride); version 1
+        const uint32_t b_hi = ((PG_MMA_KC * 16u) >> 4) | (1u << 14);                               // 16-column chunks PG_MMA_KC * 16 B apart
+        const uint32_t b_lo0 = ((pgm_smem(ring) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);             // words 8 apart 128 B apart
+        unsigned s = 0, ph = 0u, rd = 0;
+        PgMmaCursor cur;
+        cur.start(a);
+        PgMmaRead r;
+        long long t_wd = 0, t_wf = 0, t_fence = 0, t_all = clock64();
+        while (cur.next(a, r)) {
+            const unsigned acc = rd & 1u;
+            long long tw0 = a.prof ? clock64() : 0;
+            if (lane == 0) pgm_mbar_wait(pgm_smem(&s_dempty[acc]), ((rd >> 1) & 1u) ^ 1u);          // the epilogue has drained this buffer
+            __syncwarp();
+            if (a.prof) t_wd += clock64() - tw0;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t dcol = tmem + acc * 256u;
+            const int nks = (r.n + 31) >> 5;
+            uint32_t alo = a_lo;
+            for (int ks0 = 0; ks0 < nks; ks0 += PG_MMA_KC / 32) {
+                tw0 = a.prof ? clock64() : 0;
+                if (lane == 0) pgm_mbar_wait(pgm_smem(&s_full[s]), ph);
+                __syncwarp();
+                if (a.prof) t_wf += clock64() - tw0;
+                // the rows were written through the generic proxy (cp.async) and are read through the async proxy
+                tw0 = a.prof ? clock64() : 0;
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                if (a.prof) t_fence += clock64() - tw0;
+                const uint32_t blo = b_lo0 + s * (stage_bytes >> 4);
+                const int left = nks - ks0;
+                if (pgm_elect()) {
+#pragma unroll
+                    for (int u = 0; u < PG_MMA_KC / 32; u++)
+                        if (u < left)
+                            pgm_mma_i8(dcol, ((uint64_t)a_hi << 32) | (alo + (uint32_t)u * (4096u >> 4)),
+                                       ((uint64_t)b_hi << 32) | (blo + (uint32_t)u * (512u >> 4)), idesc, (ks0 + u) > 0 ? 1u : 0u);
+                    pgm_commit(pgm_smem(&s_empty[s]));                                // the slot is free once these products are done
+                    if (ks0 + PG_MMA_KC / 32 >= nks) pgm_commit(pgm_smem(&s_dfull[acc]));
+                }
+                __syncwarp();
+                alo += (PG_MMA_KC / 32) * (4096u >> 4);
+                if (++s == a.nstage) { s = 0; ph ^= 1u; }
+            }
+            rd++;
+        }
+        if (a.prof && lane == 0) {
+            a.prof[blockIdx.x * 16 + 2] = clock64() - t_all; a.prof[blockIdx.x * 16 + 3] = t_wd; a.prof[blockIdx.x * 16 + 4] = t_wf;
+            a.prof[blockIdx.x * 16 + 8] = t_fence;
         }
     } else {
         // ================================================================ epilogue: thread = task
+        // No CTA-wide barrier: a warp counts its open pairs, reserves room in the global item list from its own
+        // reservation (one returning global atomic per ~35 reads) and writes them itself; the four warps of a read meet
+        // only in three shared-memory counters (items so far, near-ties so far, warps done), all updated BEFORE the
+        // warp hands the accumulator back, so the next read on the same buffer finds them reset.
         const int t = tid;
-        int slot = (int)blockIdx.x;
         unsigned rd = 0;
+        PgMmaCursor cur;
+        cur.start(a);
         PgMmaRead r;
-        while (pgm_next_read(a, slot, r)) {
+        long long t_wd = 0, t_ld = 0, t_cmp = 0, t_all = clock64();
+        unsigned int chunk_pos = 0u, chunk_end = 0u;     // lane 0: this warp's reservation in the global item list
+        unsigned int nitems = 0u;                        // lane 0: pairs this warp wrote
+        while (cur.next(a, r)) {
             const unsigned acc = rd & 1u;
             const size_t rc = (size_t)a.slot0 + r.slot;
             const int n = r.n;
@@ -397,15 +503,24 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             const bool live = t == 0 || (t <= PG_NUM_BOOT && k > 0);
             const int best = r.gs / PG_PARTS, own = r.gs % PG_PARTS;
             const uint32_t gbase = (uint32_t)best * 64u, poff = (uint32_t)own * PG_PART_POS;
-            const uint32_t vb16 = (uint32_t)(a.blockmask[best] >> poff) & 0xFFFFu;
-            const uint32_t margin = pg_margin(t == 0 ? n : k, a.vmax);
-            pgm_mbar_wait(pgm_smem(&s_dfull[acc]), (rd >> 1) & 1u);
+            const uint32_t vb16 = r.vb16;
+            const uint32_t margin = t == 0 ? r.margin_full : r.margin_rep;
+            const long long tw0 = a.prof ? clock64() : 0;
+            if (lane == 0) pgm_mbar_wait(pgm_smem(&s_dfull[acc]), (rd >> 1) & 1u);     // one lane polls: the polls share the
+            __syncwarp();                                                             // shared-memory port with the operands
+            if (a.prof) t_wd += clock64() - tw0;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             const uint32_t trow = tmem + acc * 256u + ((uint32_t)(warp * 32) << 16);
-            uint32_t lo[16], hi[16];
+            const int nbc = a.pitch8 / 16;               // chunks of 16 block columns; one more chunk holds the sibling parts
+            uint32_t lo[16], hi[16], v0[16], v1[16], v2[16];
             PGM_LD16(trow, lo);
             PGM_LD16(trow + 16u, hi);
+            PGM_LD16(trow + 32u, v0);
+            PGM_LD16(trow + 48u, v1);
+            if (nbc >= 2) PGM_LD16(trow + 64u, v2);      // (warp-uniform)
             PGM_LD_WAIT();
+            long long tp = a.prof ? clock64() : 0;
+            if (a.prof) t_ld += tp - tw0;
             // ---- the part's champion and near-ties (k_classify_h's epilogue; the slot is still empty)
             uint32_t sum[16], bkey = 0xFFFFFFFFu;
 #pragma unroll
@@ -416,78 +531,125 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             }
             const uint32_t csum = bkey >> 6, cpos = bkey & 63u;
             const uint32_t thr = csum + margin;
-            unsigned int *lcnt = &s_cnt[acc];
-            uint32_t *list = s_list[acc];
+            uint32_t tie = 0u;
             if (live) {
                 a.champ[rc * (PG_NUM_BOOT + 1) + t] = ((unsigned long long)csum << 32) | (gbase + cpos);
 #pragma unroll
-                for (int i = 0; i < 16; i++)
-                    if (((vb16 >> i) & 1u) && sum[i] <= thr && poff + (uint32_t)i != cpos)
-                        pg_emit(a.ncand + rc, a.cand + rc * PG_CANDCAP, t, gbase + poff + (uint32_t)i, sum[i]);
+                for (int i = 0; i < 16; i++) tie |= (sum[i] <= thr ? 1u : 0u) << i;
+                tie &= vb16 & ~(1u << ((cpos - poff) & 31u));
             }
-            // ---- bound columns: 4 * D <= the smallest genus sum of the block
+            if (__any_sync(0xffffffffu, tie != 0u)) {
+                // near-ties: dense entries of the read's list, positions from a shared counter (this kernel is the
+                // read's first writer: the list starts empty)
+                const uint32_t mine = __popc(tie);
+                uint32_t incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+                uint32_t pos = 0u;
+                if (lane == 31) pos = atomicAdd(&s_ntie[acc], incl);
+                pos = __shfl_sync(0xffffffffu, pos, 31) + incl - mine;
+                while (tie) {
+                    const int i = __ffs(tie) - 1;
+                    tie &= tie - 1u;
+                    uint32_t sv = 0u;
+#pragma unroll
+                    for (int u = 0; u < 16; u++)
+                        if (u == i) sv = sum[u];
+                    if (pos < PG_CANDCAP)
+                        a.cand[rc * PG_CANDCAP + pos] = ((unsigned long long)t << 56) | ((unsigned long long)(gbase + poff + (uint32_t)i) << 32) | sv;
+                    pos++;
+                }
+            }
+            // ---- bound columns: 4 * D <= the smallest genus sum of the block.  Open pairs of up to three chunks at a time:
+            // bit i of m[j] = column i of chunk cc + j is within the threshold and names a competitor
             const uint32_t thr8 = thr >> PG_X8_SHIFT;
-            for (int cc = 0; cc < a.pitch8 / 16; cc++) {
-                uint32_t v[16];
-                PGM_LD16(trow + 32u + (uint32_t)cc * 16u, v);
-                PGM_LD_WAIT();
-                if (!live) continue;
+            auto mask16 = [&](const uint32_t (&v)[16], int cc) -> uint32_t {
                 uint32_t open = 0u;
 #pragma unroll
                 for (int i = 0; i < 16; i++) open |= (v[i] <= thr8 ? 1u : 0u) << i;
-                while (open) {
-                    const int i = __ffs(open) - 1;
-                    open &= open - 1u;
-                    const int b = cc * 16 + i;
-                    if (b < a.ntile64 && b != best) {
-                        const unsigned int pos = atomicAdd(lcnt, 1u);
-                        if (pos < PG_MMA_LIST) list[pos] = ((uint32_t)t << 16) | (uint32_t)b;
-                    }
-                }
-            }
-            {
-                uint32_t v[16];
-                PGM_LD16(trow + 32u + (uint32_t)a.pitch8, v);
-                PGM_LD_WAIT();
-                if (live) {
+                if (!live || cc > nbc) return 0u;
+                if (cc == nbc) {                          // the part minima around the best block: its 3 sibling parts
                     const int q4 = (best & 3) * 4;
+                    return open & (0xFu << q4) & ~(1u << (q4 + own));
+                }
+                const int left = a.ntile64 - cc * 16;     // real blocks in this chunk
+                if (left < 16) open &= (1u << (left > 0 ? left : 0)) - 1u;
+                if ((best >> 4) == cc) open &= ~(1u << (best & 15));
+                return open;
+            };
+            auto push = [&](uint32_t m0, uint32_t m1, uint32_t m2, int cc) {
+                const uint32_t mine = __popc(m0) + __popc(m1) + __popc(m2);
+                uint32_t incl = mine;
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int part = i - q4;
-                        if (part >= 0 && part < PG_PARTS && part != own && v[i] <= thr8) {
-                            const unsigned int pos = atomicAdd(lcnt, 1u);
-                            if (pos < PG_MMA_LIST) list[pos] = ((uint32_t)t << 16) | 0x8000u | ((uint32_t)part << 13) | (uint32_t)best;
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                if (tot == 0u) return;
+                uint32_t base = 0xFFFFFFFFu;
+                if (lane == 0 && atomicAdd(&s_cnt[acc], tot) + tot > a.light_max) a.heavy[rc] = 1;   // too many open pairs: plan 1 redoes the read
+                else if (lane == 0) {
+                    if (tot > chunk_end - chunk_pos) {
+                        // what the old reservation leaves unused is blanked: k_light skips blank entries
+                        for (unsigned int i = chunk_pos; i < chunk_end; i++) a.items[i] = (unsigned long long)PG_ITEM_NULL << 16;
+                        const unsigned int want = tot > PG_MMA_RESERVE ? tot : PG_MMA_RESERVE;
+                        chunk_pos = atomicAdd(a.item_count, want);
+                        chunk_end = chunk_pos + want;
+                        if (chunk_pos > a.item_cap || want > a.item_cap - chunk_pos) {      // the list is full: blank what fits, redo the read
+                            for (unsigned int i = chunk_pos; i < a.item_cap && i < chunk_end; i++) a.items[i] = (unsigned long long)PG_ITEM_NULL << 16;
+                            chunk_pos = chunk_end = 0u;
                         }
                     }
+                    if (tot <= chunk_end - chunk_pos) { base = chunk_pos; chunk_pos += tot; nitems += tot; }
+                    else a.heavy[rc] = 1;
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base == 0xFFFFFFFFu) return;
+                unsigned long long *out = a.items + base + (incl - mine);
+                const unsigned long long head = ((unsigned long long)rc << 32) | ((unsigned long long)t << 16);
+                const uint32_t mm[3] = {m0, m1, m2};
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    uint32_t m = mm[j];
+                    while (m) {
+                        const int i = __ffs(m) - 1;
+                        m &= m - 1u;
+                        const uint32_t field = (cc + j == nbc) ? (0x8000u | ((uint32_t)(i - (best & 3) * 4) << 13) | (uint32_t)best)
+                                                               : (uint32_t)((cc + j) * 16 + i);
+                        *out++ = head | field;
+                    }
+                }
+            };
+            push(mask16(v0, 0), mask16(v1, 1), nbc >= 2 ? mask16(v2, 2) : 0u, 0);
+            for (int cc = 3; cc <= nbc; cc += 3) {       // large models: three more chunks per round trip
+                PGM_LD16(trow + 32u + (uint32_t)cc * 16u, v0);
+                if (cc + 1 <= nbc) PGM_LD16(trow + 32u + (uint32_t)(cc + 1) * 16u, v1);
+                if (cc + 2 <= nbc) PGM_LD16(trow + 32u + (uint32_t)(cc + 2) * 16u, v2);
+                PGM_LD_WAIT();
+                push(mask16(v0, cc), mask16(v1, cc + 1), mask16(v2, cc + 2), cc);
+            }
+            // ---- the last warp of the read publishes the near-tie count and resets the shared counters
+            if (lane == 0) {
+                __threadfence_block();
+                if (atomicAdd(&s_wdone[acc], 1u) == 3u) {
+                    __threadfence_block();
+                    a.ncand[rc] = s_ntie[acc];           // more than PG_CANDCAP: phase 2 hands the read to the strict kernels
+                    s_ntie[acc] = 0u; s_cnt[acc] = 0u; s_wdone[acc] = 0u;
+                    __threadfence_block();
                 }
             }
-            // the accumulator is read: hand the buffer back to the issuing thread
+            __syncwarp();
+            if (a.prof) t_cmp += clock64() - tp;
+            // the accumulator is read and the counters are settled: hand the buffer back to the issuing thread
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             pgm_mbar_arrive(pgm_smem(&s_dempty[acc]));
-            // ---- the read's open pairs -> the global item list (one atomic per read), or the read is heavy
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");
-            const unsigned int cnt = *lcnt;
-            if (t == 0) {
-                unsigned int b = 0xFFFFFFFFu;
-                if (cnt <= a.light_max && cnt <= PG_MMA_LIST) {
-                    b = 0u;
-                    if (cnt > 0u) {
-                        b = atomicAdd(a.item_count, cnt);
-                        if (b > a.item_cap || cnt > a.item_cap - b) {      // buffer full: blank what fits, redo the read
-                            for (unsigned int i = b; i < a.item_cap && i < b + cnt; i++) a.items[i] = (unsigned long long)PG_ITEM_NULL << 16;
-                            b = 0xFFFFFFFFu;
-                        }
-                    }
-                }
-                if (b == 0xFFFFFFFFu) a.heavy[rc] = 1;
-                s_base = b;
-                s_cnt[acc ^ 1u] = 0u;                                      // the other list is idle until the next read
-            }
-            asm volatile("bar.sync 1, 128;\n" ::: "memory");
-            const unsigned int gb = s_base;
-            if (gb != 0xFFFFFFFFu)
-                for (unsigned int i = t; i < cnt; i += 128) a.items[gb + i] = ((unsigned long long)rc << 32) | list[i];
             rd++;
+        }
+        if (lane == 0) {
+            for (unsigned int i = chunk_pos; i < chunk_end; i++) a.items[i] = (unsigned long long)PG_ITEM_NULL << 16;
+            if (nitems) atomicAdd(a.items_total, nitems);
+        }
+        if (t == 0 && a.prof) {
+            a.prof[blockIdx.x * 16 + 5] = clock64() - t_all; a.prof[blockIdx.x * 16 + 6] = t_wd;
+            a.prof[blockIdx.x * 16 + 9] = t_ld; a.prof[blockIdx.x * 16 + 10] = t_cmp; a.prof[blockIdx.x * 16 + 11] = 0;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -516,14 +678,42 @@ int pg_mma_launch(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, 
     a.words = d_words; a.off = d_off; a.nwords = d_nwords; a.flags = d_flags; a.order = d_order;
     a.nreads_b = (int)nreads_b; a.slot0 = slot0; a.min_boot = min_boot; a.blockmask = md->d_blockmask; a.vmax = md->vmax;
     a.champ = cb.champ; a.ncand = cb.ncand; a.cand = cb.cand; a.guess = d_guess;
-    a.items = cb.items; a.item_count = cb.counters + 2; a.item_cap = cb.item_cap; a.heavy = cb.heavy; a.light_max = light_max;
+    a.items = cb.items; a.item_count = cb.counters + 2; a.items_total = cb.counters + 3; a.item_cap = cb.item_cap; a.heavy = cb.heavy; a.light_max = light_max;
     const int nch = 3 + md->pitch8 / 16;
-    size_t smem = (size_t)128 * a.kmax + (size_t)PG_MMA_STAGES * nch * PG_MMA_KC * 16;
+    PG_CUDA(ctx, pg_smem_unlock(ctx, k_mma_bound));
+    cudaFuncAttributes fa;
+    PG_CUDA(ctx, cudaFuncGetAttributes(&fa, k_mma_bound));
+    const size_t room = (size_t)ctx->smem_optin - fa.sharedSizeBytes - 1024, stage = (size_t)nch * PG_MMA_KC * 16;
+    size_t ns = (room - (size_t)128 * a.kmax) / stage;
+    if (ns > PG_MMA_MAXSTAGES) ns = PG_MMA_MAXSTAGES;
+    if (ns < 3) return pg_fail(ctx, PG_EINVAL, "internal: no room for the ring of the tensor-core kernel");
+    a.nstage = (unsigned)ns;
+    size_t smem = (size_t)128 * a.kmax + ns * stage;
     // the kernel owns all 512 columns of tensor memory: never two CTAs on one SM
     if (smem < (size_t)120 * 1024) smem = (size_t)120 * 1024;
-    PG_CUDA(ctx, pg_smem_unlock(ctx, k_mma_bound));
     const unsigned grid = nreads_b < (unsigned)ctx->sm_count ? nreads_b : (unsigned)ctx->sm_count;
+    const int nmeta = (int)nreads_b + (int)grid;
+    PG_TRY(pg_scratch(ctx, &ctx->s_meta, (size_t)nmeta * 2 * sizeof(int4) + (size_t)grid * 128));
+    int4 *d_meta = (int4 *)ctx->s_meta.p;
+    k_mma_meta<<<(nmeta + 255) / 256, 256, 0, ctx->stream>>>(d_off, d_nwords, d_flags, d_order, (int)nreads_b, slot0, d_guess, md->d_blockmask,
+                                                            min_boot, md->vmax, d_meta, nmeta);
+    PG_LAUNCHED(ctx);
+    a.meta = d_meta;
+    static int env_prof = -1;                            // PG_MMA_PROF=1: per-role cycle counters of every launch on stderr
+    if (env_prof < 0) { const char *e = getenv("PG_MMA_PROF"); env_prof = (e && atoi(e)) ? 1 : 0; }
+    a.prof = env_prof ? (long long *)(d_meta + 2 * nmeta) : NULL;
     k_mma_bound<<<grid, PG_MMA_THREADS, smem, ctx->stream>>>(a);
     PG_LAUNCHED(ctx);
+    if (env_prof) {
+        std::vector<long long> h((size_t)grid * 16);
+        PG_CUDA(ctx, pg_copy_sync(ctx, h.data(), a.prof, h.size() * 8, cudaMemcpyDeviceToHost));
+        double v[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (unsigned c = 0; c < grid; c++)
+            for (int i = 0; i < 16; i++) v[i] += (double)h[(size_t)c * 16 + i] / grid;
+        fprintf(stderr, "[k_mma_bound] %u reads, %u CTAs, N=%d: cycles per CTA: producer %.0f (waiting for a free slot %.0f, %.0f stages), "
+                        "issuer %.0f (waiting for the epilogue %.0f, for the producers %.0f, fences %.0f), epilogue %.0f (waiting for products %.0f incl. in "
+                        "loads %.0f, compare and push %.0f)\n",
+                nreads_b, grid, nch * 16, v[0], v[1], v[7], v[2], v[3], v[4], v[8], v[5], v[6], v[9], v[10]);
+    }
     return PG_OK;
 }

@@ -123,7 +123,37 @@ k_probe(const uint8_t *__restrict__ tabH, const uint8_t *__restrict__ tabL, cons
         __syncthreads();
         long long c0 = clock64();
         // ---- gather: plane[c][j][16] <- tab[w_j][16c .. 16c+15]
-        if (gm == 2) {
+        if (gm == 3) {
+            // 32 bytes per load (LDG.256), two 16-byte stores: do requests or bytes bound the gather?
+            const int total = n * (nchunk / 2);
+            for (int i0 = tid; i0 < total; i0 += 2 * blockDim.x) {
+                uint32_t vh[2][8], vl[2][8];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int i = i0 + u * blockDim.x;
+                    if (i < total) {
+                        const int j = i / (nchunk / 2), c2 = i - j * (nchunk / 2);
+                        const size_t src = (size_t)sw[j] * N + c2 * 32;
+                        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(vh[u][0]), "=r"(vh[u][1]), "=r"(vh[u][2]), "=r"(vh[u][3]),
+                                     "=r"(vh[u][4]), "=r"(vh[u][5]), "=r"(vh[u][6]), "=r"(vh[u][7]) : "l"(tabH + src));
+                        asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(vl[u][0]), "=r"(vl[u][1]), "=r"(vl[u][2]), "=r"(vl[u][3]),
+                                     "=r"(vl[u][4]), "=r"(vl[u][5]), "=r"(vl[u][6]), "=r"(vl[u][7]) : "l"(tabL + src));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int i = i0 + u * blockDim.x;
+                    if (i < total) {
+                        const int j = i / (nchunk / 2), c2 = i - j * (nchunk / 2);
+                        const uint32_t d0 = (uint32_t)((2 * c2) * Kpad + j) * 16, d1 = (uint32_t)((2 * c2 + 1) * Kpad + j) * 16;
+                        *reinterpret_cast<uint4 *>(sBh + d0) = make_uint4(vh[u][0], vh[u][1], vh[u][2], vh[u][3]);
+                        *reinterpret_cast<uint4 *>(sBh + d1) = make_uint4(vh[u][4], vh[u][5], vh[u][6], vh[u][7]);
+                        *reinterpret_cast<uint4 *>(sBl + d0) = make_uint4(vl[u][0], vl[u][1], vl[u][2], vl[u][3]);
+                        *reinterpret_cast<uint4 *>(sBl + d1) = make_uint4(vl[u][4], vl[u][5], vl[u][6], vl[u][7]);
+                    }
+                }
+            }
+        } else if (gm == 2) {
             const int total = n * nchunk;
             for (int i0 = tid; i0 < total; i0 += 4 * blockDim.x) {
                 uint4 vh[4], vl[4];
@@ -243,8 +273,8 @@ int main(int argc, char **argv)
     CK(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // CPU reference for a sample of reads
     std::vector<int32_t> out((size_t)nreads * 128 * N);
-    const int variants[2] = {0, 8 + 16 + 32};
-    for (int vi = 0; vi < 2; vi++) {
+    const int variants[4] = {0, 8 + 16 + 32, 768, 8 + 16 + 32 + 768};
+    for (int vi = 0; vi < 4; vi++) {
         const int variant = variants[vi];
         if ((variant & 4) && 2 * N + Kpad / 4 > 512) { printf("variant %d: A does not fit tensor memory beside D\n", variant); continue; }
         CK(cudaMemset(dOut, 0xEE, out.size() * 4)); CK(cudaMemset(dFail, 0, 4));
