@@ -30,9 +30,12 @@
 #define PG_MMA_MAXSTAGES 8                // ring depth: as many stages as shared memory holds, at least 3
 #define PG_MMA_IMG    (128 * PG_MMA_MAXN)   // bytes of one count image slot
 #define PG_MMA_NPROD  256                   // producer threads
-#define PG_MMA_THREADS (128 + 32 + PG_MMA_NPROD)
+#define PG_MMA_NEPI   128                   // epilogue threads.  256 = two groups of four warps taking the reads in turn (one per
+                                            // TMEM buffer) was measured: 96 registers and spills, more warps per scheduler: slower
+#define PG_MMA_THREADS (PG_MMA_NEPI + 32 + PG_MMA_NPROD)
 #define PG_MMA_LIST   2048                  // open pairs per read above which the read is "heavy" (default)
 #define PG_X8_SHIFT   2
+#define PG_MMA_WLIST  512                   // open pairs per (read, epilogue warp) above which the read is "heavy"
 #define PG_MMA_RESERVE 128                  // entries of the global item list an epilogue warp reserves at a time
 
 // ------------------------------------------------------------------ tables
@@ -185,11 +188,12 @@ __device__ __forceinline__ void pgm_mbar_arrive(uint32_t bar)
 // bounded wait: a protocol error must end the kernel with an error, never hang the device
 __device__ __forceinline__ void pgm_mbar_wait(uint32_t bar, uint32_t parity)
 {
-    for (unsigned spin = 0; spin < (1u << 28); spin++) {
+    for (unsigned spin = 0; spin < (1u << 26); spin++) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}\n"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;
+        __nanosleep(40);                                 // a waiting warp must not take issue slots from the working ones
     }
     __trap();
 }
@@ -322,7 +326,8 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_full[PG_MMA_MAXSTAGES], s_empty[PG_MMA_MAXSTAGES], s_dfull[2], s_dempty[2];
     __shared__ uint32_t s_tmem;
-    __shared__ unsigned int s_cnt[2], s_ntie[2], s_wdone[2];   // per accumulator buffer: open pairs, near-ties, epilogue warps done
+    __shared__ uint32_t s_wlist[PG_MMA_NEPI / 32][PG_MMA_WLIST];    // per epilogue warp: the open pairs of the read in hand
+    __shared__ unsigned int s_ntie[2], s_wdone[2];   // per accumulator buffer: near-ties so far, epilogue warps done
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nch = 3 + a.pitch8 / 16;                   // 16-column chunks of B
@@ -339,7 +344,6 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
         for (int s = 0; s < PG_MMA_MAXSTAGES; s++) { pgm_mbar_init(pgm_smem(&s_full[s]), PG_MMA_NPROD); pgm_mbar_init(pgm_smem(&s_empty[s]), 1); }
         for (int i = 0; i < 2; i++) { pgm_mbar_init(pgm_smem(&s_dfull[i]), 1); pgm_mbar_init(pgm_smem(&s_dempty[i]), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-        s_cnt[0] = s_cnt[1] = 0u;
         s_ntie[0] = s_ntie[1] = 0u;
         s_wdone[0] = s_wdone[1] = 0u;
     }
@@ -348,11 +352,11 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = s_tmem;
 
-    if (warp >= 5) {
+    if (warp > PG_MMA_NEPI / 32) {
         // ================================================================ producers
         // Thread p gathers row jr = p / 2 of every stage; lanes 2i and 2i + 1 fetch the two 16-byte halves of the same
         // 32-byte sector in one instruction (qx: low | high bytes; bm8x: two chunks of 16 blocks).
-        const int p = tid - 160, jr = p >> 1, sub = p & 1;
+        const int p = tid - (PG_MMA_NEPI + 32), jr = p >> 1, sub = p & 1;
         constexpr int MAXST = PG_MMA_MAXN / PG_MMA_KC;                       // stages of the longest read
         int cur_n = -1;
         unsigned s = 0, ph = 1u, sprev = 0, phprev = 0;  // ring slot of the next stage and the parity of its "free" phase
@@ -424,7 +428,7 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
         }
         asm volatile("cp.async.wait_all;\n" ::: "memory");
         if (a.prof && p == 0) { a.prof[blockIdx.x * 16 + 0] = clock64() - t_all; a.prof[blockIdx.x * 16 + 1] = t_wait; a.prof[blockIdx.x * 16 + 7] = nst_total; }
-    } else if (warp == 4) {
+    } else if (warp == PG_MMA_NEPI / 32) {
         // ================================================================ the issuing warp
         // The whole warp walks the loop (so every operand of tcgen05.mma is warp-uniform and lives in uniform
         // registers); one elected lane issues.  With a single lane inside `if (lane == 0)` the compiler wrapped every
@@ -486,16 +490,19 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
         // reservation (one returning global atomic per ~35 reads) and writes them itself; the four warps of a read meet
         // only in three shared-memory counters (items so far, near-ties so far, warps done), all updated BEFORE the
         // warp hands the accumulator back, so the next read on the same buffer finds them reset.
-        const int t = tid;
+        // group g = warp / 4 takes the reads whose products go to TMEM buffer g (every other read of the CTA)
+        const int t = tid & 127;
+        const unsigned grp = (unsigned)(warp >> 2);
         unsigned rd = 0;
         PgMmaCursor cur;
         cur.start(a);
         PgMmaRead r;
-        long long t_wd = 0, t_ld = 0, t_cmp = 0, t_all = clock64();
+        long long t_wd = 0, t_ld = 0, t_cmp = 0, t_ld2 = 0, t_all = clock64();
         unsigned int chunk_pos = 0u, chunk_end = 0u;     // lane 0: this warp's reservation in the global item list
         unsigned int nitems = 0u;                        // lane 0: pairs this warp wrote
         while (cur.next(a, r)) {
             const unsigned acc = rd & 1u;
+            if (PG_MMA_NEPI == 256 && acc != grp) { rd++; continue; }
             const size_t rc = (size_t)a.slot0 + r.slot;
             const int n = r.n;
             int k = n >> 3;
@@ -510,7 +517,7 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             __syncwarp();                                                             // shared-memory port with the operands
             if (a.prof) t_wd += clock64() - tw0;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            const uint32_t trow = tmem + acc * 256u + ((uint32_t)(warp * 32) << 16);
+            const uint32_t trow = tmem + acc * 256u + ((uint32_t)((warp & 3) * 32) << 16);
             const int nbc = a.pitch8 / 16;               // chunks of 16 block columns; one more chunk holds the sibling parts
             uint32_t lo[16], hi[16], v0[16], v1[16], v2[16];
             PGM_LD16(trow, lo);
@@ -564,10 +571,14 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             // bit i of m[j] = column i of chunk cc + j is within the threshold and names a competitor
             const uint32_t thr8 = thr >> PG_X8_SHIFT;
             auto mask16 = [&](const uint32_t (&v)[16], int cc) -> uint32_t {
+                // nearly every chunk has no column within the threshold (~1 % of the (task, chunk) pairs do): one
+                // minimum and one compare settle those
+                const uint32_t m01 = min(min(v[0], v[1]), min(v[2], v[3])), m23 = min(min(v[4], v[5]), min(v[6], v[7]));
+                const uint32_t m45 = min(min(v[8], v[9]), min(v[10], v[11])), m67 = min(min(v[12], v[13]), min(v[14], v[15]));
+                if (!live || cc > nbc || min(min(m01, m23), min(m45, m67)) > thr8) return 0u;
                 uint32_t open = 0u;
 #pragma unroll
                 for (int i = 0; i < 16; i++) open |= (v[i] <= thr8 ? 1u : 0u) << i;
-                if (!live || cc > nbc) return 0u;
                 if (cc == nbc) {                          // the part minima around the best block: its 3 sibling parts
                     const int q4 = (best & 3) * 4;
                     return open & (0xFu << q4) & ~(1u << (q4 + own));
@@ -577,34 +588,24 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
                 if ((best >> 4) == cc) open &= ~(1u << (best & 15));
                 return open;
             };
+            // Open pairs go to the warp's own list in shared memory first (positions from ballots, no atomics), and from
+            // there to the global item list once per read: one reservation, coalesced stores.
+            unsigned int wcount = 0u;                    // warp-uniform: pairs of this read so far
+            uint32_t *wl = s_wlist[warp];
             auto push = [&](uint32_t m0, uint32_t m1, uint32_t m2, int cc) {
                 const uint32_t mine = __popc(m0) + __popc(m1) + __popc(m2);
-                uint32_t incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
-                const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t tot = __reduce_add_sync(0xffffffffu, mine);
                 if (tot == 0u) return;
-                uint32_t base = 0xFFFFFFFFu;
-                if (lane == 0 && atomicAdd(&s_cnt[acc], tot) + tot > a.light_max) a.heavy[rc] = 1;   // too many open pairs: plan 1 redoes the read
-                else if (lane == 0) {
-                    if (tot > chunk_end - chunk_pos) {
-                        // what the old reservation leaves unused is blanked: k_light skips blank entries
-                        for (unsigned int i = chunk_pos; i < chunk_end; i++) a.items[i] = (unsigned long long)PG_ITEM_NULL << 16;
-                        const unsigned int want = tot > PG_MMA_RESERVE ? tot : PG_MMA_RESERVE;
-                        chunk_pos = atomicAdd(a.item_count, want);
-                        chunk_end = chunk_pos + want;
-                        if (chunk_pos > a.item_cap || want > a.item_cap - chunk_pos) {      // the list is full: blank what fits, redo the read
-                            for (unsigned int i = chunk_pos; i < a.item_cap && i < chunk_end; i++) a.items[i] = (unsigned long long)PG_ITEM_NULL << 16;
-                            chunk_pos = chunk_end = 0u;
-                        }
-                    }
-                    if (tot <= chunk_end - chunk_pos) { base = chunk_pos; chunk_pos += tot; nitems += tot; }
-                    else a.heavy[rc] = 1;
+                // exclusive prefix of `mine` over the lanes: counts are small (mostly 0 or 1): a ballot per level
+                uint32_t pos = wcount;
+                const uint32_t below = (1u << lane) - 1u;
+                for (uint32_t lvl = 1u;; lvl++) {
+                    const uint32_t bal = __ballot_sync(0xffffffffu, mine >= lvl);
+                    if (bal == 0u) break;
+                    pos += __popc(bal & below);
                 }
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (base == 0xFFFFFFFFu) return;
-                unsigned long long *out = a.items + base + (incl - mine);
-                const unsigned long long head = ((unsigned long long)rc << 32) | ((unsigned long long)t << 16);
+                wcount += tot;
+                if (mine == 0u) return;
                 const uint32_t mm[3] = {m0, m1, m2};
 #pragma unroll
                 for (int j = 0; j < 3; j++) {
@@ -614,25 +615,56 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
                         m &= m - 1u;
                         const uint32_t field = (cc + j == nbc) ? (0x8000u | ((uint32_t)(i - (best & 3) * 4) << 13) | (uint32_t)best)
                                                                : (uint32_t)((cc + j) * 16 + i);
-                        *out++ = head | field;
+                        if (pos < PG_MMA_WLIST) wl[pos] = ((uint32_t)t << 16) | field;
+                        pos++;
                     }
                 }
             };
             push(mask16(v0, 0), mask16(v1, 1), nbc >= 2 ? mask16(v2, 2) : 0u, 0);
             for (int cc = 3; cc <= nbc; cc += 3) {       // large models: three more chunks per round trip
+                const long long tl0 = a.prof ? clock64() : 0;
                 PGM_LD16(trow + 32u + (uint32_t)cc * 16u, v0);
                 if (cc + 1 <= nbc) PGM_LD16(trow + 32u + (uint32_t)(cc + 1) * 16u, v1);
                 if (cc + 2 <= nbc) PGM_LD16(trow + 32u + (uint32_t)(cc + 2) * 16u, v2);
                 PGM_LD_WAIT();
+                if (a.prof) {                             // a consumer of the loaded registers, so the clock is read after they arrive
+                    uint32_t sink;
+                    asm volatile("add.u32 %0, %1, %2;" : "=r"(sink) : "r"(v0[0] + v0[15]), "r"(v1[0] + v1[15]));
+                    t_ld2 += (clock64() - tl0) + (sink == 0xFFFFFFFFu ? 1 : 0);
+                }
                 push(mask16(v0, cc), mask16(v1, cc + 1), mask16(v2, cc + 2), cc);
+            }
+            if (wcount) {
+                uint32_t base = 0xFFFFFFFFu;
+                if (lane == 0) {
+                    if (wcount > a.light_max || wcount > PG_MMA_WLIST) a.heavy[rc] = 1;      // too many open pairs: plan 1 redoes the read
+                    else {
+                        if (wcount > chunk_end - chunk_pos) {
+                            // what the old reservation leaves unused is blanked: k_light skips blank entries
+                            for (unsigned int i = chunk_pos; i < chunk_end; i++) a.items[i] = (unsigned long long)PG_ITEM_NULL << 16;
+                            const unsigned int want = wcount > PG_MMA_RESERVE ? wcount : PG_MMA_RESERVE;
+                            chunk_pos = atomicAdd(a.item_count, want);
+                            chunk_end = chunk_pos + want;
+                            if (chunk_pos > a.item_cap || want > a.item_cap - chunk_pos) {  // the list is full: blank what fits, redo the read
+                                for (unsigned int i = chunk_pos; i < a.item_cap && i < chunk_end; i++) a.items[i] = (unsigned long long)PG_ITEM_NULL << 16;
+                                chunk_pos = chunk_end = 0u;
+                            }
+                        }
+                        if (wcount <= chunk_end - chunk_pos) { base = chunk_pos; chunk_pos += wcount; nitems += wcount; }
+                        else a.heavy[rc] = 1;
+                    }
+                }
+                base = __shfl_sync(0xffffffffu, base, 0);           // (also orders the list's writes before its reads)
+                if (base != 0xFFFFFFFFu)
+                    for (unsigned int i = lane; i < wcount; i += 32) a.items[base + i] = ((unsigned long long)rc << 32) | wl[i];
+                __syncwarp();
             }
             // ---- the last warp of the read publishes the near-tie count and resets the shared counters
             if (lane == 0) {
                 __threadfence_block();
                 if (atomicAdd(&s_wdone[acc], 1u) == 3u) {
-                    __threadfence_block();
-                    a.ncand[rc] = s_ntie[acc];           // more than PG_CANDCAP: phase 2 hands the read to the strict kernels
-                    s_ntie[acc] = 0u; s_cnt[acc] = 0u; s_wdone[acc] = 0u;
+                    a.ncand[rc] = atomicExch(&s_ntie[acc], 0u);      // more than PG_CANDCAP: phase 2 hands the read to the strict kernels
+                    s_wdone[acc] = 0u;
                     __threadfence_block();
                 }
             }
@@ -647,9 +679,9 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             for (unsigned int i = chunk_pos; i < chunk_end; i++) a.items[i] = (unsigned long long)PG_ITEM_NULL << 16;
             if (nitems) atomicAdd(a.items_total, nitems);
         }
-        if (t == 0 && a.prof) {
+        if (tid == 0 && a.prof) {
             a.prof[blockIdx.x * 16 + 5] = clock64() - t_all; a.prof[blockIdx.x * 16 + 6] = t_wd;
-            a.prof[blockIdx.x * 16 + 9] = t_ld; a.prof[blockIdx.x * 16 + 10] = t_cmp; a.prof[blockIdx.x * 16 + 11] = 0;
+            a.prof[blockIdx.x * 16 + 9] = t_ld; a.prof[blockIdx.x * 16 + 10] = t_cmp; a.prof[blockIdx.x * 16 + 11] = t_ld2;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -712,8 +744,8 @@ int pg_mma_launch(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, 
             for (int i = 0; i < 16; i++) v[i] += (double)h[(size_t)c * 16 + i] / grid;
         fprintf(stderr, "[k_mma_bound] %u reads, %u CTAs, N=%d: cycles per CTA: producer %.0f (waiting for a free slot %.0f, %.0f stages), "
                         "issuer %.0f (waiting for the epilogue %.0f, for the producers %.0f, fences %.0f), epilogue %.0f (waiting for products %.0f incl. in "
-                        "loads %.0f, compare and push %.0f)\n",
-                nreads_b, grid, nch * 16, v[0], v[1], v[7], v[2], v[3], v[4], v[8], v[5], v[6], v[9], v[10]);
+                        "loads %.0f, compare and push %.0f of which later loads %.0f)\n",
+                nreads_b, grid, nch * 16, v[0], v[1], v[7], v[2], v[3], v[4], v[8], v[5], v[6], v[9], v[10], v[11]);
     }
     return PG_OK;
 }
