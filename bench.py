@@ -738,7 +738,8 @@ def main():
             # measure distance to the hardware ceiling for this path (L1 data pipe of the dominant kernel).
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": ("certified phase 1 = k_guess_bm + k_classify_h (best part of the best block) + k_bound + k_light, timed as one group"
+                         "kernel": ("certified phase 1 = k_guess_bm + k_mma_meta + k_mma_bound (best part of the best block and the block "
+                                    "bounds: one u8 x u8 -> s32 tcgen05 product per read, accumulators in tensor memory) + k_light, timed as one group"
                                     if args.mode == 1 else "k_classify_strict"),
                          "kernel_ms_per_launch": kms / max(klaunch, 1),
                          "kernel_share_of_step": kms / ms if ms > 0 else None,

@@ -172,13 +172,17 @@ typedef struct {
     int32_t mode;             /* 0 = strict (reference order);
                                  1 = certified (quantised pre-filter, strict re-check)  */
     int32_t cert_plan;        /* certified mode only, results never depend on it:
-                                 0 = default (better half of the best block + lower bounds + items),
+                                 0 = default: best 16-position part of the best block + lower bounds of every other
+                                     block as one integer matrix product per read on the tensor cores (tcgen05,
+                                     reads of up to 640 good words; longer reads as 3), then the open pairs exactly,
                                  1 = every genus block with partial-sum pruning,
-                                 2 = the whole best block + lower bounds + items         */
+                                 2 = the whole best block + lower bounds + items,
+                                 3 = as 0 with the shared-memory kernels (the default of round 1/2) */
     int32_t light_max;        /* cert_plan 0: open (task, block) pairs per read above which the
                                  read is redone under cert_plan 1; 0 = default, -1 = none */
-    int32_t bound_level;      /* cert_plan 0 only, results never depend on it: which kernel bounds the blocks the
-                                 best part leaves: 0 or 1 = the 16-bit bounds, one CTA per (read, group of 28 blocks);
+    int32_t bound_level;      /* cert_plan 0 / 3, results never depend on it: which kernel bounds the blocks the
+                                 best part leaves: 0 = the plan's own (tensor cores under cert_plan 0); any other value
+                                 selects cert_plan 3 with: 1 = the 16-bit bounds, one CTA per (read, group of 28 blocks);
                                  2 = a coarse 8-bit first level over all blocks + an exact second level (measured
                                  no faster on 10 000 genera, kept for models with many more groups); 3 = the 16-bit
                                  bounds over the table's 16-position PARTS instead of its 64-position blocks (four times
@@ -200,6 +204,9 @@ int pg_classify_stats(const pg_ctx *ctx, int64_t *certified_reads, int64_t *stri
  * lower bounds left too many (task, block) pairs open, and the number of such pairs ("items")
  * evaluated exactly for the other reads. */
 int pg_classify_stats2(const pg_ctx *ctx, int64_t *heavy_reads, int64_t *items);
+/* Reads of the last call whose best part and block bounds were computed by the tensor-core kernel (certified mode's
+ * default plan, reads of up to 640 good words); the others went through the shared-memory kernels of plan 3. */
+int pg_classify_stats3(const pg_ctx *ctx, int64_t *tensor_core_reads);
 
 /* K3-K5: word extraction + orientation, gather-sum + 100 bootstraps, argmax,
  * vote.  results: nreads records (host for pg_classify, device for *_dev).

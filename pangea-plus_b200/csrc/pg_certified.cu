@@ -1878,6 +1878,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
         PG_CUDA(ctx, cudaMemsetAsync(cb.counters + 2, 0, 4, ctx->stream));
         const unsigned int lm = cb.light_max == 0 ? 2048u : (cb.light_max < 0 ? 0u : (unsigned int)cb.light_max);
         PG_TRY(pg_mma_launch(ctx, md, nreads_b, nmax, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb, d_guess, lm));
+        if (cb.count_mma) ctx->st_mma += nreads_b;
     } else if (d_guess && version == 3) {
         const unsigned npair = (nreads_b + PG_PARTS - 1) / PG_PARTS;
 #define PG_LAUNCH_H(B, M)                                                                                               \

@@ -226,7 +226,7 @@ static __global__ void k_words_scatter(const int32_t *__restrict__ nwords, int64
 // block = 32 (full-sum warp) + groups*LPR: 20 groups x 5 replicates, 52 x 2, 100 x 1.
 static const Bucket kBuckets[] = {
     {215, 8, 192},  {250, 8, 192},  {290, 8, 192},  {350, 8, 192},  {440, 8, 192},
-    {590, 8, 192},  {900, 8, 448},  {1800, 8, 832}, {3600, 4, 832}, {PG_MAX_WORDS, 2, 832},
+    {590, 8, 192},  {640, 8, 448},  {900, 8, 448},  {1800, 8, 832}, {3600, 4, 832}, {PG_MAX_WORDS, 2, 832},   // 640: the longest read of plan 4
 };
 static const int kNumBuckets = (int)(sizeof(kBuckets) / sizeof(kBuckets[0]));
 static const Bucket &bucket_of(int n)
@@ -390,6 +390,7 @@ struct ClassifyJob {
                        ((opts && (opts->cert_plan == 3 || opts->bound_level != 0)) ? 3 : 4));
         ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
         ctx->st_heavy = ctx->st_items = 0;
+        ctx->st_mma = 0;
         // Chunk of reads per pass.  Plan 1 walks every genus block of a chunk (tile-major grid) and wants the
         // chunk's word ids, champion slots and near-tie lists L2-resident across those passes (2^14 measured
         // best); plan 2 touches a read's data once per kernel and prefers fewer, larger launches (2^16).
@@ -550,6 +551,7 @@ struct ClassifyJob {
             const int32_t *ord = d_order + bstart[b];
             if (certified && plan != 0 && bk.lpr == 8) {
                 if (timed) ctx->st_certified += bcount[b];
+                cb.count_mma = timed;
                 cudaEvent_t e0 = NULL, e1 = NULL;
                 if (timed) {
                     e0 = take_event(ctx); e1 = take_event(ctx);
@@ -918,7 +920,7 @@ extern "C" int pg_classify(pg_ctx *ctx, const pg_model *md, const pg_seqbatch *r
     if (!md->committed) return pg_fail(ctx, PG_EINVAL, "pg_classify: model has no tables (commit it first)");
     PG_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t n = reads->count;
-    int64_t st[5] = {0, 0, 0, 0, 0};
+    int64_t st[6] = {0, 0, 0, 0, 0, 0};
     int64_t slice_reads = PG_SLICE_READS;
     if (const char *e = getenv("PG_SLICE_READS")) {         // tests: exercise the slicing on small batches
         const long long v = atoll(e);
@@ -934,11 +936,11 @@ extern "C" int pg_classify(pg_ctx *ctx, const pg_model *md, const pg_seqbatch *r
         PG_TRY(classify_host_batch(ctx, md, &slice, opts, results_host + r0,
                                    boot_winners_host ? boot_winners_host + r0 * PG_NUM_BOOT : NULL));
         st[0] += ctx->st_certified; st[1] += ctx->st_strict; st[2] += ctx->st_handed_back;
-        st[3] += ctx->st_heavy; st[4] += ctx->st_items;
+        st[3] += ctx->st_heavy; st[4] += ctx->st_items; st[5] += ctx->st_mma;
         r0 = r1;
     }
     ctx->st_certified = st[0]; ctx->st_strict = st[1]; ctx->st_handed_back = st[2];
-    ctx->st_heavy = st[3]; ctx->st_items = st[4];
+    ctx->st_heavy = st[3]; ctx->st_items = st[4]; ctx->st_mma = st[5];
     return PG_OK;
 }
 

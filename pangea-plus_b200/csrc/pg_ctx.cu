@@ -55,6 +55,7 @@ extern "C" pg_ctx *pg_init(int device)
     ctx->classify_launches = 0;
     ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
     ctx->st_heavy = ctx->st_items = 0;
+    ctx->st_mma = 0;
     memset(&ctx->s_words, 0, sizeof(pg_ctx::Scratch) * pg_ctx::kNumScratch);
     ctx->h_pin = NULL;
     ctx->h_pin_cap = 0;
@@ -117,6 +118,13 @@ extern "C" int pg_classify_stats2(const pg_ctx *ctx, int64_t *heavy_reads, int64
     if (!ctx) return PG_EINVAL;
     if (heavy_reads) *heavy_reads = ctx->st_heavy;
     if (items) *items = ctx->st_items;
+    return PG_OK;
+}
+
+extern "C" int pg_classify_stats3(const pg_ctx *ctx, int64_t *tensor_core_reads)
+{
+    if (!ctx) return PG_EINVAL;
+    if (tensor_core_reads) *tensor_core_reads = ctx->st_mma;
     return PG_OK;
 }
 

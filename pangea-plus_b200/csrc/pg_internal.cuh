@@ -54,6 +54,7 @@ struct pg_ctx {
       s_champ, s_ncand, s_candl, s_fb, s_guess, s_items, s_heavy, s_hist, s_meta;
     static const int kNumScratch = 19;
     int64_t st_heavy, st_items;                        // certified v2: reads redone by the all-block kernel, light items
+    int64_t st_mma;                                    // reads whose best part and bounds came from the tensor-core kernel (plan 4)
     // pinned host staging
     void  *h_pin;
     size_t h_pin_cap;

@@ -132,6 +132,7 @@ def load_library() -> C.CDLL:
     lib.pg_model_bound_columns.argtypes = [vp]
     lib.pg_classify_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.pg_classify_stats2.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.pg_classify_stats3.argtypes = [vp, C.POINTER(i64)]
     lib.pg_model_sequences.restype = i64
     lib.pg_model_sequences.argtypes = [vp]
     lib.pg_model_counts.argtypes = [vp, vp, vp, vp, C.POINTER(i64)]
@@ -325,7 +326,10 @@ class Context:
         self._chk(self.lib.pg_classify_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
         d, e = C.c_int64(), C.c_int64()
         self._chk(self.lib.pg_classify_stats2(self.h, C.byref(d), C.byref(e)))
-        return {"certified": a.value, "strict": b.value, "handed_back": c.value, "heavy": d.value, "items": e.value}
+        f = C.c_int64()
+        self._chk(self.lib.pg_classify_stats3(self.h, C.byref(f)))
+        return {"certified": a.value, "strict": b.value, "handed_back": c.value, "heavy": d.value, "items": e.value,
+                "tensor_core": f.value}
 
     def kernel_time_reset(self) -> None:
         self._chk(self.lib.pg_kernel_time_reset(self.h))

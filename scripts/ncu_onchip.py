@@ -1,6 +1,6 @@
 """profiles/r2_onchip.json from an `ncu --set full` capture of bench.py (one launch of every hot kernel on the same
 chunk of reads): the on-chip counters bench.py quotes in roofline.onchip and the measured DRAM bytes per read of the
-certified phase-1 group (k_guess_bm + k_classify_h + k_bound + k_light).
+certified phase-1 group (k_guess_bm + k_mma_meta + k_mma_bound + k_light; with cert_plan 3: k_classify_h + k_bound).
 usage: ncu_onchip.py capture.ncu-rep out.json [metrics.csv]"""
 import csv
 import io
@@ -34,9 +34,12 @@ def reads_of(r):
         return grid * 4
     if "k_guess" in name:
         return grid * 8
-    if "k_bound" in name:
+    if "k_bound" in name and "k_mma" not in name:
         return grid
     return None
+
+
+tensor_cols = [h for h in hdr if "tensor" in h and "pct" in h]
 
 
 launch = []
@@ -48,17 +51,18 @@ for r in data:
                        issue_pct=val(r, "sm__inst_issued.avg.pct_of_peak_sustained_active"),
                        warps_active_pct=val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
                        l2_hit_pct=val(r, "lts__t_sector_hit_rate.pct"),
-                       dram_bytes=val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")))
-# the chunk: the k_bound launch with the most reads, and the group's other kernels launched on the same reads around it
-ib = max((i for i, l in enumerate(launch) if "k_bound" in l["kernel"]), key=lambda i: launch[i]["reads"])
+                       dram_bytes=val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"),
+                       tensor={h: val(r, h) for h in tensor_cols if r[col[h]] not in ("", "n/a")}))
+# the chunk: the k_guess_bm launch with the most reads, and the group's other kernels launched on the same reads after it
+ib = max((i for i, l in enumerate(launch) if "k_guess_bm" in l["kernel"]), key=lambda i: launch[i]["reads"])
 nreads = launch[ib]["reads"]
 group = {}
-for i in range(max(0, ib - 3), min(len(launch), ib + 3)):
+for i in range(ib, min(len(launch), ib + 6)):
     l = launch[i]
-    for key in ("k_guess_bm", "k_classify_h", "k_bound", "k_light", "k_resolve"):
-        if key in l["kernel"] and (l["reads"] in (nreads, None)) and key not in group:
+    for key in ("k_guess_bm", "k_mma_meta", "k_mma_bound", "k_classify_h", "k_bound", "k_light", "k_resolve"):
+        if l["kernel"].startswith(key) and key not in group:
             group[key] = l
-phase1 = [group[k] for k in ("k_guess_bm", "k_classify_h", "k_bound", "k_light") if k in group]
+phase1 = [group[k] for k in ("k_guess_bm", "k_mma_meta", "k_mma_bound", "k_classify_h", "k_bound", "k_light") if k in group]
 res = {
     "capture": rep.split("/")[-1], "reads_in_chunk": nreads,
     "dram_bytes_per_read": sum(l["dram_bytes"] for l in phase1) / nreads,
@@ -66,8 +70,10 @@ res = {
     "onchip": {k: {"counter": "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "value": round(l["l1_data_pipe_pct"], 2),
                    "shared_wavefronts_pct_of_peak": round(l["shared_wavefront_pct"], 2), "issue_slots_pct": round(l["issue_pct"], 2),
                    "warps_active_pct": round(l["warps_active_pct"], 2), "l2_hit_pct": round(l["l2_hit_pct"], 2), "ms": round(l["ms"], 4),
-                   "ns_per_read": round(1e6 * l["ms"] / nreads, 2), "dram_bytes_per_read": round(l["dram_bytes"] / nreads, 1)}
+                   "ns_per_read": round(1e6 * l["ms"] / nreads, 2), "dram_bytes_per_read": round(l["dram_bytes"] / nreads, 1),
+                   **({"tensor_pipe": {h: round(v, 2) for h, v in l["tensor"].items()}} if k == "k_mma_bound" and l["tensor"] else {})}
                for k, l in group.items()},
+    "group": [k for k in ("k_guess_bm", "k_mma_meta", "k_mma_bound", "k_classify_h", "k_bound", "k_light") if k in group],
     "note": "ncu --set full --clock-control none, one launch per kernel on the same chunk of reads of `bench.py --steps 2 --warmup 3 --legs none`; "
             "cold-cache, serialised timings (shares agree with the live CUDA-event numbers, absolutes do not)",
 }
@@ -76,7 +82,7 @@ print(json.dumps(res, indent=1))
 if len(sys.argv) > 3:
     with open(sys.argv[3], "w") as f:
         w = csv.writer(f)
-        keys = list(launch[0].keys())
+        keys = [k for k in launch[0].keys() if k != "tensor"]
         w.writerow(keys)
         for l in launch:
             w.writerow([l[k] for k in keys])

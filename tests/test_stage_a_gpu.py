@@ -674,3 +674,55 @@ def test_ties_without_lineage_and_min_boot_words(ctx, seed):
         assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb), kw
     om.free()
     gm.free()
+
+
+def test_tensor_core_plan_every_read_length(ctx):
+    """Plan 4 (the default of certified mode): best part and block bounds as one integer matrix product per read on the
+    tensor cores.  Reads of every length from 9 to 640 words -- every count image, every number of ring stages, partial
+    last K steps, a new image at nearly every read -- and a few longer ones (plan 3 takes those) must come back with the
+    strict kernels' records and replicate winners, for k = n/8 and for min_boot_words = 5."""
+    tr = synth.synth16s(seed=0x44A, seqs=900, genera=300, length=1500)          # 300 genera: 5+ blocks, clade-aligned padding
+    gm = ctx.train(tr["data"], tr["off"], tr["genus"], tr["G"])
+    gm.set_lineage(tr["anc"])
+    rng = np.random.default_rng(0x44A)
+    reads = []
+    for ln in list(range(16, 648)) + [700, 900, 1200]:                        # ln bases -> ln - 7 words
+        i = int(rng.integers(0, 900))
+        s = tr["data"][tr["off"][i]:tr["off"][i + 1]]
+        p = int(rng.integers(0, len(s) - ln))
+        r = s[p:p + ln].copy()
+        flip = rng.random(ln) < 0.02
+        r[flip] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(flip.sum()))]
+        reads.append((synth.revcomp(r) if rng.random() < 0.5 else r).tobytes())
+    order = rng.permutation(len(reads))
+    data, off = pack_sequences([reads[i] for i in order])
+    for mb in (0, 5):
+        want, wb = ctx.classify(gm, data, off, mode=0, want_boot=True, min_boot_words=mb)
+        got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True, min_boot_words=mb)
+        st = ctx.classify_stats()
+        assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb), mb
+        assert st["tensor_core"] == 632 and st["certified"] == len(reads), st     # every read of up to 640 words (647 bases)
+        got3, gb3 = ctx.classify(gm, data, off, mode=1, want_boot=True, min_boot_words=mb, cert_plan=3)
+        st3 = ctx.classify_stats()
+        assert got3.tobytes() == want.tobytes() and np.array_equal(gb3, wb) and st3["tensor_core"] == 0, (mb, st3)
+    gm.free()
+
+
+def test_tensor_core_plan_heavy_and_full_lists(ctx, baseline_model):
+    """Plan 4's escape routes: every read with an open pair sent to the all-block kernel (light_max = -1), a small
+    budget (light_max = 3), and reads far from every genus (their lists of open pairs and near-ties overflow)."""
+    tr, om, gm = baseline_model
+    data, off, src = synth.synth_reads(0x252, tr, 3000, paired=True)
+    rng = np.random.default_rng(5)
+    junk = [np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, 500)].tobytes() for _ in range(40)]
+    jd, jo = pack_sequences(junk)
+    data = np.concatenate([data, jd])
+    off = np.concatenate([off, off[-1] + jo[1:]])
+    want, wb = ctx.classify(gm, data, off, mode=0, want_boot=True)
+    for kw in (dict(), dict(light_max=-1), dict(light_max=3)):
+        got, gb = ctx.classify(gm, data, off, mode=1, want_boot=True, **kw)
+        st = ctx.classify_stats()
+        assert got.tobytes() == want.tobytes() and np.array_equal(gb, wb), kw
+        assert st["tensor_core"] == 3040, (kw, st)
+        if kw:
+            assert st["heavy"] > 0, (kw, st)
