@@ -804,7 +804,7 @@ k_guess_block(const uint16_t *__restrict__ qtable, const uint16_t *__restrict__ 
 __global__ void __launch_bounds__(256)
 k_guess_bm(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, const int64_t *__restrict__ off,
            const int32_t *__restrict__ nwords, const int32_t *__restrict__ order, int nreads_b, int64_t slot0,
-           int count, int per_group, int ngroup, int32_t *__restrict__ guess)
+           int count, int per_group, int ngroup, int32_t *__restrict__ guess, int nsample /* 32, or 64 for a second try */)
 {
     const int lane = threadIdx.x & 31;
     const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -814,18 +814,19 @@ k_guess_bm(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ words, 
     uint32_t best = 0u;
     if (n > 0) {
         const uint16_t *w = words + off[read];
-        const int ns = n < 32 ? n : 32, stride = n / ns;
+        const int ns = n < nsample ? n : nsample, stride = n / ns;
         const uint32_t wv = lane < ns ? (uint32_t)__ldg(w + lane * stride) : 0u;
+        const uint32_t wv2 = lane + 32 < ns ? (uint32_t)__ldg(w + (lane + 32) * stride) : 0u;
         uint32_t bestkey = 0xFFFFFFFFu;
         for (int grp = 0; grp < ngroup; grp++) {
             uint32_t acc = 0u;
             for (int j = 0; j < ns; j++) {
-                const uint32_t wj = __shfl_sync(0xffffffffu, wv, j);
+                const uint32_t wj = __shfl_sync(0xffffffffu, j < 32 ? wv : wv2, j & 31);
                 acc += __ldg(bm + ((size_t)grp * PG_NWORDS + wj) * 32 + lane);
             }
             // the table holds `count` units (blocks: PG_GB per group; parts: 32 per group)
             const uint32_t blk = (uint32_t)grp * (uint32_t)per_group + lane;
-            const uint32_t key = ((int)lane < per_group && (int)blk < count) ? ((acc << 12) | blk) : 0xFFFFFFFFu;   // acc < 2^17, blk < 2^12
+            const uint32_t key = ((int)lane < per_group && (int)blk < count) ? ((acc << 12) | blk) : 0xFFFFFFFFu;   // acc < 2^18, blk < 2^12
             bestkey = min(bestkey, __reduce_min_sync(0xffffffffu, key));
         }
         best = bestkey & 0xFFFu;
@@ -1852,18 +1853,19 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     // the coarse table also picks the block to evaluate first (k_guess8), whichever kernel bounds the rest
     static int env_g8 = -2;                             // PG_GUESS8=0: k_guess_bm even for large models (A/B switch)
     if (env_g8 == -2) { const char *e = getenv("PG_GUESS8"); env_g8 = e ? atoi(e) : -1; }
-    const bool guess8 = d_guess && version == 3 && md->d_bm8 && (use8 || (env_g8 != 0 && md->ngroup > 1));
+    // a second try (reads the first guess left "heavy"): the exact part minima of EVERY part over 64 sampled words
+    const bool guess8 = d_guess && version == 3 && md->d_bm8 && (use8 || (env_g8 != 0 && md->ngroup > 1)) && !cb.retry;
     if (guess8) {
         k_guess8<<<(nreads_b + 7) / 8, 256, (size_t)8 * md->bm8_pitch * 2, ctx->stream>>>(
             md->d_bm8, md->bm8_pitch, md->d_hmtable, d_words, d_off, d_nwords, d_order, (int)nreads_b, slot0, md->ntile64, d_guess);
         PG_LAUNCHED(ctx);
     } else if (d_guess && version == 3) {
         k_guess_bm<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_hmtable, d_words, d_off, d_nwords, d_order, (int)nreads_b,
-                                                               slot0, PG_PARTS * md->ntile64, 32, md->ngroup_h, d_guess);
+                                                               slot0, PG_PARTS * md->ntile64, 32, md->ngroup_h, d_guess, cb.retry ? 64 : 32);
         PG_LAUNCHED(ctx);
     } else if (d_guess && version == 2) {
         k_guess_bm<<<(nreads_b + 7) / 8, 256, 0, ctx->stream>>>(md->d_bmtable, d_words, d_off, d_nwords, d_order, (int)nreads_b,
-                                                               slot0, md->ntile64, PG_GB, md->ngroup, d_guess);
+                                                               slot0, md->ntile64, PG_GB, md->ngroup, d_guess, 32);
         PG_LAUNCHED(ctx);
         nblk_y = 1;                                     // grid row 0 = the guessed block, in full
     } else if (d_guess) {

@@ -107,6 +107,7 @@ struct PgCertBufs {
     unsigned int        item_cap;
     int                 light_max;   // pg_classify_opts.light_max
     int                 bound_level; // pg_classify_opts.bound_level
+    bool                retry;       // second try of reads the first guess left heavy: a more careful guess (k_guess_bm, 64 words)
     bool                count_mma;   // this pass counts for pg_classify_stats3 (not the one-off trials)
     int                 force_part;  // -1: the model's choice; 0 / 1: block / part columns in k_bound (the one-off trial of a model)
     unsigned int       *counters;    // [0] strict fallbacks, [1] heavy reads, [2] items of the bucket in flight, [3] items so far

@@ -1,5 +1,5 @@
 """Per CUDA source line: warp-stall samples, instructions, shared wavefronts of one kernel of an .ncu-rep
-(needs -lineinfo and --import-source on).  usage: ncu_lines.py report.ncu-rep [top] [kernel regex]"""
+(needs -lineinfo and --import-source on).  usage: ncu_lines.py report.ncu-rep [top] [kernel regex] [matching launches to skip]"""
 import csv
 import io
 import subprocess
@@ -11,6 +11,8 @@ kern = sys.argv[3] if len(sys.argv) > 3 else None           # regex of the kerne
 cmd = ["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass,cuda"]
 if kern:
     cmd += ["--kernel-name", "regex:" + kern, "--launch-count", "1"]
+    if len(sys.argv) > 4:                                    # skip that many matching launches first
+        cmd += ["--launch-skip", sys.argv[4]]
 out = subprocess.run(cmd, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Line No")

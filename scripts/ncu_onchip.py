@@ -39,7 +39,7 @@ def reads_of(r):
     return None
 
 
-tensor_cols = [h for h in hdr if "tensor" in h and "pct" in h]
+tensor_cols = [h for h in hdr if "tensor" in h and "pct" in h and (".avg." in h) and "ops_path" not in h]
 
 
 launch = []
@@ -71,7 +71,7 @@ res = {
                    "shared_wavefronts_pct_of_peak": round(l["shared_wavefront_pct"], 2), "issue_slots_pct": round(l["issue_pct"], 2),
                    "warps_active_pct": round(l["warps_active_pct"], 2), "l2_hit_pct": round(l["l2_hit_pct"], 2), "ms": round(l["ms"], 4),
                    "ns_per_read": round(1e6 * l["ms"] / nreads, 2), "dram_bytes_per_read": round(l["dram_bytes"] / nreads, 1),
-                   **({"tensor_pipe": {h: round(v, 2) for h, v in l["tensor"].items()}} if k == "k_mma_bound" and l["tensor"] else {})}
+                   **({"tensor_pipe": {h: round(v, 2) for h, v in l["tensor"].items() if v > 0}} if k == "k_mma_bound" and l["tensor"] else {})}
                for k, l in group.items()},
     "group": [k for k in ("k_guess_bm", "k_mma_meta", "k_mma_bound", "k_classify_h", "k_bound", "k_light") if k in group],
     "note": "ncu --set full --clock-control none, one launch per kernel on the same chunk of reads of `bench.py --steps 2 --warmup 3 --legs none`; "
