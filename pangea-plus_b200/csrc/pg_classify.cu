@@ -678,7 +678,9 @@ struct ClassifyJob {
         // exact minima of every part) and the same kernels again cost a few dozen ns per such read; the all-block kernel
         // costs ~22 ns per read AND BLOCK (4 us on a 10 000-genus model).
         unsigned int first_heavy = 0;
-        if (cnts[1] > 0 && cert_version == 4 && (int64_t)cnts[1] * 2 <= count) {
+        // (when more than a twentieth of the batch is heavy the guess is not the problem -- random or low-complexity
+        // reads -- and the second try would only add its own cost)
+        if (cnts[1] > 0 && cert_version == 4 && (int64_t)cnts[1] * 20 <= count) {
             first_heavy = cnts[1];
             lst.resize(cnts[1]);
             sorted.resize(cnts[1]);
