@@ -1855,7 +1855,11 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     if (env_g8 == -2) { const char *e = getenv("PG_GUESS8"); env_g8 = e ? atoi(e) : -1; }
     // a second try (reads the first guess left "heavy"): the exact part minima of EVERY part over 64 sampled words
     const bool guess8 = d_guess && version == 3 && md->d_bm8 && (use8 || (env_g8 != 0 && md->ngroup > 1)) && !cb.retry;
-    if (guess8) {
+    // cb.stage (plan 4 only): 1 = guess + tensor-core kernel, 2 = the item kernel of reads that went through stage 1 --
+    // the caller runs stage 2 of one slice on a second stream under stage 1 of the next; 0 = everything, in turn
+    const bool back_only = cb.stage == 2 && use_mma;
+    if (back_only) {
+    } else if (guess8) {
         k_guess8<<<(nreads_b + 7) / 8, 256, (size_t)8 * md->bm8_pitch * 2, ctx->stream>>>(
             md->d_bm8, md->bm8_pitch, md->d_hmtable, d_words, d_off, d_nwords, d_order, (int)nreads_b, slot0, md->ntile64, d_guess);
         PG_LAUNCHED(ctx);
@@ -1876,8 +1880,9 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     static int qblock = -1;                             // PG_Q_BLOCK=448: experiment switch for the first bucket
     if (qblock < 0) { const char *e = getenv("PG_Q_BLOCK"); qblock = e ? atoi(e) : 0; }
     int rc = PG_OK;
-    if (use_mma) {
-        PG_CUDA(ctx, cudaMemsetAsync(cb.counters + 2, 0, 4, ctx->stream));
+    if (back_only) {
+    } else if (use_mma) {
+        PG_CUDA(ctx, cudaMemsetAsync(cb.item_count, 0, 4, ctx->stream));
         const unsigned int lm = cb.light_max == 0 ? 2048u : (cb.light_max < 0 ? 0u : (unsigned int)cb.light_max);
         PG_TRY(pg_mma_launch(ctx, md, nreads_b, nmax, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb, d_guess, lm));
         if (cb.count_mma) ctx->st_mma += nreads_b;
@@ -1904,10 +1909,11 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
         rc = launch_q<832, 1>(ctx, md, nreads_b, nblk_y, smem, d_words, d_off, d_nwords, d_flags, d_order, slot0, min_boot, cb.champ, cb.ncand, cb.cand, d_guess);
     PG_TRY(rc);
     if (!(d_guess && version >= 2)) return PG_OK;
+    if (cb.stage == 1 && use_mma) return PG_OK;
 
     int light_max = cb.light_max == 0 ? PG_LIGHT_MAX : (cb.light_max < 0 ? 0 : cb.light_max);
     if (light_max > PG_LIGHT_MAX) light_max = PG_LIGHT_MAX;
-    if (!use_mma) PG_CUDA(ctx, cudaMemsetAsync(cb.counters + 2, 0, 4, ctx->stream));
+    if (!use_mma) PG_CUDA(ctx, cudaMemsetAsync(cb.item_count, 0, 4, ctx->stream));
     // (a two-reads-per-CTA k_bound with interleaved rows, like k_classify_h, was measured: same wavefronts,
     // 46 % more instructions, 28 % slower -- LDS.64 rows of 64 bytes gain nothing from the interleave)
     if (use_mma) {
@@ -1918,7 +1924,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
         k_bound8<<<dim3(nreads_b, (unsigned)nchunk8), block8, bsmem, ctx->stream>>>(
             md->d_bm8, md->bm8_pitch, nsegc, pitch_s, md->d_bmtable, md->d_hmtable, d_words, d_off, d_nwords, d_flags, d_order,
             slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot, md->ntile64, md->sib0, md->vmax, cb.champ, d_guess, cb.items,
-            cb.counters + 2, cb.item_cap, cb.heavy, (unsigned int)(cb.light_max == 0 ? PG_B8_KEEP : light_max));
+            cb.item_count, cb.item_cap, cb.heavy, (unsigned int)(cb.light_max == 0 ? PG_B8_KEEP : light_max));
         PG_LAUNCHED(ctx);
     } else {
     const size_t bsmem = (size_t)(nmax + 1) * 64;
@@ -1929,13 +1935,13 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
         PG_CUDA(ctx, pg_smem_unlock(ctx, k_bound<160, true>));
         k_bound<160, true><<<dim3(nreads_b, (unsigned)md->ngroup_h), 160, bsmem, ctx->stream>>>(
             md->d_hmtable, d_words, d_off, d_nwords, d_flags, d_order, slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot,
-            md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.counters + 2, cb.item_cap, cb.heavy,
+            md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.item_count, cb.item_cap, cb.heavy,
             (unsigned int)light_max, md->d_hmtable);
     } else {
     PG_CUDA(ctx, pg_smem_unlock(ctx, k_bound<160, false>));
     k_bound<160, false><<<dim3(nreads_b, (unsigned)md->ngroup), 160, bsmem, ctx->stream>>>(
         md->d_bmtable, d_words, d_off, d_nwords, d_flags, d_order, slot0, ctx->d_boot_pool, ctx->d_boot_off, min_boot,
-        md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.counters + 2, cb.item_cap, cb.heavy,
+        md->ntile64, md->vmax, cb.champ, d_guess, cb.items, cb.item_count, cb.item_cap, cb.heavy,
         (unsigned int)light_max, version == 3 ? md->d_hmtable : NULL);
     }
     PG_LAUNCHED(ctx);
@@ -1946,7 +1952,7 @@ int pg_certified_phase1(pg_ctx *ctx, const pg_model *md, const Bucket &bk, unsig
     }
     k_light<<<ctx->sm_count * light_ctas, 256, 0, ctx->stream>>>(md->d_qtable, d_words, d_off, d_nwords, d_order - slot0, ctx->d_boot_pool,
                                                         ctx->d_boot_off, min_boot, md->d_blockmask, md->vmax, cb.items,
-                                                        cb.counters + 2, cb.item_cap, cb.champ, cb.ncand, cb.cand, use_mma ? NULL : cb.counters + 3,
+                                                        cb.item_count, cb.item_cap, cb.champ, cb.ncand, cb.cand, use_mma ? NULL : cb.counters + 3,
                                                         version == 3 ? md->d_hmtable : NULL);
     PG_LAUNCHED(ctx);
     return PG_OK;

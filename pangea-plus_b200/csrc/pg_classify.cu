@@ -259,6 +259,8 @@ int pg_certified_phase2(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int 
                         const int32_t *d_order, int64_t slot0, int min_boot, const PgCertBufs &cb, bool use_heavy,
                         pg_result *d_results, int32_t *d_boot_winners);
 int pg_mma_ensure_images(pg_ctx *ctx, const std::vector<int> &need_n, int min_boot);          // pg_mma.cu
+bool pg_mma_usable(const pg_model *md, int nmax);
+#define PG_PIPE_SLICE 16384                         // reads per slice of a pipelined plan-4 bucket
 int pg_certified_reset(pg_ctx *ctx, const int32_t *d_list, int cnt, int64_t slot0, const PgCertBufs &cb);   // pg_certified.cu
 #define PG_CANDCAP 128
 
@@ -386,6 +388,7 @@ struct ClassifyJob {
         if (env_v1 < 0) { const char *e = getenv("PG_CERT_V1"); env_v1 = (e && atoi(e)) ? 1 : 0; }
         // 4 = plan 4, the default: plan 3's best part and bounds on the tensor cores (pg_mma.cu); an explicit
         // bound_level or cert_plan 3 asks for plan 3's own kernels
+        { static int env_pipe = -2; if (env_pipe == -2) { const char *e = getenv("PG_PIPE"); env_pipe = e ? atoi(e) : 0; } pipe_ok = env_pipe != 0; }
         cert_version = (env_v1 || (opts && opts->cert_plan == 1)) ? 1 : ((opts && opts->cert_plan == 2) ? 2 :
                        ((opts && (opts->cert_plan == 3 || opts->bound_level != 0)) ? 3 : 4));
         ctx->st_certified = ctx->st_strict = ctx->st_handed_back = 0;
@@ -425,7 +428,7 @@ struct ClassifyJob {
             PG_TRY(pg_scratch(ctx, &ctx->s_champ, (size_t)cmax * nkeys * 8));
             PG_TRY(pg_scratch(ctx, &ctx->s_ncand, (size_t)cmax * 4));
             PG_TRY(pg_scratch(ctx, &ctx->s_candl, (size_t)cmax * PG_CANDCAP * 8));
-            PG_TRY(pg_scratch(ctx, &ctx->s_fb, (size_t)count * 4 + 16));
+            PG_TRY(pg_scratch(ctx, &ctx->s_fb, (size_t)count * 4 + 32));
             PG_TRY(pg_scratch(ctx, &ctx->s_guess, (size_t)cmax * 4));
             // room for 512 open (task, block) pairs per read of a chunk on average (268 MB for 2^16 reads): a full buffer
             // sends reads to the all-block kernel, which costs far more than the items would (models with hundreds of
@@ -436,13 +439,14 @@ struct ClassifyJob {
             cb.champ = (unsigned long long *)ctx->s_champ.p;
             cb.ncand = (unsigned int *)ctx->s_ncand.p;
             cb.cand = (unsigned long long *)ctx->s_candl.p;
-            cb.counters = (unsigned int *)ctx->s_fb.p;
-            cb.fb_list = (int32_t *)ctx->s_fb.p + 4;
+            cb.counters = (unsigned int *)ctx->s_fb.p;           // [4], [5]: item cursor of the second half of a pipelined bucket, spare
+            cb.item_count = cb.counters + 2;
+            cb.fb_list = (int32_t *)ctx->s_fb.p + 8;
             cb.guess = (int32_t *)ctx->s_guess.p;
             cb.items = (unsigned long long *)ctx->s_items.p;
             cb.hv_list = (int32_t *)ctx->s_heavy.p;
             cb.heavy = (uint8_t *)((int32_t *)ctx->s_heavy.p + count);
-            PG_CUDA(ctx, cudaMemsetAsync(cb.counters, 0, 16, ctx->stream));
+            PG_CUDA(ctx, cudaMemsetAsync(cb.counters, 0, 32, ctx->stream));
         }
         return PG_OK;
     }
@@ -528,6 +532,16 @@ struct ClassifyJob {
         return PG_OK;
     }
 
+    // second stream and events of the pipelined buckets (run_pass)
+    bool pipe_ok = false;                            // PG_PIPE=1: two streams (A/B switch; measured slower, see run_pass)
+    int pipe_setup()
+    {
+        if (ctx->aux_stream) return PG_OK;
+        PG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; i++) PG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_pipe[i], cudaEventDisableTiming));
+        return PG_OK;
+    }
+
     // one pass over a set of reads (a chunk of the batch, or a list): plan 2 / plan 1 / strict (plan 0).
     // A "slot" is a position in the order array of the pass; the per-read scratch (champion slots,
     // near-tie lists, strict keys, guesses) is indexed by slot.
@@ -556,6 +570,47 @@ struct ClassifyJob {
                 if (timed) {
                     e0 = take_event(ctx); e1 = take_event(ctx);
                     PG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+                }
+                if (plan == 4 && cb.bound_level == 0 && cb.force_part < 0 && bcount[b] >= 2 * PG_PIPE_SLICE && pipe_ok && pg_mma_usable(md, nmax)) {
+                    // Plan 4, a large bucket: slices of PG_PIPE_SLICE reads; the item kernel and phase 2 of slice j run on
+                    // a second stream UNDER the tensor-core kernel of slice j + 1 -- that kernel is one latency-bound CTA
+                    // per SM (issue slots 40 % busy), the others fit beside it.  Two halves of the item list alternate.
+                    // MEASURED (PG_PIPE=1): same records, 24.0 M reads/s against 26.1 M on one stream -- the kernels
+                    // compete for the same thing, L2 requests in flight per SM, and 16 384-read launches add tails.  Off by default.
+                    PG_TRY(pipe_setup());
+                    cudaStream_t main_stream = ctx->stream;
+                    const unsigned int half = cb.item_cap / 2;
+                    int64_t j = 0;
+                    for (int64_t o = 0; o < bcount[b]; o += PG_PIPE_SLICE, j++) {
+                        const unsigned c = (unsigned)(bcount[b] - o < PG_PIPE_SLICE ? bcount[b] - o : PG_PIPE_SLICE);
+                        const int p = (int)(j & 1);
+                        PgCertBufs cs = cb;
+                        cs.items = cb.items + (size_t)p * half;
+                        cs.item_cap = half;
+                        cs.item_count = cb.counters + (p ? 4 : 2);
+                        if (j >= 2) PG_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_pipe[2 + p], 0));   // that half of the list is consumed
+                        cs.stage = 1;
+                        PG_TRY(pg_certified_phase1(ctx, md, bk, c, nmax, d_words, d_off, d_nwords, d_flags, ord + o, bstart[b] + o, min_boot, cs, plan));
+                        PG_CUDA(ctx, cudaEventRecord(ctx->ev_pipe[p], main_stream));
+                        PG_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_pipe[p], 0));
+                        ctx->stream = ctx->aux_stream;
+                        cs.stage = 2;
+                        int rc2 = pg_certified_phase1(ctx, md, bk, c, nmax, d_words, d_off, d_nwords, d_flags, ord + o, bstart[b] + o, min_boot, cs, plan);
+                        if (rc2 == PG_OK)
+                            rc2 = pg_certified_phase2(ctx, md, c, nmax, d_words, d_off, d_nwords, d_flags, ord + o, bstart[b] + o, min_boot, cs, true,
+                                                      d_results, d_boot_winners);
+                        cudaError_t ee = cudaEventRecord(ctx->ev_pipe[2 + p], ctx->aux_stream);
+                        ctx->stream = main_stream;
+                        PG_TRY(rc2);
+                        PG_CUDA(ctx, ee);
+                    }
+                    PG_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_pipe[2], 0));
+                    if (j >= 2) PG_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_pipe[3], 0));
+                    if (timed) {
+                        PG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+                        ctx->ev_pending.push_back(std::make_pair(e0, e1));
+                    }
+                    continue;
                 }
                 PG_TRY(pg_certified_phase1(ctx, md, bk, (unsigned)bcount[b], nmax, d_words, d_off, d_nwords, d_flags, ord,
                                            bstart[b], min_boot, cb, plan));

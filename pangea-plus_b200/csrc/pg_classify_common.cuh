@@ -107,6 +107,8 @@ struct PgCertBufs {
     unsigned int        item_cap;
     int                 light_max;   // pg_classify_opts.light_max
     int                 bound_level; // pg_classify_opts.bound_level
+    unsigned int       *item_count;  // cursor of the item list in flight (counters + 2; + 4 for the second half of a pipelined bucket)
+    int                 stage;       // plan 4: 0 = all of phase 1, 1 = up to the tensor-core kernel, 2 = the item kernel only
     bool                retry;       // second try of reads the first guess left heavy: a more careful guess (k_guess_bm, 64 words)
     bool                count_mma;   // this pass counts for pg_classify_stats3 (not the one-off trials)
     int                 force_part;  // -1: the model's choice; 0 / 1: block / part columns in k_bound (the one-off trial of a model)

@@ -89,6 +89,7 @@ extern "C" void pg_shutdown(pg_ctx *ctx)
     cudaFree(ctx->d_boot_pool);
     cudaFree(ctx->d_boot_off);
     cudaFree(ctx->d_cnt_img);
+    if (ctx->aux_stream) { cudaStreamDestroy(ctx->aux_stream); for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->ev_pipe[i]); }
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     for (auto &p : ctx->ev_pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     for (auto &ev : ctx->ev_free) cudaEventDestroy(ev);

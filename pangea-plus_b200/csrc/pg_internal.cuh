@@ -23,6 +23,8 @@ struct pg_ctx {
     cudaStream_t stream;
     cudaStream_t own_stream;
     cudaStream_t copy_stream, down_stream;    // uploads / downloads of pg_classify(), created on first use
+    cudaStream_t aux_stream;                  // plan 4: item kernel + phase 2 of one slice run here under the tensor-core kernel of the next
+    cudaEvent_t  ev_pipe[4];                  // [0..1] stage 1 of slice parity p done, [2..3] stages 2 + phase 2 done
     mutable char err[512];
     int64_t      launches;
 

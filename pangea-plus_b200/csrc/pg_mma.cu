@@ -31,7 +31,9 @@
 #define PG_MMA_IMG    (128 * PG_MMA_MAXN)   // bytes of one count image slot
 #define PG_MMA_NPROD  256                   // producer threads
 #define PG_MMA_NEPI   128                   // epilogue threads.  256 = two groups of four warps taking the reads in turn (one per
-                                            // TMEM buffer) was measured: 96 registers and spills, more warps per scheduler: slower
+                                            // TMEM buffer) was measured: 96 registers and spills, more warps per scheduler: slower;
+                                            // with setmaxnreg (64 / 160) it compiled without spills and did not come back from the
+                                            // device (the 17th warp is a warpgroup of its own); the bounded barrier waits ended it
 #define PG_MMA_THREADS (PG_MMA_NEPI + 32 + PG_MMA_NPROD)
 #define PG_MMA_LIST   2048                  // open pairs per read above which the read is "heavy" (default)
 #define PG_X8_SHIFT   2
@@ -710,7 +712,7 @@ int pg_mma_launch(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, 
     a.words = d_words; a.off = d_off; a.nwords = d_nwords; a.flags = d_flags; a.order = d_order;
     a.nreads_b = (int)nreads_b; a.slot0 = slot0; a.min_boot = min_boot; a.blockmask = md->d_blockmask; a.vmax = md->vmax;
     a.champ = cb.champ; a.ncand = cb.ncand; a.cand = cb.cand; a.guess = d_guess;
-    a.items = cb.items; a.item_count = cb.counters + 2; a.items_total = cb.counters + 3; a.item_cap = cb.item_cap; a.heavy = cb.heavy; a.light_max = light_max;
+    a.items = cb.items; a.item_count = cb.item_count; a.items_total = cb.counters + 3; a.item_cap = cb.item_cap; a.heavy = cb.heavy; a.light_max = light_max;
     const int nch = 3 + md->pitch8 / 16;
     PG_CUDA(ctx, pg_smem_unlock(ctx, k_mma_bound));
     cudaFuncAttributes fa;
