@@ -297,28 +297,37 @@ struct PgMmaRead {
 // flight; meta[] is padded with empty slots past the end, so the look-ahead never needs a bound check.
 struct PgMmaCursor {
     int slot;
-    int4 ahead, ahead2;
+    int a_n, a_gv, a_wlo, a_whi, a_mf, a_mr;          // metadata of `slot`, in flight
+    // Six scalar loads, not two 16-byte ones: a vector load lands in an aligned register quad and the compiler then MOVES
+    // it into the loop-carried registers right behind the load -- a full L2 round trip per read in every role (the
+    // hottest instruction of the first profile: 6.6 % of all stall samples on one MOV).
+    __device__ __forceinline__ static int ld(const int *p)
+    {
+        int v;
+        asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+        return v;
+    }
+    __device__ __forceinline__ void fetch(const PgMmaArgs &a)
+    {
+        const int *m = reinterpret_cast<const int *>(a.meta) + (size_t)slot * 8;
+        a_n = ld(m); a_gv = ld(m + 1); a_wlo = ld(m + 2); a_whi = ld(m + 3); a_mf = ld(m + 4); a_mr = ld(m + 5);
+    }
     __device__ __forceinline__ void start(const PgMmaArgs &a)
     {
         slot = (int)blockIdx.x;
-        ahead = __ldg(a.meta + 2 * slot);
-        ahead2 = __ldg(a.meta + 2 * slot + 1);
+        fetch(a);
     }
+    // the next slot of this CTA, skipped reads included (n = 0: every role passes over them by itself -- a loop HERE
+    // made the compiler copy the freshly loaded registers at once, i.e. wait for the load it had just issued)
     __device__ __forceinline__ bool next(const PgMmaArgs &a, PgMmaRead &r)
     {
-        while (slot < a.nreads_b) {
-            const int4 m = ahead, m2 = ahead2;
-            const int s = slot;
-            slot += (int)gridDim.x;
-            ahead = __ldg(a.meta + 2 * slot);
-            ahead2 = __ldg(a.meta + 2 * slot + 1);
-            if (m.x == 0) continue;
-            r.slot = s; r.n = m.x; r.gs = m.y & 0xFFFF; r.vb16 = (uint32_t)m.y >> 16;
-            r.margin_full = (uint32_t)m2.x; r.margin_rep = (uint32_t)m2.y;
-            r.woff = (int64_t)(((unsigned long long)(uint32_t)m.w << 32) | (uint32_t)m.z);
-            return true;
-        }
-        return false;
+        if (slot >= a.nreads_b) return false;
+        r.slot = slot; r.n = a_n; r.gs = a_gv & 0xFFFF; r.vb16 = (uint32_t)a_gv >> 16;
+        r.margin_full = (uint32_t)a_mf; r.margin_rep = (uint32_t)a_mr;
+        r.woff = (int64_t)(((unsigned long long)(uint32_t)a_whi << 32) | (uint32_t)a_wlo);
+        slot += (int)gridDim.x;
+        fetch(a);
+        return true;
     }
 };
 
@@ -390,7 +399,7 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
                 for (int i = 0; i < MAXST; i++)
                     if (i * PG_MMA_KC + jr < rn.n) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(qn + (size_t)wn[i] * 32));
             }
-            if (r.n != cur_n) {
+            if (r.n > 0 && r.n != cur_n) {
                 // a new count image: every product that reads the old one must be done, i.e. those of the last stage issued
                 if (!first && lane == 0) pgm_mbar_wait(pgm_smem(&s_empty[sprev]), phprev);
                 __syncwarp();
@@ -446,6 +455,7 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
         PgMmaRead r;
         long long t_wd = 0, t_wf = 0, t_fence = 0, t_all = clock64();
         while (cur.next(a, r)) {
+            if (r.n == 0) continue;                      // skipped read (short, or no word)
             const unsigned acc = rd & 1u;
             long long tw0 = a.prof ? clock64() : 0;
             if (lane == 0) pgm_mbar_wait(pgm_smem(&s_dempty[acc]), ((rd >> 1) & 1u) ^ 1u);          // the epilogue has drained this buffer
@@ -503,6 +513,7 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
         unsigned int chunk_pos = 0u, chunk_end = 0u;     // lane 0: this warp's reservation in the global item list
         unsigned int nitems = 0u;                        // lane 0: pairs this warp wrote
         while (cur.next(a, r)) {
+            if (r.n == 0) continue;                      // skipped read (short, or no word)
             const unsigned acc = rd & 1u;
             if (PG_MMA_NEPI == 256 && acc != grp) { rd++; continue; }
             const size_t rc = (size_t)a.slot0 + r.slot;
