@@ -14,20 +14,24 @@
 //     32..    one byte per block, c = min(bm >> 2, 255) (bm8x): rounded DOWN and capped, so 4 * D[col] <= LB <= every
 //             genus sum of the block; a block is dismissed when D[col] > (champion + margin) >> 2
 //     last 16 the coarse part minima (hm8x) of the four blocks around the best one: its 3 sibling parts compete like blocks
-// One persistent CTA per SM, three roles over mbarriers:
-//     8 producer warps  gather the rows of 128 words per stage into a 4-stage ring (MN-major, no swizzle: 16 columns of
-//                       8 consecutive words = one 128-byte core matrix), and the count image when n changes;
-//     1 issuing thread  tcgen05.mma M = 128 (tasks), N, K = 32 words per instruction, A = count image (K-major) and
-//                       B = ring stage straight from shared memory, accumulating in one of two TMEM buffers;
+// One persistent CTA per SM (it owns all 512 columns of tensor memory), three roles over mbarriers:
+//     8 producer warps  gather the rows of 128 words per stage into a ring of up to 8 stages (MN-major, no swizzle: 16
+//                       columns of 8 consecutive words = one 128-byte core matrix) and the count image when n changes;
+//                       word ids two reads ahead, the exact rows prefetched into L2 one read ahead; a thread's arrival on
+//                       the stage's barrier fires when its copies have landed (cp.async.mbarrier.arrive.noinc);
+//     1 issuing warp    tcgen05.mma M = 128 (tasks), N, K = 32 words per instruction, A = count image (K-major) and
+//                       B = ring stage straight from shared memory, accumulating in one of two TMEM buffers; the whole
+//                       warp walks the loop (uniform operands), one elected lane issues; tcgen05.commit frees the stage;
 //     4 epilogue warps  thread = task: tcgen05.ld its row, champion of the part -> champion slot and near-ties (what
 //                       k_classify_h's epilogue does), then the bound columns -> (task, block) items (what k_bound does).
+// Every barrier wait is bounded: a protocol error ends the kernel with a launch failure, it cannot hang the device.
 // Results are those of plan 3 (and so of the strict kernels): the exact columns are the same integers, the bound columns
 // only decide which pairs k_light evaluates exactly.  tests: test_certified_plans_agree and every parity test (default plan).
 #include "pg_certified.cuh"
 
 #define PG_MMA_MAXN   640                   // reads with more good words go through plan 3
 #define PG_MMA_KC     128                   // words per ring stage
-#define PG_MMA_MAXSTAGES 8                // ring depth: as many stages as shared memory holds, at least 3
+#define PG_MMA_MAXSTAGES 8                   // ring depth: as many stages as shared memory holds, at least 3
 #define PG_MMA_IMG    (128 * PG_MMA_MAXN)   // bytes of one count image slot
 #define PG_MMA_NPROD  256                   // producer threads
 #define PG_MMA_NEPI   128                   // epilogue threads.  256 = two groups of four warps taking the reads in turn (one per
@@ -35,7 +39,6 @@
                                             // with setmaxnreg (64 / 160) it compiled without spills and did not come back from the
                                             // device (the 17th warp is a warpgroup of its own); the bounded barrier waits ended it
 #define PG_MMA_THREADS (PG_MMA_NEPI + 32 + PG_MMA_NPROD)
-#define PG_MMA_LIST   2048                  // open pairs per read above which the read is "heavy" (default)
 #define PG_X8_SHIFT   2
 #define PG_MMA_WLIST  512                   // open pairs per (read, epilogue warp) above which the read is "heavy"
 #define PG_MMA_RESERVE 128                  // entries of the global item list an epilogue warp reserves at a time
