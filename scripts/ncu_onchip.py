@@ -52,7 +52,7 @@ for r in data:
                        warps_active_pct=val(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
                        l2_hit_pct=val(r, "lts__t_sector_hit_rate.pct"),
                        dram_bytes=val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum"),
-                       tensor={h: val(r, h) for h in tensor_cols if r[col[h]] not in ("", "n/a")}))
+                       tensor={h: val(r, h) for h in tensor_cols if r[col[h]].replace(",", "").replace(".", "").isdigit()}))
 # the chunk: the k_guess_bm launch with the most reads, and the group's other kernels launched on the same reads after it
 ib = max((i for i, l in enumerate(launch) if "k_guess_bm" in l["kernel"]), key=lambda i: launch[i]["reads"])
 nreads = launch[ib]["reads"]
