@@ -365,6 +365,9 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem = s_tmem;
+    // shared-window addresses of the barrier arrays, once (a generic-to-shared conversion per use showed up in the profile)
+    const uint32_t full0 = pgm_smem(&s_full[0]), empty0 = pgm_smem(&s_empty[0]), dfull0 = pgm_smem(&s_dfull[0]), dempty0 = pgm_smem(&s_dempty[0]);
+    const uint32_t sA0 = pgm_smem(sA), ring0 = pgm_smem(ring);
 
     if (warp > PG_MMA_NEPI / 32) {
         // ================================================================ producers
@@ -404,11 +407,11 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             }
             if (r.n > 0 && r.n != cur_n) {
                 // a new count image: every product that reads the old one must be done, i.e. those of the last stage issued
-                if (!first && lane == 0) pgm_mbar_wait(pgm_smem(&s_empty[sprev]), phprev);
+                if (!first && lane == 0) pgm_mbar_wait((empty0 + 8u * (sprev)), phprev);
                 __syncwarp();
                 const uint8_t *img = a.images + (size_t)r.n * PG_MMA_IMG;
                 const int pieces = 128 * ((r.n + 31) & ~31) / 16;
-                for (int i = p; i < pieces; i += PG_MMA_NPROD) PGM_CP16(pgm_smem(sA) + (uint32_t)i * 16u, img + (size_t)i * 16);
+                for (int i = p; i < pieces; i += PG_MMA_NPROD) PGM_CP16(sA0 + (uint32_t)i * 16u, img + (size_t)i * 16);
                 cur_n = r.n;
             }
             const uint8_t *qrow = a.qx + (size_t)r.gs * PG_NWORDS * 32 + sub * 16;
@@ -417,12 +420,12 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             for (int kc = 0; kc < MAXST; kc++) {
                 if (kc * PG_MMA_KC >= r.n) break;
                 const long long tw0 = a.prof ? clock64() : 0;
-                if (lane == 0) pgm_mbar_wait(pgm_smem(&s_empty[s]), ph);             // the ring slot is free
+                if (lane == 0) pgm_mbar_wait((empty0 + 8u * (s)), ph);             // the ring slot is free
                 __syncwarp();
                 if (a.prof) t_wait += clock64() - tw0;
                 if (kc * PG_MMA_KC + jr < r.n) {
                     const uint32_t wid = w[kc];
-                    const uint32_t dst0 = pgm_smem(ring) + s * stage_bytes + (uint32_t)jr * 16u;
+                    const uint32_t dst0 = ring0 + s * stage_bytes + (uint32_t)jr * 16u;
                     PGM_CP16(dst0 + (uint32_t)sub * (PG_MMA_KC * 16u), qrow + (size_t)wid * 32);
                     const uint8_t *brow = a.bm8x + (size_t)wid * a.pitch8;
                     for (int c = sub; c < nb8; c += 2) PGM_CP16(dst0 + (uint32_t)(2 + c) * (PG_MMA_KC * 16u), brow + c * 16);
@@ -431,7 +434,7 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
                 // This thread's arrival fires when its copies have landed; the thread itself never waits for data, so a
                 // whole ring of stages is in flight.  (Waiting per stage -- cp.async.wait_group, then fence.proxy.async --
                 // cost 1 700 cycles a stage: the fence waits for every copy in flight, not just the stage being signalled.)
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(pgm_smem(&s_full[s])) : "memory");
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((full0 + 8u * (s))) : "memory");
                 sprev = s; phprev = ph ^ 1u; first = false;
                 if (++s == a.nstage) { s = 0; ph ^= 1u; }
                 nst_total++;
@@ -448,10 +451,10 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
         // registers); one elected lane issues.  With a single lane inside `if (lane == 0)` the compiler wrapped every
         // product in a divergence loop and ~12 register-to-uniform moves: 150 cycles per instruction.
         const uint32_t idesc = (2u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | (8u << 24);   // u8 x u8 -> s32, B MN-major, M = 128
-        const uint32_t a_lo = ((pgm_smem(sA) >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);               // K chunks 2 048 B apart (leading)
+        const uint32_t a_lo = ((sA0 >> 4) & 0x3FFFu) | ((2048u >> 4) << 16);               // K chunks 2 048 B apart (leading)
         const uint32_t a_hi = (128u >> 4) | (1u << 14);                                            // row groups 128 B apart (stride); version 1
         const uint32_t b_hi = ((PG_MMA_KC * 16u) >> 4) | (1u << 14);                               // 16-column chunks PG_MMA_KC * 16 B apart
-        const uint32_t b_lo0 = ((pgm_smem(ring) >> 4) & 0x3FFFu) | ((128u >> 4) << 16);             // words 8 apart 128 B apart
+        const uint32_t b_lo0 = ((ring0 >> 4) & 0x3FFFu) | ((128u >> 4) << 16);             // words 8 apart 128 B apart
         unsigned s = 0, ph = 0u, rd = 0;
         PgMmaCursor cur;
         cur.start(a);
@@ -461,7 +464,7 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             if (r.n == 0) continue;                      // skipped read (short, or no word)
             const unsigned acc = rd & 1u;
             long long tw0 = a.prof ? clock64() : 0;
-            if (lane == 0) pgm_mbar_wait(pgm_smem(&s_dempty[acc]), ((rd >> 1) & 1u) ^ 1u);          // the epilogue has drained this buffer
+            if (lane == 0) pgm_mbar_wait((dempty0 + 8u * (acc)), ((rd >> 1) & 1u) ^ 1u);          // the epilogue has drained this buffer
             __syncwarp();
             if (a.prof) t_wd += clock64() - tw0;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -470,7 +473,7 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             uint32_t alo = a_lo;
             for (int ks0 = 0; ks0 < nks; ks0 += PG_MMA_KC / 32) {
                 tw0 = a.prof ? clock64() : 0;
-                if (lane == 0) pgm_mbar_wait(pgm_smem(&s_full[s]), ph);
+                if (lane == 0) pgm_mbar_wait((full0 + 8u * (s)), ph);
                 __syncwarp();
                 if (a.prof) t_wf += clock64() - tw0;
                 // the rows were written through the generic proxy (cp.async) and are read through the async proxy
@@ -486,8 +489,8 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
                         if (u < left)
                             pgm_mma_i8(dcol, ((uint64_t)a_hi << 32) | (alo + (uint32_t)u * (4096u >> 4)),
                                        ((uint64_t)b_hi << 32) | (blo + (uint32_t)u * (512u >> 4)), idesc, (ks0 + u) > 0 ? 1u : 0u);
-                    pgm_commit(pgm_smem(&s_empty[s]));                                // the slot is free once these products are done
-                    if (ks0 + PG_MMA_KC / 32 >= nks) pgm_commit(pgm_smem(&s_dfull[acc]));
+                    pgm_commit((empty0 + 8u * (s)));                                // the slot is free once these products are done
+                    if (ks0 + PG_MMA_KC / 32 >= nks) pgm_commit((dfull0 + 8u * (acc)));
                 }
                 __syncwarp();
                 alo += (PG_MMA_KC / 32) * (4096u >> 4);
@@ -529,7 +532,7 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             const uint32_t vb16 = r.vb16;
             const uint32_t margin = t == 0 ? r.margin_full : r.margin_rep;
             const long long tw0 = a.prof ? clock64() : 0;
-            if (lane == 0) pgm_mbar_wait(pgm_smem(&s_dfull[acc]), (rd >> 1) & 1u);     // one lane polls: the polls share the
+            if (lane == 0) pgm_mbar_wait((dfull0 + 8u * (acc)), (rd >> 1) & 1u);     // one lane polls: the polls share the
             __syncwarp();                                                             // shared-memory port with the operands
             if (a.prof) t_wd += clock64() - tw0;
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -688,7 +691,7 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             if (a.prof) t_cmp += clock64() - tp;
             // the accumulator is read and the counters are settled: hand the buffer back to the issuing thread
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            pgm_mbar_arrive(pgm_smem(&s_dempty[acc]));
+            pgm_mbar_arrive((dempty0 + 8u * (acc)));
             rd++;
         }
         if (lane == 0) {
