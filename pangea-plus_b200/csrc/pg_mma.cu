@@ -257,7 +257,7 @@ struct PgMmaArgs {
     unsigned int item_cap;
     uint8_t *heavy;
     unsigned int light_max;
-    const int4 *meta;                                 // [nreads_b + gridDim.x][2], k_mma_meta
+    const int4 *meta;                                 // [nreads_b + (gridDim.x + 1) * PG_MMA_RUN][2], k_mma_meta
     long long *prof;                                  // PG_MMA_PROF=1: per CTA 8 cycle counters, else NULL
 };
 
@@ -298,6 +298,10 @@ struct PgMmaRead {
 };
 // A role's cursor over the slots of its CTA (blockIdx.x, + gridDim.x, ...).  The metadata of the NEXT slot is always in
 // flight; meta[] is padded with empty slots past the end, so the look-ahead never needs a bound check.
+// A CTA takes the slots in blocks of PG_MMA_RUN consecutive ones (block b = blockIdx.x, + gridDim.x, ...): the order array
+// is sorted by word count, so a run shares its count image (one slot at a time, round robin, changed the image at
+// nearly every read of a batch with many different lengths: 64 KB of copies per read beside 39 KB of rows).
+#define PG_MMA_RUN 16
 struct PgMmaCursor {
     int slot;
     int a_n, a_gv, a_wlo, a_whi, a_mf, a_mr;          // metadata of `slot`, in flight
@@ -317,7 +321,7 @@ struct PgMmaCursor {
     }
     __device__ __forceinline__ void start(const PgMmaArgs &a)
     {
-        slot = (int)blockIdx.x;
+        slot = (int)blockIdx.x * PG_MMA_RUN;
         fetch(a);
     }
     // the next slot of this CTA, skipped reads included (n = 0: every role passes over them by itself -- a loop HERE
@@ -328,7 +332,7 @@ struct PgMmaCursor {
         r.slot = slot; r.n = a_n; r.gs = a_gv & 0xFFFF; r.vb16 = (uint32_t)a_gv >> 16;
         r.margin_full = (uint32_t)a_mf; r.margin_rep = (uint32_t)a_mr;
         r.woff = (int64_t)(((unsigned long long)(uint32_t)a_whi << 32) | (uint32_t)a_wlo);
-        slot += (int)gridDim.x;
+        slot = ((slot + 1) & (PG_MMA_RUN - 1)) ? slot + 1 : slot + 1 + ((int)gridDim.x - 1) * PG_MMA_RUN;
         fetch(a);
         return true;
     }
@@ -742,8 +746,9 @@ int pg_mma_launch(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, 
     size_t smem = (size_t)128 * a.kmax + ns * stage;
     // the kernel owns all 512 columns of tensor memory: never two CTAs on one SM
     if (smem < (size_t)120 * 1024) smem = (size_t)120 * 1024;
-    const unsigned grid = nreads_b < (unsigned)ctx->sm_count ? nreads_b : (unsigned)ctx->sm_count;
-    const int nmeta = (int)nreads_b + (int)grid;
+    const unsigned nrun = (nreads_b + PG_MMA_RUN - 1) / PG_MMA_RUN;
+    const unsigned grid = nrun < (unsigned)ctx->sm_count ? nrun : (unsigned)ctx->sm_count;
+    const int nmeta = (int)nreads_b + (int)(grid + 1) * PG_MMA_RUN;          // the cursors look one slot past the end
     PG_TRY(pg_scratch(ctx, &ctx->s_meta, (size_t)nmeta * 2 * sizeof(int4) + (size_t)grid * 128));
     int4 *d_meta = (int4 *)ctx->s_meta.p;
     k_mma_meta<<<(nmeta + 255) / 256, 256, 0, ctx->stream>>>(d_off, d_nwords, d_flags, d_order, (int)nreads_b, slot0, d_guess, md->d_blockmask,
