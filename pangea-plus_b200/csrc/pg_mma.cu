@@ -39,7 +39,14 @@
                                             // with setmaxnreg (64 / 160) it compiled without spills and did not come back from the
                                             // device (the 17th warp is a warpgroup of its own); the bounded barrier waits ended it
 #define PG_MMA_THREADS (PG_MMA_NEPI + 32 + PG_MMA_NPROD)
-#define PG_X8_SHIFT   2
+// units of the byte bounds: 2^shift / 128 nat, capped at 255 of them.  A larger shift reaches further (shift 2: 8 nat,
+// 3: 16 nat) and rounds more away per draw; PG_X8_SHIFT in the environment overrides the default for A/B runs.
+static int pg_x8_shift()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("PG_X8_SHIFT"); v = e ? atoi(e) : 2; if (v < 0 || v > 4) v = 2; }
+    return v;
+}
 #define PG_MMA_WLIST  512                   // open pairs per (read, epilogue warp) above which the read is "heavy"
 #define PG_MMA_RESERVE 128                  // entries of the global item list an epilogue warp reserves at a time
 
@@ -68,7 +75,7 @@ __global__ void k_qx(const uint16_t *__restrict__ q, int ntile64, uint8_t *__res
 
 // bm8x[w][pitch8]: one byte per block; hm8x[w][hpitch]: one byte per part (4 * block + part); padding = 255
 __global__ void k_x8(const uint16_t *__restrict__ bm, const uint16_t *__restrict__ hm, int ntile64, int pitch8, int hpitch,
-                     uint8_t *__restrict__ bm8x, uint8_t *__restrict__ hm8x)
+                     uint8_t *__restrict__ bm8x, uint8_t *__restrict__ hm8x, int shift)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int per = pitch8 + hpitch;
@@ -77,11 +84,11 @@ __global__ void k_x8(const uint16_t *__restrict__ bm, const uint16_t *__restrict
     if (w >= PG_NWORDS) return;
     uint32_t c = 255u;
     if (col < pitch8) {
-        if (col < ntile64) c = min((uint32_t)bm[((size_t)(col / PG_GB) * PG_NWORDS + w) * 32 + (col % PG_GB)] >> PG_X8_SHIFT, 255u);
+        if (col < ntile64) c = min((uint32_t)bm[((size_t)(col / PG_GB) * PG_NWORDS + w) * 32 + (col % PG_GB)] >> shift, 255u);
         bm8x[w * (size_t)pitch8 + col] = (uint8_t)c;
     } else {
         const int pb = col - pitch8;
-        if (pb < PG_PARTS * ntile64) c = min((uint32_t)hm[((size_t)(pb >> 5) * PG_NWORDS + w) * 32 + (pb & 31)] >> PG_X8_SHIFT, 255u);
+        if (pb < PG_PARTS * ntile64) c = min((uint32_t)hm[((size_t)(pb >> 5) * PG_NWORDS + w) * 32 + (pb & 31)] >> shift, 255u);
         hm8x[w * (size_t)hpitch + pb] = (uint8_t)c;
     }
 }
@@ -113,7 +120,7 @@ int pg_mma_build_tables(pg_model *md)
     PG_LAUNCHED(ctx);
     const size_t cells = (size_t)PG_NWORDS * (pitch8 + hpitch);
     k_x8<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(md->d_bmtable, md->d_hmtable, md->ntile64, pitch8, hpitch, md->d_bm8x,
-                                                                  md->d_hm8x);
+                                                                  md->d_hm8x, pg_x8_shift());
     PG_LAUNCHED(ctx);
     md->x8_blocks = md->ntile64;
     return PG_OK;
@@ -238,6 +245,7 @@ struct PgMmaArgs {
     const uint8_t *qx, *bm8x, *hm8x, *images;
     int pitch8, hpitch, ntile64, kmax;               // kmax: words of the longest read of the launch, rounded up to 32
     unsigned nstage;                                 // ring depth of this launch
+    int shift;                                       // log2 of the byte bounds' unit (pg_x8_shift)
     const uint16_t *words;
     const int64_t *off;
     const int32_t *nwords;
@@ -592,7 +600,7 @@ k_mma_bound(const __grid_constant__ PgMmaArgs a)
             }
             // ---- bound columns: 4 * D <= the smallest genus sum of the block.  Open pairs of up to three chunks at a time:
             // bit i of m[j] = column i of chunk cc + j is within the threshold and names a competitor
-            const uint32_t thr8 = thr >> PG_X8_SHIFT;
+            const uint32_t thr8 = thr >> a.shift;
             auto mask16 = [&](const uint32_t (&v)[16], int cc) -> uint32_t {
                 // nearly every chunk has no column within the threshold (~1 % of the (task, chunk) pairs do): one
                 // minimum and one compare settle those
@@ -730,6 +738,7 @@ int pg_mma_launch(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, 
     a.qx = md->d_qx; a.bm8x = md->d_bm8x; a.hm8x = md->d_hm8x; a.images = ctx->d_cnt_img;
     a.pitch8 = md->pitch8; a.hpitch = md->hpitch; a.ntile64 = md->ntile64;
     a.kmax = (nmax + 31) & ~31;
+    a.shift = pg_x8_shift();
     a.words = d_words; a.off = d_off; a.nwords = d_nwords; a.flags = d_flags; a.order = d_order;
     a.nreads_b = (int)nreads_b; a.slot0 = slot0; a.min_boot = min_boot; a.blockmask = md->d_blockmask; a.vmax = md->vmax;
     a.champ = cb.champ; a.ncand = cb.ncand; a.cand = cb.cand; a.guess = d_guess;
