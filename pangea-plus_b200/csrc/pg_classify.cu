@@ -396,10 +396,11 @@ struct ClassifyJob {
         ctx->st_mma = 0;
         // Chunk of reads per pass.  Plan 1 walks every genus block of a chunk (tile-major grid) and wants the
         // chunk's word ids, champion slots and near-tie lists L2-resident across those passes (2^14 measured
-        // best); plan 2 touches a read's data once per kernel and prefers fewer, larger launches (2^16).
+        // best); plan 2 touches a read's data once per kernel and prefers fewer, larger launches (2^16); plan 4's
+        // persistent kernel has a ramp and a tail per launch (2^16 / 2^17 / 2^18: 26.3 / 27.5 / 28.3 M reads/s).
         static int64_t chunk_override = -1;
         if (chunk_override < 0) { const char *e = getenv("PG_CHUNK_LOG2"); chunk_override = e ? atoi(e) : 0; }
-        CHUNK = !certified ? ((int64_t)1 << 20) : ((int64_t)1 << (chunk_override ? chunk_override : (cert_version == 1 ? 14 : 16)));
+        CHUNK = !certified ? ((int64_t)1 << 20) : ((int64_t)1 << (chunk_override ? chunk_override : (cert_version == 1 ? 14 : (cert_version == 4 ? 18 : 16))));
         cmax = count < CHUNK ? count : CHUNK;
         if (cmax < 1) cmax = 1;
         PG_TRY(pg_pinned(ctx, (size_t)count * 16 + 128 + 2 * PG_HB * 4));
