@@ -107,9 +107,8 @@ int pg_mma_build_tables(pg_model *md)
     if (32 + pitch8 + 16 > 256) return PG_OK;            // more than 208 blocks: one instruction cannot hold the columns; plan 3
     const size_t qxb = (size_t)md->ntile64 * PG_PARTS * PG_NWORDS * 32;
     if (!md->d_qx) {
-        cudaError_t e;
-        if ((e = cudaMalloc(&md->d_qx, qxb)) != cudaSuccess || (e = cudaMalloc(&md->d_bm8x, (size_t)PG_NWORDS * pitch8)) != cudaSuccess ||
-            (e = cudaMalloc(&md->d_hm8x, (size_t)PG_NWORDS * hpitch)) != cudaSuccess) {
+        if (cudaMalloc(&md->d_qx, qxb) != cudaSuccess || cudaMalloc(&md->d_bm8x, (size_t)PG_NWORDS * pitch8) != cudaSuccess ||
+            cudaMalloc(&md->d_hm8x, (size_t)PG_NWORDS * hpitch) != cudaSuccess) {
             (void)cudaGetLastError();
             cudaFree(md->d_qx); cudaFree(md->d_bm8x); cudaFree(md->d_hm8x);
             md->d_qx = md->d_bm8x = md->d_hm8x = NULL;
@@ -167,7 +166,12 @@ int pg_mma_ensure_images(pg_ctx *ctx, const std::vector<int> &need_n, int min_bo
     for (int n : need_n)
         if (n >= 1 && n <= PG_MMA_MAXN && !ctx->cnt_built[(size_t)n]) { ns.push_back(n); ctx->cnt_built[(size_t)n] = 1; }
     if (ns.empty()) return PG_OK;
-    if (!ctx->d_cnt_img) PG_CUDA(ctx, cudaMalloc(&ctx->d_cnt_img, (size_t)(PG_MMA_MAXN + 1) * PG_MMA_IMG));
+    if (!ctx->d_cnt_img && cudaMalloc(&ctx->d_cnt_img, (size_t)(PG_MMA_MAXN + 1) * PG_MMA_IMG) != cudaSuccess) {
+        (void)cudaGetLastError();                        // no room for the images: pg_mma_usable() says no, plan 3 runs
+        ctx->d_cnt_img = NULL;
+        ctx->cnt_built.clear();
+        return PG_OK;
+    }
     int32_t *d_ns = NULL;
     PG_CUDA(ctx, pg_dev_alloc(ctx, (void **)&d_ns, ns.size() * 4));
     PG_CUDA(ctx, cudaMemcpyAsync(d_ns, ns.data(), ns.size() * 4, cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before return
@@ -247,19 +251,12 @@ struct PgMmaArgs {
     unsigned nstage;                                 // ring depth of this launch
     int shift;                                       // log2 of the byte bounds' unit (pg_x8_shift)
     const uint16_t *words;
-    const int64_t *off;
-    const int32_t *nwords;
-    const uint8_t *flags;
-    const int32_t *order;
     int nreads_b;
     int64_t slot0;
     int min_boot;
-    const unsigned long long *blockmask;
-    double vmax;
     unsigned long long *champ;
     unsigned int *ncand;
     unsigned long long *cand;
-    const int32_t *guess;
     unsigned long long *items;
     unsigned int *item_count, *items_total;        // list cursor (reservations incl. blanks); pairs written, for the statistics
     unsigned int item_cap;
@@ -739,9 +736,9 @@ int pg_mma_launch(pg_ctx *ctx, const pg_model *md, unsigned nreads_b, int nmax, 
     a.pitch8 = md->pitch8; a.hpitch = md->hpitch; a.ntile64 = md->ntile64;
     a.kmax = (nmax + 31) & ~31;
     a.shift = pg_x8_shift();
-    a.words = d_words; a.off = d_off; a.nwords = d_nwords; a.flags = d_flags; a.order = d_order;
-    a.nreads_b = (int)nreads_b; a.slot0 = slot0; a.min_boot = min_boot; a.blockmask = md->d_blockmask; a.vmax = md->vmax;
-    a.champ = cb.champ; a.ncand = cb.ncand; a.cand = cb.cand; a.guess = d_guess;
+    a.words = d_words;                                   // (read offsets, lengths, flags, order, guesses, margins: per slot, k_mma_meta)
+    a.nreads_b = (int)nreads_b; a.slot0 = slot0; a.min_boot = min_boot;
+    a.champ = cb.champ; a.ncand = cb.ncand; a.cand = cb.cand;
     a.items = cb.items; a.item_count = cb.item_count; a.items_total = cb.counters + 3; a.item_cap = cb.item_cap; a.heavy = cb.heavy; a.light_max = light_max;
     const int nch = 3 + md->pitch8 / 16;
     PG_CUDA(ctx, pg_smem_unlock(ctx, k_mma_bound));
