@@ -223,3 +223,27 @@ def test_min_boot_words_parameter(toy):
     data, off = pack_sequences([seqs[0][:50]])                         # 43 words -> k = 5 either way
     c = model.classify(data, off, 8)                                   # k forced to 8: another stream
     assert c["n_words"][0] == 43
+
+
+@pytest.mark.parametrize("n,min_boot", [(486, 0), (243, 0), (37, 5), (9, 5), (640, 0)])
+def test_bootstrap_is_a_count_matrix_product(n, min_boot):
+    """What the tensor-core kernel (csrc/pg_mma.cu) rests on, checked on the CPU with the oracle's java.util.Random:
+    every read re-seeds the generator with 1, so replicate t of a read with n words draws the same word POSITIONS in
+    every read, and the 100 replicate sums of any integer column x are the product C_n x with C_n[t][j] = how often
+    replicate t draws position j.  Split into two byte columns the product stays exact: 256 * (C hi) + (C lo)."""
+    k = max(n // 8, min_boot)
+    draws = ora.jrandom_stream(1, n, 100 * k).reshape(100, k)            # the oracle's stream: replicate by replicate
+    C = np.zeros((101, n), np.int64)
+    C[0] = 1                                                             # task 0: the full sum
+    for t in range(100):
+        np.add.at(C[1 + t], draws[t], 1)
+    assert C[1:].sum(axis=1).tolist() == [k] * 100 and C.max() <= 255    # counts fit the u8 operand
+    rng = np.random.default_rng(n)
+    q = rng.integers(0, 4096, (n, 7))                                    # 12-bit deficits of 7 table positions
+    by_draw = np.stack([q.sum(axis=0)] + [q[draws[t]].sum(axis=0) for t in range(100)])
+    assert np.array_equal(C @ q, by_draw)
+    lo, hi = q & 255, q >> 8
+    assert np.array_equal(256 * (C @ hi) + (C @ lo), by_draw)
+    # the byte bounds: rounded down and capped, four times their sum never exceeds the sum of the 16-bit minima
+    b8 = np.minimum(q >> 2, 255)
+    assert np.all(4 * (C @ b8) <= by_draw)
